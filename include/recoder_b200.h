@@ -1,0 +1,205 @@
+/* recoder_b200 — C ABI of the B200-native Recoder training hot path.
+ *
+ * The reference (amoussawi/recoder @ a9ed3e8) has no FFI of its own: its extension points are Python classes
+ * (SURVEY.md §8b).  This header is the boundary a maintainer binds underneath those classes (ctypes stub in
+ * INTEGRATION.md).  Every entry point cites the reference code it replaces (paths relative to the reference
+ * root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - every function is asynchronous and ordered on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 = ok, negative = error (RCD_ERR_*); `rcd_last_error()` gives the message of the last
+ *     failure on the calling thread; nothing throws, nothing allocates caller-visible memory;
+ *   - scratch memory is provided by the caller (`*_scratch_bytes` helpers give the size);
+ *   - row-major everywhere; "ld" arguments are leading dimensions in ELEMENTS;
+ *   - bf16 operands are `uint16_t` bit patterns (same layout as __nv_bfloat16 / torch.bfloat16).
+ */
+#ifndef RECODER_B200_H_
+#define RECODER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCD_ABI_VERSION 1
+
+#define RCD_OK 0
+#define RCD_ERR_INVALID (-1) /* bad argument */
+#define RCD_ERR_CUDA (-2)    /* CUDA runtime / driver error */
+#define RCD_ERR_UNSUPPORTED (-3)
+
+/* activation ids — recoder/nn.py:6-9 `activation(x, act)` */
+#define RCD_ACT_NONE 0
+#define RCD_ACT_TANH 1
+#define RCD_ACT_SIGMOID 2
+#define RCD_ACT_RELU 3
+
+/* loss ids — recoder/model.py:87-99 `__init_loss_module` */
+#define RCD_LOSS_MSE 0      /* recoder/losses.py:16-47  MSELoss(confidence, 'sum') */
+#define RCD_LOSS_NLL 1      /* recoder/losses.py:50-71  MultinomialNLLLoss('sum') ('logloss') */
+#define RCD_LOSS_LOGISTIC 2 /* torch BCEWithLogitsLoss('sum') ('logistic'), recoder/model.py:90-91 */
+
+/* GEMM engines: the tcgen05/TMA kernels are the product; the SIMT engine is a slow reference of the same
+ * math (same bf16 operands, fp32 accumulation) used by the tests to localise faults. */
+#define RCD_GEMM_TCGEN05 0
+#define RCD_GEMM_SIMT 1
+
+int rcd_abi_version(void);
+const char* rcd_last_error(void);
+/* number of SMs of the current device (148 on B200); <0 on error */
+int rcd_device_sms(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K1  collate — replaces RecommendationDataset.__getitem__/_extract (recoder/data.py:50-83) and
+ *     BatchCollator.collate (recoder/data.py:203-251) plus the COO->dense scatter at recoder/model.py:457-462.
+ *
+ * Inputs : dataset CSR (indptr int64[U+1], indices int32[], data fp32[]), the pool's user ids (int64[P]).
+ * Outputs: row_ptr int32[P+1] (exclusive scan of the pool rows' nnz), raw_items int32[nnz] (global item id),
+ *          cols int32[nnz] (position of the item in `items`, or the raw id without negative sampling),
+ *          vals fp32[nnz] (stored CSR order inside each row — data.py:236-242),
+ *          row_inv_norm fp32[P] = 1/max(||x_u||_2, 1e-12)  (F.normalize, recoder/nn.py:235),
+ *          row_sum fp32[P] = sum_j x_uj (needed by the multinomial NLL gradient),
+ *          pos int32[num_items] (item -> column or -1), items int64[>=n] sorted ascending unique
+ *          (np.unique, data.py:220), counts int32[2] = {n, nnz}.
+ * `nnz_capacity` is the capacity of raw_items/cols/vals; the pool's nnz must not exceed it.
+ * ------------------------------------------------------------------------------------------------------- */
+size_t rcd_collate_scratch_bytes(int pool_rows, int num_items);
+int rcd_collate(const int64_t* indptr, const int32_t* indices, const float* data, const int64_t* users,
+                int pool_rows, int num_items, int negative_sampling, int nnz_capacity, int32_t* row_ptr,
+                int32_t* raw_items, int32_t* cols, float* vals, float* row_inv_norm, float* row_sum, int32_t* pos,
+                int64_t* items, int32_t* counts, void* scratch, size_t scratch_bytes, void* stream);
+
+/* Batch.indices of one slice (recoder/data.py:244): indices int64[2, nnz_slice], rows relative to row0. */
+int rcd_collate_coo(const int32_t* row_ptr, const int32_t* cols, int row0, int rows, int64_t* indices_out,
+                    void* stream);
+
+/* Column-major view (CSC) of one slice of the pool, used by the encoder weight gradient and by the
+ * loss kernel: csc_ptr int32[n+1], csc_row int32[nnz_slice] (row relative to row0, ascending inside a column),
+ * csc_val fp32[nnz_slice] (raw interaction value). */
+size_t rcd_slice_csc_scratch_bytes(int n, int nnz_slice);
+int rcd_slice_csc(const int32_t* row_ptr, const int32_t* cols, const float* vals, int row0, int rows, int n,
+                  int32_t* csc_ptr, int32_t* csc_row, float* csc_val, void* scratch, size_t scratch_bytes,
+                  void* stream);
+
+/* dense [rows, n] fp32 input (the `input` argument of FactorizationModel.forward, recoder/nn.py:49-65)
+ * -> CSR of its non-zeros (row_ptr int32[rows+1], cols, vals, row_inv_norm, row_sum). */
+size_t rcd_dense_to_csr_scratch_bytes(int rows);
+int rcd_dense_to_csr(const float* dense, int rows, int n, int ld, int nnz_capacity, int32_t* row_ptr,
+                     int32_t* cols, float* vals, float* row_inv_norm, float* row_sum, int32_t* nnz_out,
+                     void* scratch, size_t scratch_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K2  embedding gather — replaces nn.Embedding lookups / index_select in LinearEmbedding.forward
+ *     (recoder/nn.py:271-272) and MatrixFactorization.forward (recoder/nn.py:348,358-359).
+ *     out_bf16[r, 0:H] = bf16(act(table[ids[r], :])), zero padded to ld_out; optional fp32 copy.
+ *     ids == NULL means the identity (full table, `items is None`, nn.py:273-275).
+ * ------------------------------------------------------------------------------------------------------- */
+int rcd_gather_rows(const float* table, int H, const int64_t* ids, int n, int act, uint16_t* out_bf16,
+                    int ld_out, float* out_f32, void* stream);
+int rcd_gather_vec(const float* vec, const int64_t* ids, int n, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K3  autoencoder encoder forward — replaces F.normalize + LinearEmbedding(en) + activation
+ *     (recoder/nn.py:235-240, 269-278) and the dense materialisation of the input (recoder/model.py:457-458).
+ *     Z[r,:] = act( keep_scale * row_inv_norm[r] * sum_p vals[p] * We[raw_items[p], :] + be )
+ *     for the slice rows [row0, row0+rows).  Sparse formulation: 2*nnz*H executed flops, fp32 exact.
+ *     Writes Z fp32 [rows, H] and a bf16 copy [rows, ldzb] (zero padded) that feeds the decoder GEMM.
+ * ------------------------------------------------------------------------------------------------------- */
+int rcd_ae_encoder_fwd(const float* We, int H, const float* be, const int32_t* row_ptr, const int32_t* raw_items,
+                       const float* vals, const float* row_inv_norm, int row0, int rows, int act, float* Z,
+                       uint16_t* Zb, int ldzb, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K4  decoder forward GEMM — replaces LinearEmbedding(de).forward `F.linear(z, W_d[items], b_d[items])`
+ *     (recoder/nn.py:280; MF: recoder/nn.py:361).
+ *     O[r, c] = sum_h Zb[r,h] * Wg[c,h] + bias[c]   (bf16 operands, fp32 accumulate in TMEM)
+ *     stored as bf16 [rows, ldo]; when stat_max/stat_sum are non-NULL also per-(n-tile,row) online-softmax
+ *     partials (max, sum exp) laid out [n_tiles, rows] for the multinomial NLL.
+ *     `out_f32` (optional) stores O in fp32 [rows, ldo] instead of bf16 (inference / tests).
+ * ------------------------------------------------------------------------------------------------------- */
+int rcd_decoder_tile_n(void); /* n-tile width the stats are laid out for (256) */
+int rcd_decoder_fwd(const uint16_t* Zb, int ldzb, const uint16_t* Wg, int ldw, const float* bias, int rows, int n,
+                    int H, uint16_t* O_bf16, float* out_f32, int ldo, float* stat_max, float* stat_sum, int engine,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K5  loss + dL/dlogits — replaces MSELoss.forward (recoder/losses.py:43-47), MultinomialNLLLoss.forward
+ *     (recoder/losses.py:68-71), BCEWithLogitsLoss('sum') (recoder/model.py:91), the `/ B` normalisation
+ *     (recoder/model.py:483-484) and autograd's backward through them.
+ *     rcd_softmax_lse : lse[r] = logsumexp_c O[r,c] from the K4 partials (NLL only); adds sum_r lse[r]*row_sum[r]
+ *                       * inv_b to loss_acc.
+ *     rcd_loss_grad   : dO[r,c] (bf16) from O (bf16) and the sparse target given as the slice CSC,
+ *                       db[c] = sum_r dO[r,c] (fp32, deterministic), loss_acc[0] += loss/B (double).
+ *        MSE      dO = 2*(1+conf*[t>0])*(o-t)*inv_b
+ *        NLL      dO = (exp(o-lse_r)*row_sum_r - t)*inv_b
+ *        LOGISTIC dO = (sigmoid(o)-t)*inv_b
+ * ------------------------------------------------------------------------------------------------------- */
+int rcd_softmax_lse(const float* stat_max, const float* stat_sum, int n_tiles, int rows, const float* row_sum,
+                    float inv_b, float* lse, double* loss_acc, void* stream);
+int rcd_loss_grad(const uint16_t* O_bf16, int ldo, int rows, int n, int loss, float confidence, float inv_b,
+                  const float* lse, const float* row_sum, const int32_t* csc_ptr, const int32_t* csc_row,
+                  const float* csc_val, uint16_t* dO, int lddo, float* db, double* loss_acc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K6  decoder backward GEMMs — replace autograd's `mm` nodes of F.linear.
+ *     rcd_decoder_dgrad : dZ[r,h]  = sum_c dO[r,c] * Wg[c,h]     (K = n, split-K; partials fp32
+ *                         [splits, rows, ldp]); the caller reduces them with rcd_dz_act.
+ *     rcd_decoder_wgrad : dW[c,h]  = sum_r dO[r,c] * Zb[r,h]     (K = rows) -> fp32 [n, H] compact row grads
+ * ------------------------------------------------------------------------------------------------------- */
+int rcd_decoder_dgrad_splits(int rows, int n, int H);
+int rcd_decoder_dgrad(const uint16_t* dO, int lddo, const uint16_t* Wg, int ldw, int rows, int n, int H,
+                      int splits, float* partials, int ldp, int engine, void* stream);
+int rcd_decoder_wgrad(const uint16_t* dO, int lddo, const uint16_t* Zb, int ldzb, int rows, int n, int H,
+                      float* dW, int lddw, int engine, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K7  encoder backward — replaces tanh_backward + the `mm`/`sum` nodes of the encoder F.linear and
+ *     embedding_dense_backward.
+ *     rcd_dz_act        : dA = (sum_s partials[s]) * act'(Z)  -> fp32 [rows, H]; db_e[h] = sum_r dA[r,h]
+ *     rcd_ae_encoder_wgrad : dWe_rows[c,:] = sum_{(r,x) in column c} x * row_inv_norm[row0+r] * dA[r,:]
+ * ------------------------------------------------------------------------------------------------------- */
+int rcd_dz_act(const float* partials, int splits, int ldp, const float* Z, int rows, int H, int act, float* dA,
+               float* db, void* stream);
+int rcd_ae_encoder_wgrad(const float* dA, int H, const int32_t* csc_ptr, const int32_t* csc_row,
+                         const float* csc_val, const float* row_inv_norm, int row0, int n, float* dWe_rows,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K8  optimizers — replace torch.optim.{Adam,SGD,SparseAdam}.step as configured by
+ *     Recoder.__init_optimizer (recoder/model.py:101-164); per-parameter weight decay (0 for biases,
+ *     model.py:123-124).  Gradients arrive as compact row blocks: the gradient of table row i is
+ *     grad_rows[pos[i], :] when pos[i] >= 0 and exactly zero otherwise (pos == NULL: grad is dense [rows,H]).
+ *     Dense semantics: EVERY row of the table is updated (momentum and weight decay move untouched rows).
+ *     `t` is the 1-based step count of this parameter.
+ * ------------------------------------------------------------------------------------------------------- */
+int rcd_adam_step(float* p, float* m, float* v, long long rows, int H, const float* grad_rows, int ldg,
+                  const int32_t* pos, double lr, double beta1, double beta2, double eps, double weight_decay,
+                  long long t, void* stream);
+int rcd_sgd_step(float* p, float* buf, long long rows, int H, const float* grad_rows, int ldg, const int32_t* pos,
+                 double lr, double momentum, double weight_decay, void* stream);
+/* torch.optim.SparseAdam on the n rows `ids` (no weight decay; recoder/model.py:137-138) */
+int rcd_sparse_adam_step(float* p, float* m, float* v, int H, const float* grad_rows, int ldg, const int64_t* ids,
+                         int n, double lr, double beta1, double beta2, double eps, long long t, void* stream);
+/* pos[ids[r]] = r (or -1 to reset) — inverse map for row-indexed gradients (MF user table) */
+int rcd_scatter_pos(const int64_t* ids, int n, int32_t* pos, int reset, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Telemetry / tests: L2 norm squared of a strided fp32 matrix (double accumulation), out_sq[0] += ...
+ * ------------------------------------------------------------------------------------------------------- */
+int rcd_sumsq(const float* x, long long rows, int cols, int ld, double* out_sq, void* stream);
+
+/* Plain bf16 GEMM entry used by the kernel unit tests (and by the inner MLP layers):
+ *   mode 0: C[M,N] = A[M,K] * B[N,K]^T        (A, B K-major)
+ *   mode 1: C[M,N] = A[M,K] * B[K,N]          (B MN-major)
+ *   mode 2: C[M,N] = A[K,M]^T * B[K,N]        (A, B MN-major)
+ * C fp32 [M, ldc]. */
+int rcd_gemm_bf16(int mode, const uint16_t* A, int lda, const uint16_t* B, int ldb, int M, int N, int K, float* C,
+                  int ldc, int engine, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECODER_B200_H_ */

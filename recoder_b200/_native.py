@@ -1,0 +1,107 @@
+"""ctypes binding of librecoder_b200.so (the C ABI declared in include/recoder_b200.h).
+
+There is NO CPU fallback: if the library is missing or a call fails, a RuntimeError is raised.
+PyTorch tensors are only containers here — every call passes `tensor.data_ptr()`, sizes and the raw handle
+of the current CUDA stream.
+"""
+import ctypes
+import os
+from ctypes import c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'librecoder_b200.so')
+
+ACT_IDS = {'none': 0, 'tanh': 1, 'sigmoid': 2, 'relu': 3}
+LOSS_IDS = {'mse': 0, 'logloss': 1, 'logistic': 2}
+GEMM_TCGEN05, GEMM_SIMT = 0, 1
+
+_P = c_void_p
+# name -> (restype, argtypes); mirrors include/recoder_b200.h one to one
+_SIGNATURES = {
+  'rcd_abi_version': (c_int, []),
+  'rcd_last_error': (ctypes.c_char_p, []),
+  'rcd_device_sms': (c_int, []),
+  'rcd_collate_scratch_bytes': (c_size_t, [c_int, c_int]),
+  'rcd_collate': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                          c_size_t, _P]),
+  'rcd_collate_coo': (c_int, [_P, _P, c_int, c_int, _P, _P]),
+  'rcd_slice_csc_scratch_bytes': (c_size_t, [c_int, c_int]),
+  'rcd_slice_csc': (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
+  'rcd_dense_to_csr_scratch_bytes': (c_size_t, [c_int]),
+  'rcd_dense_to_csr': (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+  'rcd_gather_rows': (c_int, [_P, c_int, _P, c_int, c_int, _P, c_int, _P, _P]),
+  'rcd_gather_vec': (c_int, [_P, _P, c_int, _P, _P]),
+  'rcd_ae_encoder_fwd': (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, c_int, _P]),
+  'rcd_decoder_tile_n': (c_int, []),
+  'rcd_decoder_fwd': (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P]),
+  'rcd_softmax_lse': (c_int, [_P, _P, c_int, c_int, _P, c_float, _P, _P, _P]),
+  'rcd_loss_grad': (c_int, [_P, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P, c_int, _P, _P,
+                            _P]),
+  'rcd_decoder_dgrad_splits': (c_int, [c_int, c_int, c_int]),
+  'rcd_decoder_dgrad': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
+  'rcd_decoder_wgrad': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
+  'rcd_dz_act': (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P]),
+  'rcd_ae_encoder_wgrad': (c_int, [_P, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P]),
+  'rcd_adam_step': (c_int, [_P, _P, _P, c_longlong, c_int, _P, c_int, _P, c_double, c_double, c_double, c_double,
+                            c_double, c_longlong, _P]),
+  'rcd_sgd_step': (c_int, [_P, _P, c_longlong, c_int, _P, c_int, _P, c_double, c_double, c_double, _P]),
+  'rcd_sparse_adam_step': (c_int, [_P, _P, _P, c_int, _P, c_int, _P, c_int, c_double, c_double, c_double, c_double,
+                                   c_longlong, _P]),
+  'rcd_scatter_pos': (c_int, [_P, c_int, _P, c_int, _P]),
+  'rcd_sumsq': (c_int, [_P, c_longlong, c_int, c_int, _P, _P]),
+  'rcd_gemm_bf16': (c_int, [c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())
+
+_lib = None
+
+
+def load():
+  """Loads the shared library (no GPU needed to load it)."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.isfile(LIB_PATH):
+    raise RuntimeError('recoder_b200: CUDA extension %s is missing — build it with '
+                       '`python -m recoder_b200.csrc.build` (there is no CPU fallback)' % LIB_PATH)
+  lib = ctypes.CDLL(LIB_PATH)
+  for name, (res, args) in _SIGNATURES.items():
+    fn = getattr(lib, name)
+    fn.restype = res
+    fn.argtypes = args
+  if lib.rcd_abi_version() != 1:
+    raise RuntimeError('recoder_b200: ABI version mismatch')
+  _lib = lib
+  return lib
+
+
+def require_cuda():
+  if not torch.cuda.is_available():
+    raise RuntimeError('recoder_b200 needs a CUDA device (sm_100a); there is no CPU path')
+
+
+def ptr(t):
+  """Device pointer of a tensor (None -> NULL)."""
+  if t is None:
+    return None
+  return c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+  return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check(status, what):
+  if status != 0:
+    msg = load().rcd_last_error().decode('utf-8', 'replace')
+    raise RuntimeError('recoder_b200: %s failed (status %d): %s' % (what, status, msg))
+
+
+def call(name, *args):
+  """Calls an `int`-status entry point on the current stream (stream appended automatically)."""
+  lib = load()
+  status = getattr(lib, name)(*args, stream_ptr())
+  check(status, name)

@@ -1,0 +1,85 @@
+// Shared helpers for the recoder_b200 CUDA kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/recoder_b200.h"
+
+#define RCD_EXPORT extern "C" __attribute__((visibility("default")))
+
+// ---- error reporting: C ABI returns int status, message via rcd_last_error() -------------------
+void rcd_set_error(const char* fmt, ...);
+
+#define RCD_CHECK_ARG(cond, msg)                                   \
+  do {                                                             \
+    if (!(cond)) {                                                 \
+      rcd_set_error("%s: invalid argument: %s", __func__, msg);    \
+      return RCD_ERR_INVALID;                                      \
+    }                                                              \
+  } while (0)
+
+#define RCD_CUDA(expr)                                                               \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      rcd_set_error("%s: %s failed: %s", __func__, #expr, cudaGetErrorString(_e));   \
+      return RCD_ERR_CUDA;                                                           \
+    }                                                                                \
+  } while (0)
+
+#define RCD_LAUNCH_CHECK() RCD_CUDA(cudaGetLastError())
+
+static inline int rcd_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+int rcd_num_sms();
+
+// ---- device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Activation ids shared by host and device (recoder/nn.py:6-9 allows any torch.<name>; these are the ones
+// the reference's scripts, docs and tests use).
+__device__ __forceinline__ float act_apply(float x, int act) {
+  switch (act) {
+    case RCD_ACT_TANH: return tanhf(x);
+    case RCD_ACT_SIGMOID: return 1.0f / (1.0f + expf(-x));
+    case RCD_ACT_RELU: return fmaxf(x, 0.0f);
+    default: return x;
+  }
+}
+// derivative expressed through the OUTPUT y = act(x)
+__device__ __forceinline__ float act_grad_from_out(float y, int act) {
+  switch (act) {
+    case RCD_ACT_TANH: return 1.0f - y * y;
+    case RCD_ACT_SIGMOID: return y * (1.0f - y);
+    case RCD_ACT_RELU: return y > 0.0f ? 1.0f : 0.0f;
+    default: return 1.0f;
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }

@@ -1,0 +1,353 @@
+// tcgen05 / TMEM / TMA GEMM engine for sm_100a (bf16 x bf16 -> fp32), hand-written PTX.
+//
+// One persistent CTA per SM, 192 threads, warp-specialised:
+//   warp 0 (one lane)  TMA producer : cp.async.bulk.tensor 2D boxes (128B swizzle) -> 4-stage smem ring
+//   warp 1 (one lane)  MMA issuer   : tcgen05.mma.cta_group::1.kind::f16, M=128, N=bn<=256, K=16 per instruction;
+//                                      accumulators double-buffered in TMEM (2 x 256 columns); also owns
+//                                      tcgen05.alloc/dealloc
+//   warps 2-5          epilogue     : tcgen05.ld 32x32b (TMEM lane == output row) -> row epilogue -> global
+// Three mbarrier pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue).
+//
+// Operand layouts (smem, 128B swizzle, one 64-wide K block per stage):
+//   K-major  operand X[rows, K]  : one TMA box {64 k, rows}; UMMA desc SBO = 1024 B (8 rows x 128 B),
+//                                  K step of 16 elements = +32 B on the start address
+//   MN-major operand Y[K, cols]  : boxes {64 cols, 64 k} of 8 KB each; UMMA desc LBO = 8192 B (next 64 columns),
+//                                  SBO = 1024 B (next 8 k), K step of 16 = +2048 B
+// Out-of-range parts of a box are zero-filled by TMA, so ragged M/N/K need no special casing before the
+// epilogue, which masks rows >= M and columns >= N.
+#include <cuda.h>
+
+#include "gemm_internal.cuh"
+
+namespace rcd {
+
+constexpr int kStages = 4;
+constexpr int kAStageBytes = kTileM * kTileK * 2;     // 16 KB
+constexpr int kBStageBytes = kTileNMax * kTileK * 2;  // 32 KB
+constexpr int kStageBytes = kAStageBytes + kBStageBytes;
+constexpr int kBarrierBytes = 256;
+constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;  // + slack for 1024 B alignment
+constexpr int kGemmThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr int kBoxBytes = 64 * 64 * 2;  // MN-major box
+constexpr long long kTimeoutCycles = 4000000000LL;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug must surface as a CUDA error, never as a hung GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kTimeoutCycles) {
+      printf("recoder_b200 gemm_tc: mbarrier wait timed out (block %d thread %d tag %d parity %u)\n", blockIdx.x,
+             threadIdx.x, tag, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
+// | layout type [61,64) (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+static __global__ void __launch_bounds__(kGemmThreads, 1)
+    k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmProblem g,
+              EpiParams e, int m_tiles, int n_tiles, int kblocks, uint32_t idesc, int b_boxes,
+              uint32_t stage_tx_bytes) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t tiles = (raw_addr + 1023u) & ~1023u;  // 128B-swizzle atoms need 1024 B alignment
+  uint8_t* smem = smem_raw + (tiles - raw_addr);
+  const uint32_t bars = tiles + kStages * kStageBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * kStages + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kStages * kStageBytes + 8 * (2 * kStages + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int units = m_tiles * n_tiles * g.splits;
+  const bool a_mn = (g.mode == 2), b_mn = (g.mode != 0);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      uint32_t stage = 0, phase = 0;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        const UnitCoord u = decode_unit(unit, m_tiles, n_tiles, g.splits, kblocks, g.n_fastest);
+        const int m0 = u.mt * kTileM, n0 = u.nt * g.bn;
+        for (int kb = u.kb0; kb < u.kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, 0);
+          mbar_arrive_expect_tx(full_bar(stage), stage_tx_bytes);
+          const uint32_t a_dst = tiles + stage * kStageBytes, b_dst = a_dst + kAStageBytes;
+          const int k = kb * kTileK;
+          if (a_mn) {
+            tma_load_2d(a_dst, &tmA, full_bar(stage), m0, k);
+            tma_load_2d(a_dst + kBoxBytes, &tmA, full_bar(stage), m0 + 64, k);
+          } else {
+            tma_load_2d(a_dst, &tmA, full_bar(stage), k, m0);
+          }
+          if (b_mn) {
+            for (int j = 0; j < b_boxes; ++j) tma_load_2d(b_dst + j * kBoxBytes, &tmB, full_bar(stage), n0 + 64 * j, k);
+          } else {
+            tma_load_2d(b_dst, &tmB, full_bar(stage), k, n0);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+        const UnitCoord u = decode_unit(unit, m_tiles, n_tiles, g.splits, kblocks, g.n_fastest);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kTileNMax);
+        for (int kb = u.kb0; kb < u.kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase, 2);
+          tc_fence_after();
+          const uint32_t a_addr = tiles + stage * kStageBytes, b_addr = a_addr + kAStageBytes;
+#pragma unroll
+          for (int k = 0; k < kTileK / 16; ++k) {
+            const uint64_t adesc = a_mn ? make_smem_desc(a_addr + k * 2048, kBoxBytes, 1024)
+                                        : make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = b_mn ? make_smem_desc(b_addr + k * 2048, kBoxBytes, 1024)
+                                        : make_smem_desc(b_addr + k * 32, 16, 1024);
+            tc_mma_bf16(tmem_d, adesc, bdesc, idesc, (kb > u.kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit(tfull_bar(acc));  // accumulator complete
+      }
+    }
+  } else {
+    // ---------------- epilogue warps (2..5): TMEM lane quarter = warp % 4 ----------------
+    const int q = warp & 3;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+      const UnitCoord u = decode_unit(unit, m_tiles, n_tiles, g.splits, kblocks, g.n_fastest);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), acc_phase, 3);
+      tc_fence_after();
+      const int row = u.mt * kTileM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTileNMax);
+      RowEpilogue epi;
+      epi.begin();
+      for (int cb = 0; cb < g.bn; cb += 32) {
+        float v[32];
+        tc_ld_32x32(taddr + (uint32_t)cb, v);
+        epi.chunk32(e, row, u.nt * g.bn + cb, u.split, v);
+      }
+      epi.end(e, row, u.nt);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess || !p)
+    return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+// 2D bf16 tensor [outer, inner] row-major with leading dimension ld (elements), box {box_inner, box_outer}
+static int encode_map(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld,
+                      int box_inner, int box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    rcd_set_error("gemm_tc: cuTensorMapEncodeTiled not available from the driver");
+    return RCD_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0) {
+    rcd_set_error("gemm_tc: operand base must be 16-byte aligned and ld a multiple of 8 elements (ld=%lld)", ld);
+    return RCD_ERR_INVALID;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    rcd_set_error("gemm_tc: cuTensorMapEncodeTiled failed (CUresult %d; inner=%lld outer=%lld ld=%lld box=%dx%d)",
+                  (int)r, inner, outer, ld, box_inner, box_outer);
+    return RCD_ERR_CUDA;
+  }
+  return RCD_OK;
+}
+
+int gemm_tc_launch(const GemmProblem& g, const EpiParams& e, cudaStream_t st) {
+  if (g.bn % 16 != 0 || g.bn < 16 || g.bn > kTileNMax) {
+    rcd_set_error("gemm_tc: bad n-tile %d", g.bn);
+    return RCD_ERR_INVALID;
+  }
+  const int m_tiles = rcd_div_up(g.M, kTileM), n_tiles = rcd_div_up(g.N, g.bn);
+  const int kblocks = rcd_div_up(g.K, kTileK);
+  if (n_tiles > 1 && g.bn % 32 != 0) {
+    rcd_set_error("gemm_tc: n-tile %d must be a multiple of 32 when N spans several tiles", g.bn);
+    return RCD_ERR_INVALID;
+  }
+  if (g.splits < 1 || (long long)(g.splits - 1) * rcd_div_up(kblocks, g.splits) >= kblocks) {
+    rcd_set_error("gemm_tc: %d k-splits over %d k-blocks leaves an empty split", g.splits, kblocks);
+    return RCD_ERR_INVALID;
+  }
+  CUtensorMap tmA, tmB;
+  int rc;
+  const bool a_mn = (g.mode == 2), b_mn = (g.mode != 0);
+  if (a_mn) rc = encode_map(&tmA, g.A, g.M, g.K, g.lda, 64, 64);
+  else rc = encode_map(&tmA, g.A, g.K, g.M, g.lda, kTileK, kTileM);
+  if (rc != RCD_OK) return rc;
+  if (b_mn) rc = encode_map(&tmB, g.B, g.N, g.K, g.ldb, 64, 64);
+  else rc = encode_map(&tmB, g.B, g.K, g.N, g.ldb, kTileK, kTileNMax);
+  if (rc != RCD_OK) return rc;
+  const int b_boxes = rcd_div_up(g.bn, 64);
+  const uint32_t tx = (uint32_t)kAStageBytes + (b_mn ? (uint32_t)(b_boxes * kBoxBytes) : (uint32_t)kBStageBytes);
+  // instruction descriptor: D=f32 [4,6)=1 | A=bf16 [7,10)=1 | B=bf16 [10,13)=1 | a_major [15] | b_major [16] |
+  // N>>3 [17,23) | M>>4 [24,29)
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+                         ((uint32_t)(g.bn >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RCD_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  const int units = m_tiles * n_tiles * g.splits;
+  const int sms = rcd_num_sms();
+  const int grid = units < sms ? units : sms;
+  k_gemm_tc<<<grid, kGemmThreads, kSmemBytes, st>>>(tmA, tmB, g, e, m_tiles, n_tiles, kblocks, idesc, b_boxes, tx);
+  RCD_LAUNCH_CHECK();
+  return RCD_OK;
+}
+
+}  // namespace rcd

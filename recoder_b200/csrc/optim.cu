@@ -1,0 +1,184 @@
+// K8: fused optimizer steps (HBM-bound streaming kernels; 24 B/param for Adam: read+write of p, m, v).
+// Arithmetic follows torch.optim's single-tensor kernels as configured by Recoder.__init_optimizer
+// (recoder/model.py:101-164): Adam(lr, betas=(0.9,0.999), eps=1e-8, L2 weight decay added to the gradient),
+// SGD(momentum=0.9, dampening=0), SparseAdam (touched rows only, no weight decay).
+// Gradients arrive compact: row i of the table has gradient grad_rows[pos[i]] if pos[i] >= 0 else 0, so the
+// scatter of embedding_dense_backward is folded into the optimizer read.
+#include "common.cuh"
+
+namespace rcd {
+
+struct AdamScalars {
+  float beta2, eps, wd;
+  float omb1, omb2;       // 1 - beta1, 1 - beta2 (formed in double on the host, like torch's Python scalars)
+  float step_size;        // lr / (1 - beta1^t)
+  float inv_bc2_sqrt;     // 1 / sqrt(1 - beta2^t)
+};
+
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, const AdamScalars& a) {
+  g = fmaf(a.wd, p, g);                                  // grad.add(param, alpha=weight_decay)
+  m = fmaf(a.omb1, g - m, m);                            // exp_avg.lerp_(grad, 1 - beta1)
+  v = fmaf(a.omb2, g * g, a.beta2 * v);                  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  const float denom = sqrtf(v) * a.inv_bc2_sqrt + a.eps; // (sqrt(v) / sqrt(bc2)).add_(eps)
+  p = p - a.step_size * (m / denom);                     // param.addcdiv_(exp_avg, denom, value=-step_size)
+}
+
+// VEC = 4: one thread per float4; requires H % 4 == 0 and 16-byte aligned pointers.
+template <int VEC>
+static __global__ void __launch_bounds__(256)
+    k_adam(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, long long rows, int H,
+           const float* __restrict__ grad_rows, int ldg, const int32_t* __restrict__ pos, AdamScalars a) {
+  const int vpr = H / VEC;
+  const long long total = rows * vpr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vpr;
+    const int h = (int)(i % vpr) * VEC;
+    long long gr = pos ? (long long)pos[r] : r;
+    const size_t off = (size_t)r * H + h;
+    if (VEC == 4) {
+      float4 pp = *reinterpret_cast<float4*>(p + off);
+      float4 mm = *reinterpret_cast<float4*>(m + off);
+      float4 vv = *reinterpret_cast<float4*>(v + off);
+      float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gr >= 0 && grad_rows) gg = __ldg(reinterpret_cast<const float4*>(grad_rows + (size_t)gr * ldg + h));
+      adam_update(pp.x, mm.x, vv.x, gg.x, a);
+      adam_update(pp.y, mm.y, vv.y, gg.y, a);
+      adam_update(pp.z, mm.z, vv.z, gg.z, a);
+      adam_update(pp.w, mm.w, vv.w, gg.w, a);
+      *reinterpret_cast<float4*>(p + off) = pp;
+      *reinterpret_cast<float4*>(m + off) = mm;
+      *reinterpret_cast<float4*>(v + off) = vv;
+    } else {
+      float pp = p[off], mm = m[off], vv = v[off];
+      float gg = (gr >= 0 && grad_rows) ? grad_rows[(size_t)gr * ldg + h] : 0.f;
+      adam_update(pp, mm, vv, gg, a);
+      p[off] = pp;
+      m[off] = mm;
+      v[off] = vv;
+    }
+  }
+}
+
+template <int VEC>
+static __global__ void __launch_bounds__(256)
+    k_sgd(float* __restrict__ p, float* __restrict__ buf, long long rows, int H, const float* __restrict__ grad_rows,
+          int ldg, const int32_t* __restrict__ pos, float lr, float momentum, float wd) {
+  const int vpr = H / VEC;
+  const long long total = rows * vpr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vpr;
+    const int h = (int)(i % vpr) * VEC;
+    long long gr = pos ? (long long)pos[r] : r;
+    const size_t off = (size_t)r * H + h;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float pp = p[off + k], bb = buf[off + k];
+      float g = (gr >= 0 && grad_rows) ? grad_rows[(size_t)gr * ldg + h + k] : 0.f;
+      g = fmaf(wd, pp, g);
+      bb = fmaf(momentum, bb, g);  // buf.mul_(momentum).add_(grad); zero-initialised buf == clone(grad) on step 1
+      p[off + k] = pp - lr * bb;
+      buf[off + k] = bb;
+    }
+  }
+}
+
+// torch.optim.SparseAdam on the n rows `ids` (sparse_adam functional): no weight decay, eps outside the
+// bias correction: p -= lr*sqrt(bc2)/bc1 * m / (sqrt(v) + eps)
+static __global__ void __launch_bounds__(256)
+    k_sparse_adam(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, int H,
+                  const float* __restrict__ grad_rows, int ldg, const int64_t* __restrict__ ids, int n, float omb1,
+                  float omb2, float eps, float step_size) {
+  const long long total = (long long)n * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / H), h = (int)(i % H);
+    const size_t off = (size_t)ids[r] * H + h;
+    const float g = grad_rows[(size_t)r * ldg + h];
+    float mm = m[off], vv = v[off];
+    mm = mm + omb1 * (g - mm);                    // exp_avg.add_(make_sparse(grad.sub(m).mul_(1-beta1)))
+    vv = vv + omb2 * (g * g - vv);                // exp_avg_sq.add_(make_sparse(grad^2.sub(v).mul_(1-beta2)))
+    m[off] = mm;
+    v[off] = vv;
+    p[off] = p[off] - step_size * (mm / (sqrtf(vv) + eps));
+  }
+}
+
+static __global__ void k_scatter_pos(const int64_t* __restrict__ ids, int n, int32_t* __restrict__ pos, int reset) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pos[ids[i]] = reset ? -1 : i;
+}
+
+static inline int stream_grid(long long work_items) {
+  long long b = (work_items + 255) / 256;
+  long long cap = (long long)rcd_num_sms() * 8;  // 8 x 256-thread CTAs per SM, grid-stride beyond that
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace rcd
+
+using namespace rcd;
+
+RCD_EXPORT int rcd_adam_step(float* p, float* m, float* v, long long rows, int H, const float* grad_rows, int ldg,
+                             const int32_t* pos, double lr, double beta1, double beta2, double eps,
+                             double weight_decay, long long t, void* stream) {
+  RCD_CHECK_ARG(p && m && v && rows > 0 && H > 0 && t >= 1, "bad arguments");
+  RCD_CHECK_ARG(!grad_rows || ldg >= H, "ldg < H");
+  AdamScalars a;
+  a.beta2 = (float)beta2; a.eps = (float)eps; a.wd = (float)weight_decay;
+  a.omb1 = (float)(1.0 - beta1); a.omb2 = (float)(1.0 - beta2);
+  const double bc1 = 1.0 - pow(beta1, (double)t);
+  const double bc2 = 1.0 - pow(beta2, (double)t);
+  a.step_size = (float)(lr / bc1);
+  a.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (H % 4 == 0) && aligned16(p) && aligned16(m) && aligned16(v) &&
+                   (!grad_rows || (aligned16(grad_rows) && ldg % 4 == 0));
+  if (vec)
+    k_adam<4><<<stream_grid(rows * (H / 4)), 256, 0, st>>>(p, m, v, rows, H, grad_rows, ldg, pos, a);
+  else
+    k_adam<1><<<stream_grid(rows * H), 256, 0, st>>>(p, m, v, rows, H, grad_rows, ldg, pos, a);
+  RCD_LAUNCH_CHECK();
+  return RCD_OK;
+}
+
+RCD_EXPORT int rcd_sgd_step(float* p, float* buf, long long rows, int H, const float* grad_rows, int ldg,
+                            const int32_t* pos, double lr, double momentum, double weight_decay,
+                            void* stream) {
+  RCD_CHECK_ARG(p && buf && rows > 0 && H > 0, "bad arguments");
+  RCD_CHECK_ARG(!grad_rows || ldg >= H, "ldg < H");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (H % 4 == 0)
+    k_sgd<4><<<stream_grid(rows * (H / 4)), 256, 0, st>>>(p, buf, rows, H, grad_rows, ldg, pos, (float)lr,
+                                                         (float)momentum, (float)weight_decay);
+  else
+    k_sgd<1><<<stream_grid(rows * H), 256, 0, st>>>(p, buf, rows, H, grad_rows, ldg, pos, (float)lr, (float)momentum,
+                                                   (float)weight_decay);
+  RCD_LAUNCH_CHECK();
+  return RCD_OK;
+}
+
+RCD_EXPORT int rcd_sparse_adam_step(float* p, float* m, float* v, int H, const float* grad_rows, int ldg,
+                                    const int64_t* ids, int n, double lr, double beta1, double beta2, double eps,
+                                    long long t, void* stream) {
+  RCD_CHECK_ARG(p && m && v && grad_rows && ids && n > 0 && H > 0 && t >= 1 && ldg >= H, "bad arguments");
+  const double bc1 = 1.0 - pow(beta1, (double)t);
+  const double bc2 = 1.0 - pow(beta2, (double)t);
+  const float step_size = (float)(lr * sqrt(bc2) / bc1);
+  k_sparse_adam<<<stream_grid((long long)n * H), 256, 0, (cudaStream_t)stream>>>(p, m, v, H, grad_rows, ldg, ids, n,
+                                                                                (float)(1.0 - beta1),
+                                                                                (float)(1.0 - beta2), (float)eps,
+                                                                                step_size);
+  RCD_LAUNCH_CHECK();
+  return RCD_OK;
+}
+
+RCD_EXPORT int rcd_scatter_pos(const int64_t* ids, int n, int32_t* pos, int reset, void* stream) {
+  RCD_CHECK_ARG(ids && pos && n > 0, "bad arguments");
+  k_scatter_pos<<<rcd_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(ids, n, pos, reset);
+  RCD_LAUNCH_CHECK();
+  return RCD_OK;
+}

@@ -1,0 +1,345 @@
+"""Data pipeline of the hot path with the reference's interface (recoder/data.py), collate on the GPU.
+
+Same class names, constructor arguments, field names and assertion behaviour as the reference:
+`UsersInteractions` (data.py:14-25), `RecommendationDataset` (data.py:28-83), `RecommendationDataLoader`
+(data.py:86-167), `Batch` (data.py:170-187), `BatchCollator` (data.py:190-251).  The difference is where the
+work happens: the interaction matrix lives in HBM as CSR and `BatchCollator.collate` launches the K1 kernels
+(`rcd_collate`), so a `Batch` holds CUDA tensors (plus a handle on the compute layout the trainer consumes).
+"""
+import numbers
+
+import numpy as np
+import scipy.sparse as sparse
+import torch
+
+from . import _native
+
+
+def _issequence(t):
+  return (isinstance(t, (list, tuple)) and (len(t) == 0 or np.isscalar(t[0]))) or \
+         (isinstance(t, np.ndarray) and t.ndim == 1)
+
+
+def _isintlike(x):
+  if isinstance(x, numbers.Integral):
+    return True
+  return isinstance(x, np.ndarray) and x.ndim == 0 and np.issubdtype(x.dtype, np.integer)
+
+
+class DeviceCSR:
+  """A CSR matrix resident in HBM: indptr int64[U+1], indices int32[nnz], data fp32[nnz]."""
+
+  def __init__(self, matrix: sparse.csr_matrix, device=None):
+    _native.require_cuda()
+    self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    self.shape = matrix.shape
+    self.indptr_host = np.ascontiguousarray(matrix.indptr, dtype=np.int64)
+    self.indptr = torch.from_numpy(self.indptr_host).to(self.device)
+    self.indices = torch.from_numpy(np.ascontiguousarray(matrix.indices, dtype=np.int32)).to(self.device)
+    self.data = torch.from_numpy(np.ascontiguousarray(matrix.data, dtype=np.float32)).to(self.device)
+    if self.indices.numel() == 0:  # keep pointers valid
+      self.indices = torch.zeros(1, dtype=torch.int32, device=self.device)
+      self.data = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+  def pool_nnz(self, users: np.ndarray) -> int:
+    return int((self.indptr_host[users + 1] - self.indptr_host[users]).sum())
+
+
+class UsersInteractions:
+  """
+  Holds the interactions of a set of users in an interactions sparse matrix (reference data.py:14-25).
+
+  Args:
+    users (np.array): users being represented.
+    interactions_matrix (scipy.sparse.csr_matrix): user-item interactions matrix, where ``interactions_matrix[i]``
+      correspond to the interactions of ``users[i]``.
+  """
+
+  def __init__(self, users, interactions_matrix=None, _source=None):
+    self.users = users
+    self._matrix = interactions_matrix
+    self._source = _source  # (host csr, DeviceCSR getter, row index array) when it comes from a dataset
+
+  @property
+  def interactions_matrix(self):
+    if self._matrix is None:
+      host_csr, _, index = self._source
+      self._matrix = RecommendationDataset._extract(host_csr, index)
+    return self._matrix
+
+  @property
+  def num_rows(self):
+    if self._source is not None:
+      return len(self._source[2])
+    return self._matrix.shape[0]
+
+  @property
+  def num_cols(self):
+    if self._source is not None:
+      return self._source[0].shape[1]
+    return self._matrix.shape[1]
+
+
+class RecommendationDataset:
+  """
+  Iterates through the users interactions with items (reference data.py:28-83).  Indexing returns a
+  :class:`UsersInteractions` of the users in the index; the CSR itself is uploaded to HBM once, on first use.
+
+  Args:
+    interactions_matrix (scipy.sparse.csr_matrix): the user-item interactions matrix.
+    target_interactions_matrix (scipy.sparse.csr_matrix, optional): the target user-item interactions
+      matrix. Mainly used for evaluation, representing the items to recommend.
+  """
+
+  def __init__(self, interactions_matrix, target_interactions_matrix=None):
+    self.interactions_matrix = interactions_matrix
+    self.target_interactions_matrix = target_interactions_matrix
+    self.users = np.arange(self.interactions_matrix.shape[0])
+    self.items = np.arange(self.interactions_matrix.shape[1])
+    self._device_csr = None
+    self._device_target_csr = None
+
+  def __len__(self):
+    return self.interactions_matrix.shape[0]
+
+  def device_csr(self):
+    if self._device_csr is None:
+      self._device_csr = DeviceCSR(self.interactions_matrix)
+    return self._device_csr
+
+  def device_target_csr(self):
+    if self.target_interactions_matrix is None:
+      return None
+    if self._device_target_csr is None:
+      self._device_target_csr = DeviceCSR(self.target_interactions_matrix)
+    return self._device_target_csr
+
+  def __getitem__(self, index):
+    assert _issequence(index) or _isintlike(index)  # data.py:51
+    users = np.array(index).reshape(-1,)
+    input = UsersInteractions(users=users, _source=(self.interactions_matrix, self.device_csr, users))
+    if self.target_interactions_matrix is None:
+      return input, None
+    target = UsersInteractions(users=users, _source=(self.target_interactions_matrix, self.device_target_csr, users))
+    return input, target
+
+  @staticmethod
+  def _extract(sparse_matrix, index):
+    """Host-side row extraction (only used when somebody asks a UsersInteractions for its SciPy matrix)."""
+    index = np.asarray(index).reshape(-1)
+    return sparse_matrix[index]
+
+
+class Batch:
+  """
+  Represents a sparse batch of users and items interactions (reference data.py:170-187).
+
+  Args:
+    users (torch.LongTensor): users that are in the batch
+    items (torch.LongTensor): items that are in the batch
+    indices (torch.LongTensor): the indices of the interactions in the sparse matrix
+    values (torch.LongTensor): the values of the interactions
+    size (torch.Size): the size of the sparse interactions matrix
+  """
+
+  def __init__(self, users, items, indices, values, size, _pool=None, _row0=0):
+    self.users = users
+    self.items = items
+    self._indices = indices
+    self.values = values
+    self.size = size
+    self._pool = _pool  # PoolBatch: compute layout shared by the slices of one pool
+    self._row0 = _row0
+
+  @property
+  def indices(self):
+    """COO indices int64[2, nnz] (data.py:244); built on demand — the trainer consumes the CSR layout."""
+    if self._indices is None:
+      p = self._pool
+      rows = self.size[0]
+      lo, hi = p.row_ptr_host[self._row0], p.row_ptr_host[self._row0 + rows]
+      out = torch.empty((2, hi - lo), dtype=torch.int64, device=p.cols.device)
+      if hi > lo:
+        _native.call('rcd_collate_coo', _native.ptr(p.row_ptr), _native.ptr(p.cols), int(self._row0), int(rows),
+                     _native.ptr(out))
+      self._indices = out
+    return self._indices
+
+
+class PoolBatch:
+  """Compute layout of one collated pool (outputs of `rcd_collate`), shared by all its slices."""
+
+  def __init__(self, users_dev, num_rows, num_items, negative_sampling):
+    self.users = users_dev
+    self.num_rows = num_rows
+    self.num_items = num_items
+    self.negative_sampling = negative_sampling
+    self.row_ptr = self.raw_items = self.cols = self.vals = None
+    self.row_inv_norm = self.row_sum = self.pos = self.items_buf = self.counts = None
+    self.n = 0
+    self.nnz = 0
+    self.row_ptr_host = None
+
+  @property
+  def items(self):
+    return self.items_buf[:self.n]
+
+
+def collate_pool(csr: DeviceCSR, users, negative_sampling: bool) -> PoolBatch:
+  """Runs K1 on the rows `users` of `csr` and returns the pool's compute layout."""
+  users = np.ascontiguousarray(np.asarray(users).reshape(-1), dtype=np.int64)
+  assert users.size > 0
+  assert users.min() >= 0 and users.max() < csr.shape[0], 'user index out of range'
+  dev = csr.device
+  P, I = int(users.size), int(csr.shape[1])
+  lens = csr.indptr_host[users + 1] - csr.indptr_host[users]
+  nnz = int(lens.sum())
+  assert nnz < 2 ** 31, 'pool too large'
+  pb = PoolBatch(torch.from_numpy(users).to(dev), P, I, negative_sampling)
+  row_ptr_host = np.zeros(P + 1, dtype=np.int64)
+  np.cumsum(lens, out=row_ptr_host[1:])
+  pb.row_ptr_host = row_ptr_host
+  cap = max(nnz, 1)
+  pb.row_ptr = torch.empty(P + 1, dtype=torch.int32, device=dev)
+  pb.raw_items = torch.empty(cap, dtype=torch.int32, device=dev)
+  pb.cols = torch.empty(cap, dtype=torch.int32, device=dev)
+  pb.vals = torch.empty(cap, dtype=torch.float32, device=dev)
+  pb.row_inv_norm = torch.empty(P, dtype=torch.float32, device=dev)
+  pb.row_sum = torch.empty(P, dtype=torch.float32, device=dev)
+  pb.pos = torch.empty(I, dtype=torch.int32, device=dev)
+  pb.items_buf = torch.empty(min(I, cap) if negative_sampling else I, dtype=torch.int64, device=dev)
+  pb.counts = torch.zeros(2, dtype=torch.int32, device=dev)
+  lib = _native.load()
+  sbytes = lib.rcd_collate_scratch_bytes(P, I)
+  scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+  _native.call('rcd_collate', _native.ptr(csr.indptr), _native.ptr(csr.indices), _native.ptr(csr.data),
+               _native.ptr(pb.users), P, I, int(bool(negative_sampling)), cap, _native.ptr(pb.row_ptr),
+               _native.ptr(pb.raw_items), _native.ptr(pb.cols), _native.ptr(pb.vals), _native.ptr(pb.row_inv_norm),
+               _native.ptr(pb.row_sum), _native.ptr(pb.pos), _native.ptr(pb.items_buf), _native.ptr(pb.counts),
+               _native.ptr(scratch), sbytes)
+  counts = pb.counts.cpu()  # the one host sync of the collate: n decides every downstream shape
+  pb.n = int(counts[0])
+  pb.nnz = int(counts[1])
+  assert pb.nnz == nnz, 'device/host nnz mismatch'
+  return pb
+
+
+class BatchCollator:
+  """
+  Collator of :class:`UsersInteractions` into multiple :class:`Batch` based on ``batch_size``
+  (reference data.py:190-251), executed on the GPU.
+
+  Args:
+    batch_size (int): number of samples per batch
+    negative_sampling (bool, optional): whether to apply mini-batch based negative sampling or not.
+  """
+
+  def __init__(self, batch_size, negative_sampling=False):
+    self.batch_size = batch_size
+    self.negative_sampling = negative_sampling
+
+  def collate(self, users_interactions):
+    """
+    Collates :class:`UsersInteractions` into batches of size ``batch_size``.
+
+    Returns:
+      list[Batch]: list of batches (``items`` shared by all slices, data.py:246).
+    """
+    if users_interactions._source is not None:
+      _, get_csr, index = users_interactions._source
+      csr, rows = get_csr(), index
+    else:
+      m = users_interactions.interactions_matrix.tocsr()
+      csr, rows = DeviceCSR(m), np.arange(m.shape[0])
+    pb = collate_pool(csr, rows, self.negative_sampling)
+    batch_users = torch.as_tensor(np.asarray(users_interactions.users), dtype=torch.int64, device=csr.device)
+    vector_dim = pb.n if self.negative_sampling else csr.shape[1]
+    items = pb.items if self.negative_sampling else None
+    slices = []
+    P = pb.num_rows
+    for offset in range(0, P, self.batch_size):
+      hi = min(offset + self.batch_size, P)
+      lo_n, hi_n = int(pb.row_ptr_host[offset]), int(pb.row_ptr_host[hi])
+      slices.append(Batch(users=batch_users[offset:hi], items=items, indices=None, values=pb.vals[lo_n:hi_n],
+                          size=torch.Size([hi - offset, vector_dim]), _pool=pb, _row0=offset))
+    return slices
+
+
+class RecommendationDataLoader:
+  """
+  Generates batches with mini-batch negative sampling (reference data.py:86-167).
+
+  The sampling order follows the reference: ``RandomSampler`` over the dataset (torch global RNG), grouped into
+  pools of ``num_sampling_users`` (data.py:124-126); every pool is collated at once and yielded one
+  ``batch_size`` slice at a time (data.py:138-144).  ``num_workers`` is accepted for interface compatibility;
+  the collate runs on the GPU, so no worker processes are forked.
+
+  Args:
+    dataset (RecommendationDataset): dataset from which to load the data
+    batch_size (int): number of samples per batch
+    negative_sampling (bool, optional): whether to apply mini-batch based negative sampling or not.
+    num_sampling_users (int, optional): number of users to consider for mini-batch based negative
+      sampling. If 0, then num_sampling_users will be equal to batch_size.
+    num_workers (int, optional): ignored (see above).
+    collate_fn (callable, optional): A function that transforms a :class:`UsersInteractions` into a mini-batch.
+    user_order (callable, optional): ``epoch -> np.ndarray`` explicit user order (tests, benchmarks).
+  """
+
+  def __init__(self, dataset, batch_size, negative_sampling=False, num_sampling_users=0, num_workers=0,
+               collate_fn=None, user_order=None):
+    self.dataset = dataset
+    self.num_sampling_users = num_sampling_users
+    self.num_workers = num_workers
+    self.batch_size = batch_size
+    self.negative_sampling = negative_sampling
+    if self.num_sampling_users == 0:
+      self.num_sampling_users = batch_size
+    assert self.num_sampling_users >= batch_size, 'num_sampling_users should be at least equal to the batch_size'
+    self.batch_collator = BatchCollator(batch_size=self.batch_size, negative_sampling=self.negative_sampling)
+    if collate_fn is None:
+      self._collate_fn = self.batch_collator.collate
+      self._use_default_data_generator = True
+    else:
+      self._collate_fn = collate_fn
+      self._use_default_data_generator = False
+    self._user_order = user_order
+    self._epoch = 0
+
+  def _sample_order(self):
+    """torch.utils.data.RandomSampler semantics: a generator seeded from the global RNG, then randperm."""
+    self._epoch += 1
+    if self._user_order is not None:
+      return np.asarray(self._user_order(self._epoch), dtype=np.int64)
+    seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    gen = torch.Generator()
+    gen.manual_seed(seed)
+    return torch.randperm(len(self.dataset), generator=gen).numpy()
+
+  def pools(self):
+    """Yields the index list of every sampling pool of one epoch (data.py:124-126, drop_last=False)."""
+    order = self._sample_order()
+    for off in range(0, len(order), self.num_sampling_users):
+      yield order[off:off + self.num_sampling_users]
+
+  def _collated(self):
+    for index in self.pools():
+      input_ui, target_ui = self.dataset[index]
+      input = self._collate_fn(input_ui)
+      target = None if target_ui is None else self._collate_fn(target_ui)
+      yield input, target
+
+  def _default_data_generator(self):
+    for input, target in self._collated():
+      for batch_ind in range(len(input)):
+        if target is None:
+          yield input[batch_ind], None
+        else:
+          yield input[batch_ind], target[batch_ind]
+
+  def __iter__(self):
+    if self._use_default_data_generator:
+      return self._default_data_generator()
+    return self._collated()
+
+  def __len__(self):
+    return int(np.ceil(len(self.dataset) / self.batch_collator.batch_size))

@@ -1,0 +1,388 @@
+"""Step engine: one training step of the hot path as a fixed sequence of C-ABI kernel launches.
+
+Replaces the per-batch body of `Recoder._train` (recoder/model.py:383-404) and `Recoder.__compute_loss`
+(recoder/model.py:454-485): no dense [B, n] fp32 input/target is ever materialised, no autograd graph is
+built, the loss stays on the device.  Data-parallel mode shards the rows of a *global* batch over ranks and
+sums one contiguous gradient slab with a single all-reduce.
+
+Launch sequence of an autoencoder step (names are include/recoder_b200.h entry points):
+  rcd_slice_csc -> rcd_gather_rows/rcd_gather_vec (W_d, b_d of the n batch items) -> rcd_ae_encoder_fwd ->
+  rcd_decoder_fwd [-> rcd_softmax_lse] -> rcd_loss_grad -> rcd_decoder_dgrad -> rcd_dz_act ->
+  rcd_decoder_wgrad -> rcd_ae_encoder_wgrad -> [all-reduce] -> rcd_adam_step x4 (or SGD / SparseAdam)
+"""
+import math
+
+import torch
+
+from . import _native
+from ._native import call, ptr
+
+ADAM_BETAS = (0.9, 0.999)   # torch.optim.Adam defaults used at recoder/model.py:135
+ADAM_EPS = 1e-8
+SGD_MOMENTUM = 0.9          # recoder/model.py:149
+
+
+def _round_up(x, m):
+  return (x + m - 1) // m * m
+
+
+class _Buffers:
+  """Grow-only named device buffers (a step never allocates once shapes have been seen)."""
+
+  def __init__(self, device):
+    self.device = device
+    self._store = {}
+
+  def get(self, name, numel, dtype):
+    t = self._store.get(name)
+    if t is None or t.numel() < numel or t.dtype != dtype:
+      cap = int(numel * 1.2) + 64 if t is not None else int(numel)
+      t = torch.empty(max(cap, 1), dtype=dtype, device=self.device)
+      self._store[name] = t
+    return t[:numel]
+
+
+class ParamState:
+  """Optimizer state of one parameter tensor viewed as a [rows, H] matrix."""
+
+  def __init__(self, name, tensor, weight_decay, sparse):
+    self.name = name
+    self.p = tensor
+    self.weight_decay = weight_decay
+    self.sparse = sparse
+    self.step = 0
+    self.m = None   # Adam exp_avg / SGD momentum buffer
+    self.v = None   # Adam exp_avg_sq
+
+  def view2d(self):
+    t = self.p
+    if t.dim() == 1:
+      return t.numel(), 1
+    return t.shape[0], t.shape[1]
+
+
+class Optimizer:
+  """Fused replacements of the torch.optim objects Recoder.__init_optimizer builds (recoder/model.py:101-164):
+  one group per parameter, weight decay 0 for parameters with 'bias' in their name (model.py:123-124), a
+  separate row-sparse Adam for `sparse=True` embedding tables (model.py:110-115,137-138)."""
+
+  def __init__(self, named_params, optimizer_type, lr, weight_decay, sparse_names=()):
+    if optimizer_type not in ('adam', 'sgd'):
+      if optimizer_type in ('adagrad', 'rmsprop'):
+        raise NotImplementedError("optimizer '%s' is outside the B200 hot path (adam and sgd are implemented)"
+                                  % optimizer_type)
+      raise Exception('Unknown optimizer kind')                       # model.py:156
+    self.type = optimizer_type
+    self.lr = lr            # dense optimizer lr (MultiStepLR acts on it, model.py:327-332)
+    self.sparse_lr = lr     # SparseAdam lr never decays (reference quirk)
+    self.states = {}
+    for name, p in named_params:
+      wd = 0 if 'bias' in name else weight_decay
+      sp = name in sparse_names
+      if sp and optimizer_type != 'adam':
+        raise ValueError('Sparse gradients optimization not supported with %s' % optimizer_type)  # model.py:142-152
+      self.states[name] = ParamState(name, p, wd, sp)
+
+  def _ensure(self, st):
+    if st.m is None:
+      st.m = torch.zeros_like(st.p)
+      if self.type == 'adam':
+        st.v = torch.zeros_like(st.p)
+
+  def step_param(self, name, grad, ldg, pos=None, ids=None, n_ids=0):
+    """grad: compact rows [*, ldg] (see rcd_adam_step); pos: int32 map row->grad row or None for dense grads;
+    ids: int64 row ids for the row-sparse Adam."""
+    st = self.states[name]
+    self._ensure(st)
+    st.step += 1
+    rows, H = st.view2d()
+    if self.type == 'adam':
+      if st.sparse:
+        call('rcd_sparse_adam_step', ptr(st.p), ptr(st.m), ptr(st.v), H, ptr(grad), ldg, ptr(ids), int(n_ids),
+             float(self.sparse_lr), ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS, st.step)
+      else:
+        call('rcd_adam_step', ptr(st.p), ptr(st.m), ptr(st.v), rows, H, ptr(grad), ldg, ptr(pos), float(self.lr),
+             ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS, float(st.weight_decay), st.step)
+    else:
+      call('rcd_sgd_step', ptr(st.p), ptr(st.m), rows, H, ptr(grad), ldg, ptr(pos), float(self.lr), SGD_MOMENTUM,
+           float(st.weight_decay))
+
+  # --- torch.optim-compatible state_dict (param index = position in named_parameters(), model.py:208-215) ----
+  def state_dict(self, dense=True):
+    names = [n for n, s in self.states.items() if s.sparse != dense]
+    state, groups = {}, []
+    for i, n in enumerate(names):
+      s = self.states[n]
+      if s.m is not None:
+        if self.type == 'adam':
+          state[i] = {'step': torch.tensor(float(s.step)), 'exp_avg': s.m.detach().cpu().clone(),
+                      'exp_avg_sq': s.v.detach().cpu().clone()}
+        else:
+          state[i] = {'momentum_buffer': s.m.detach().cpu().clone()}
+      g = {'params': [i], 'lr': self.lr if dense else self.sparse_lr, 'weight_decay': s.weight_decay}
+      if self.type == 'adam':
+        g.update({'betas': ADAM_BETAS, 'eps': ADAM_EPS})
+      else:
+        g.update({'momentum': SGD_MOMENTUM, 'dampening': 0, 'nesterov': False})
+      groups.append(g)
+    return {'state': state, 'param_groups': groups}
+
+  def load_state_dict(self, sd, dense=True):
+    names = [n for n, s in self.states.items() if s.sparse != dense]
+    for i, n in enumerate(names):
+      s = self.states[n]
+      entry = sd['state'].get(i)
+      if entry is None:
+        continue
+      dev = s.p.device
+      if self.type == 'adam':
+        s.m = entry['exp_avg'].to(dev, torch.float32).clone()
+        s.v = entry['exp_avg_sq'].to(dev, torch.float32).clone()
+        s.step = int(float(entry['step']))
+      else:
+        s.m = entry['momentum_buffer'].to(dev, torch.float32).clone()
+    if sd.get('param_groups'):
+      lr = sd['param_groups'][0].get('lr')
+      if lr is not None:
+        if dense:
+          self.lr = lr
+        else:
+          self.sparse_lr = lr
+
+
+class TrainEngine:
+  """Executes training steps for a single-hidden-layer DynamicAutoencoder ('ae') or a MatrixFactorization ('mf')."""
+
+  LOSS_RING = 4096
+
+  def __init__(self, kind, params, loss, confidence, activation, optimizer: Optimizer, gemm_engine=None,
+               process_group=None, tied=False):
+    _native.require_cuda()
+    self.kind = kind
+    self.params = params          # dict of role -> (name, tensor)
+    self.loss_id = _native.LOSS_IDS[loss]
+    self.confidence = float(confidence)
+    self.act = _native.ACT_IDS[activation]
+    self.opt = optimizer
+    self.gemm = _native.GEMM_TCGEN05 if gemm_engine is None else gemm_engine
+    self.pg = process_group
+    self.tied = tied
+    dev = next(iter(params.values()))[1].device
+    self.device = dev
+    self.buf = _Buffers(dev)
+    self.loss_ring = torch.zeros(self.LOSS_RING, dtype=torch.float64, device=dev)
+    self.steps_done = 0
+    self.lib = _native.load()
+    self.tile_n = self.lib.rcd_decoder_tile_n()
+    self.last = {}                # views of the last step's compact gradients (tests / telemetry)
+
+  # ------------------------------------------------------------------------------------------------------
+  def _loss_slot(self):
+    i = self.steps_done % self.LOSS_RING
+    slot = self.loss_ring[i:i + 1]
+    slot.zero_()
+    return slot
+
+  def losses(self, last_k):
+    """The last `last_k` step losses as a CPU float64 tensor (one sync)."""
+    k = min(last_k, self.steps_done, self.LOSS_RING)
+    idx = [(self.steps_done - k + j) % self.LOSS_RING for j in range(k)]
+    return self.loss_ring[torch.tensor(idx, device=self.device, dtype=torch.long)].cpu() if k else torch.zeros(0)
+
+  def _world(self):
+    if self.pg is None:
+      return 1, 0
+    import torch.distributed as dist
+    return dist.get_world_size(self.pg), dist.get_rank(self.pg)
+
+  # ------------------------------------------------------------------------------------------------------
+  def train_step(self, pool, row0, rows, target_pool=None, global_rows=None):
+    """One optimizer step on rows [row0, row0+rows) of `pool` (a data.PoolBatch).  `target_pool` is the collate
+    of the dataset's target matrix for the same users (recoder/model.py:464-472) or None when the input is its
+    own target (model.py:473-476).  `global_rows` is the number of rows of the whole (all-rank) batch the loss
+    is averaged over (model.py:483-484); defaults to `rows`."""
+    inv_b = 1.0 / float(global_rows or rows)
+    loss_slot = self._loss_slot()
+    if self.kind == 'ae':
+      self._ae_step(pool, target_pool or pool, row0, rows, inv_b, loss_slot, train=True)
+    else:
+      self._mf_step(pool, target_pool or pool, row0, rows, inv_b, loss_slot, train=True)
+    self.steps_done += 1
+
+  def eval_loss(self, pool, row0, rows, target_pool=None):
+    """Loss of one batch without touching the parameters (`Recoder._validate`, recoder/model.py:439-452)."""
+    slot = self.buf.get('eval_loss', 1, torch.float64)
+    slot.zero_()
+    if self.kind == 'ae':
+      self._ae_step(pool, target_pool or pool, row0, rows, 1.0 / rows, slot, train=False)
+    else:
+      self._mf_step(pool, target_pool or pool, row0, rows, 1.0 / rows, slot, train=False)
+    return float(slot.item())
+
+  def _slice_csc(self, pool, row0, rows, n, tag):
+    nnz = int(pool.row_ptr_host[row0 + rows] - pool.row_ptr_host[row0])
+    b = self.buf
+    csc_ptr = b.get(tag + 'csc_ptr', n + 1, torch.int32)
+    csc_row = b.get(tag + 'csc_row', max(nnz, 1), torch.int32)
+    csc_val = b.get(tag + 'csc_val', max(nnz, 1), torch.float32)
+    sbytes = self.lib.rcd_slice_csc_scratch_bytes(n, max(nnz, 1))
+    scratch = b.get('csc_scratch', sbytes, torch.uint8)
+    call('rcd_slice_csc', ptr(pool.row_ptr), ptr(pool.cols), ptr(pool.vals), row0, rows, n, ptr(csc_ptr),
+         ptr(csc_row), ptr(csc_val), ptr(scratch), sbytes)
+    return csc_ptr, csc_row, csc_val
+
+  def _decoder_and_loss(self, Zb, ldh, Wg, bias_g, rows, n, H, inv_b, tpool, row0, csc, loss_slot, db_out):
+    """K4 + K5: logits (bf16) -> dO (bf16), db, loss.  Returns (dO, ldn)."""
+    b = self.buf
+    ldn = _round_up(n, 8)
+    O = b.get('O', rows * ldn, torch.bfloat16)
+    dO = b.get('dO', rows * ldn, torch.bfloat16)
+    nll = self.loss_id == _native.LOSS_IDS['logloss']
+    n_tiles = (n + self.tile_n - 1) // self.tile_n
+    smax = ssum = lse = None
+    if nll:
+      smax = b.get('stat_max', n_tiles * rows, torch.float32)
+      ssum = b.get('stat_sum', n_tiles * rows, torch.float32)
+      lse = b.get('lse', rows, torch.float32)
+    call('rcd_decoder_fwd', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bias_g), rows, n, H, ptr(O), None, ldn, ptr(smax),
+         ptr(ssum), self.gemm)
+    row_sum = tpool.row_sum[row0:row0 + rows]
+    if nll:
+      call('rcd_softmax_lse', ptr(smax), ptr(ssum), n_tiles, rows, ptr(row_sum), inv_b, ptr(lse), ptr(loss_slot))
+    csc_ptr, csc_row, csc_val = csc
+    call('rcd_loss_grad', ptr(O), ldn, rows, n, self.loss_id, self.confidence, inv_b, ptr(lse), ptr(row_sum),
+         ptr(csc_ptr), ptr(csc_row), ptr(csc_val), ptr(dO), ldn, ptr(db_out), ptr(loss_slot))
+    return dO, ldn
+
+  def _dgrad(self, dO, ldn, Wg, ldh, rows, n, H, Zf32, act, dA, db):
+    b = self.buf
+    splits = self.lib.rcd_decoder_dgrad_splits(rows, n, H)
+    partials = b.get('dz_partials', splits * rows * H, torch.float32)
+    call('rcd_decoder_dgrad', ptr(dO), ldn, ptr(Wg), ldh, rows, n, H, splits, ptr(partials), H, self.gemm)
+    call('rcd_dz_act', ptr(partials), splits, H, ptr(Zf32), rows, H, act, ptr(dA), ptr(db))
+
+  def _reduce_slab(self, slab, loss_slot):
+    """Data-parallel exchange: ONE all-reduce over the gradient slab; the loss rides in its last 2 floats
+    (hi/lo split of the double, so nothing is lost to fp32)."""
+    if self.pg is None:
+      return
+    import torch.distributed as dist
+    tail = slab[-2:]
+    hi = loss_slot.to(torch.float32)
+    lo = (loss_slot - hi.to(torch.float64)).to(torch.float32)
+    tail[0:1].copy_(hi)
+    tail[1:2].copy_(lo)
+    dist.all_reduce(slab, op=dist.ReduceOp.SUM, group=self.pg)
+    loss_slot.copy_(tail[0:1].to(torch.float64) + tail[1:2].to(torch.float64))
+
+  # ------------------------------------------------------------------------------------------------------
+  def _ae_step(self, pool, tpool, row0, rows, inv_b, loss_slot, train):
+    b = self.buf
+    (en_name, We), (enb_name, be) = self.params['en_w'], self.params['en_b']
+    (de_name, Wd), (deb_name, bd) = self.params['de_w'], self.params['de_b']
+    H = We.shape[1]
+    ldh = _round_up(H, 8)
+    n_in, n = pool.n, tpool.n
+    same = tpool is pool
+    if self.tied and not same:
+      raise NotImplementedError('tied weights with a separate target matrix are not supported')
+    t_items = tpool.items if tpool.negative_sampling else None
+    csc_t = self._slice_csc(tpool, row0, rows, n, 't_')
+    csc_in = csc_t if same else (self._slice_csc(pool, row0, rows, n_in, 'i_') if train else None)
+
+    # gradient slab: [dWe_rows n_in*H | dWd_rows n*H | dbd n (pad 4) | dbe H (pad 4) | pad 2 | loss hi, lo]
+    n4, h4 = _round_up(n, 4), _round_up(H, 4)
+    o_wd = n_in * H
+    o_bd = o_wd + n * H
+    o_be = o_bd + n4
+    slab = b.get('slab', o_be + h4 + 4, torch.float32)
+    dWe, dWd = slab[0:o_wd], slab[o_wd:o_bd]
+    dbd, dbe = slab[o_bd:o_bd + n], slab[o_be:o_be + H]
+
+    Wg = b.get('Wg', n * ldh, torch.bfloat16)
+    bg = b.get('bias_g', n, torch.float32)
+    call('rcd_gather_rows', ptr(Wd), H, ptr(t_items), n, 0, ptr(Wg), ldh, None)
+    call('rcd_gather_vec', ptr(bd), ptr(t_items), n, ptr(bg))
+
+    Z = b.get('Z', rows * H, torch.float32)
+    Zb = b.get('Zb', rows * ldh, torch.bfloat16)
+    call('rcd_ae_encoder_fwd', ptr(We), H, ptr(be), ptr(pool.row_ptr), ptr(pool.raw_items), ptr(pool.vals),
+         ptr(pool.row_inv_norm), row0, rows, self.act, ptr(Z), ptr(Zb), ldh)
+
+    dO, ldn = self._decoder_and_loss(Zb, ldh, Wg, bg, rows, n, H, inv_b, tpool, row0, csc_t, loss_slot, dbd)
+    if not train:
+      return
+
+    dA = b.get('dA', rows * H, torch.float32)
+    self._dgrad(dO, ldn, Wg, ldh, rows, n, H, Z, self.act, dA, dbe)
+    call('rcd_decoder_wgrad', ptr(dO), ldn, ptr(Zb), ldh, rows, n, H, ptr(dWd), H, self.gemm)
+    csc_ptr, csc_row, csc_val = csc_in
+    call('rcd_ae_encoder_wgrad', ptr(dA), H, ptr(csc_ptr), ptr(csc_row), ptr(csc_val), ptr(pool.row_inv_norm), row0,
+         n_in, ptr(dWe))
+
+    self._reduce_slab(slab, loss_slot)
+    self.last = {'n': n, 'n_in': n_in, 'dWe': dWe.view(n_in, H), 'dWd': dWd.view(n, H), 'dbd': dbd, 'dbe': dbe}
+
+    if self.tied:  # is_constrained: one table receives both gradients (recoder/nn.py:200)
+      dWe.add_(dWd)
+      self.opt.step_param(en_name, dWe, H, pos=pool.pos, ids=pool.items_buf, n_ids=n_in)
+    else:
+      self.opt.step_param(en_name, dWe, H, pos=pool.pos, ids=pool.items_buf, n_ids=n_in)
+      self.opt.step_param(de_name, dWd, H, pos=tpool.pos, ids=tpool.items_buf, n_ids=n)
+    self.opt.step_param(enb_name, dbe, H)
+    self.opt.step_param(deb_name, dbd, 1, pos=tpool.pos)
+
+  # ------------------------------------------------------------------------------------------------------
+  def _mf_step(self, pool, tpool, row0, rows, inv_b, loss_slot, train):
+    b = self.buf
+    (u_name, U), (v_name, V), (bias_name, bias) = self.params['user_w'], self.params['item_w'], self.params['bias']
+    D = V.shape[1]
+    ldd = _round_up(D, 8)
+    n = tpool.n
+    world, rank = self._world()
+    t_items = tpool.items if tpool.negative_sampling else None
+    csc = self._slice_csc(tpool, row0, rows, n, 't_')
+    users = pool.users[row0:row0 + rows]
+
+    # slab: [dV_rows n*D | dbias n (pad 4) | dU rows of ALL ranks (other ranks' blocks zero) | pad 2 | loss hi, lo]
+    n4 = _round_up(n, 4)
+    all_rows = rows * world
+    o_b = n * D
+    o_u = o_b + n4
+    slab = b.get('slab', o_u + all_rows * D + 4, torch.float32)
+    dV, dbias = slab[0:o_b], slab[o_b:o_b + n]
+    dU_all = slab[o_u:o_u + all_rows * D]
+    if world > 1:
+      dU_all.zero_()
+    dU = dU_all[rank * rows * D:(rank + 1) * rows * D]
+
+    Vg = b.get('Wg', n * ldd, torch.bfloat16)
+    bg = b.get('bias_g', n, torch.float32)
+    call('rcd_gather_rows', ptr(V), D, ptr(t_items), n, 0, ptr(Vg), ldd, None)
+    call('rcd_gather_vec', ptr(bias), ptr(t_items), n, ptr(bg))
+    Ue = b.get('Z', rows * D, torch.float32)
+    Ub = b.get('Zb', rows * ldd, torch.bfloat16)
+    call('rcd_gather_rows', ptr(U), D, ptr(users), rows, self.act, ptr(Ub), ldd, ptr(Ue))
+
+    dO, ldn = self._decoder_and_loss(Ub, ldd, Vg, bg, rows, n, D, inv_b, tpool, row0, csc, loss_slot, dbias)
+    if not train:
+      return
+    self._dgrad(dO, ldn, Vg, ldd, rows, n, D, Ue, self.act, dU, None)
+    call('rcd_decoder_wgrad', ptr(dO), ldn, ptr(Ub), ldd, rows, n, D, ptr(dV), D, self.gemm)
+
+    self._reduce_slab(slab, loss_slot)
+    self.last = {'n': n, 'dV': dV.view(n, D), 'dbias': dbias, 'dU': dU.view(rows, D)}
+
+    # In DP the pool holds the GLOBAL batch and rank r works on its r-th block of `rows` rows, so the users
+    # of all ranks are the pool rows of the whole global slice.
+    base = row0 - rank * rows
+    all_users = pool.users[base:base + all_rows]
+    upos = b.get('user_pos', U.shape[0], torch.int32)
+    if not getattr(self, '_upos_init', False):
+      upos.fill_(-1)
+      self._upos_init = True
+    call('rcd_scatter_pos', ptr(all_users), all_rows, ptr(upos), 0)
+    self.opt.step_param(u_name, dU_all, D, pos=upos, ids=all_users, n_ids=all_rows)
+    call('rcd_scatter_pos', ptr(all_users), all_rows, ptr(upos), 1)
+    self.opt.step_param(v_name, dV, D, pos=tpool.pos, ids=tpool.items_buf, n_ids=n)
+    self.opt.step_param(bias_name, dbias, 1, pos=tpool.pos)

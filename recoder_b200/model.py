@@ -1,0 +1,495 @@
+"""`Recoder` trainer with the reference's interface (recoder/model.py), driving the B200 step engine.
+
+Same constructor / `train()` keyword arguments, optimizer and loss selection rules, epoch / iteration
+bookkeeping, learning-rate milestones, checkpoint file layout and exceptions as the reference.  What changed
+underneath: the interaction matrix lives in HBM, every mini-batch is collated by CUDA kernels, and one
+training step is a fixed sequence of C-ABI kernel launches (engine.TrainEngine) instead of
+`__compute_loss` → autograd → torch.optim (recoder/model.py:383-404, 454-485).  The loss is kept on the
+device and read back only when the progress bar refreshes (the reference syncs with `loss.item()` every
+step, model.py:404).
+"""
+import logging
+import os
+
+import numpy as np
+import torch
+from torch.nn import BCEWithLogitsLoss
+
+from . import __version__
+from . import _native
+from .data import RecommendationDataLoader, BatchCollator, collate_pool
+from .engine import Optimizer, TrainEngine
+from .losses import MSELoss, MultinomialNLLLoss
+from .nn import FactorizationModel
+
+log = logging.getLogger('recoder_b200')
+
+try:
+  from tqdm import tqdm
+except ImportError:  # pragma: no cover
+  tqdm = None
+
+
+class _NoBar:
+  def __init__(self, *a, **k): pass
+  def set_postfix(self, *a, **k): pass
+  def update(self, *a, **k): pass
+  def close(self): pass
+
+
+class Recoder(object):
+  """
+  Module to train/evaluate a recommendation :class:`recoder_b200.nn.FactorizationModel`.
+
+  Args:
+    model (FactorizationModel): the factorization model to train.
+    num_items (int, optional): the number of items to represent. If None, it will
+      be computed from the first training dataset passed to ``train()``.
+    num_users (int, optional): the number of users to represent. If not provided, it will
+      be computed from the first training dataset passed to ``train()``.
+    optimizer_type (str, optional): optimizer type (one of 'sgd', 'adam'; 'adagrad' and 'rmsprop' raise
+      NotImplementedError — they are outside the accelerated path).
+    loss (str or torch.nn.Module, optional): `mse` for ``MSELoss``, `logistic` for ``BCEWithLogitsLoss``,
+      `logloss` for ``MultinomialNLLLoss``, or an instance of one of those modules.
+    loss_params (dict, optional): loss function extra params based on loss module if ``loss`` is a ``str``.
+    use_cuda (bool, optional): must be True to train — this implementation has no CPU path.
+    user_based (bool, optional): raise on inconsistencies between model users and dataset users.
+    item_based (bool, optional): raise on inconsistencies between model items and dataset items.
+    process_group (optional, extension): torch.distributed group for data-parallel training; defaults to the
+      WORLD group when torch.distributed is initialised with more than one rank.
+    gemm_engine (optional, extension): _native.GEMM_TCGEN05 (default) or _native.GEMM_SIMT (validation).
+  """
+
+  def __init__(self, model: FactorizationModel,
+               num_items=None, num_users=None,
+               optimizer_type='sgd', loss='mse',
+               loss_params=None, use_cuda=False,
+               user_based=True, item_based=True,
+               process_group=None, gemm_engine=None):
+
+    self.model = model
+    self.num_items = num_items
+    self.num_users = num_users
+    self.optimizer_type = optimizer_type
+    self.loss = loss
+    self.loss_params = loss_params if loss_params else {}
+    self.use_cuda = use_cuda
+    self.user_based = user_based
+    self.item_based = item_based
+    self.process_group = process_group
+    self.gemm_engine = gemm_engine
+
+    if self.use_cuda:
+      self.device = torch.device('cuda')
+    else:
+      self.device = torch.device('cpu')
+
+    self.optimizer = None
+    self.sparse_optimizer = None  # kept for interface parity: the fused Optimizer handles both kinds
+    self.engine = None
+    self.current_epoch = 1
+    self.items = None
+    self.users = None
+    self.__model_initialized = False
+    self.__optimizer_state_dict = None
+    self.__sparse_optimizer_state_dict = None
+
+  # ---------------------------------------------------------------------------------------------------
+  def __require_cuda(self):
+    if self.device.type != 'cuda':
+      raise RuntimeError('recoder_b200 has no CPU path: construct Recoder(..., use_cuda=True)')
+    _native.require_cuda()
+    _native.load()
+
+  def __init_model(self):
+    if self.__model_initialized:
+      return
+    self.model.init_model(self.num_items, self.num_users)
+    self.model = self.model.to(device=self.device)
+    self.__model_initialized = True
+
+  def __loss_spec(self):
+    """Resolves `self.loss` like `__init_loss_module` (reference model.py:87-99) into (kind, confidence)."""
+    loss = self.loss
+    if isinstance(loss, torch.nn.Module):
+      if isinstance(loss, MSELoss):
+        return 'mse', float(loss.confidence)
+      if isinstance(loss, MultinomialNLLLoss):
+        return 'logloss', 0.0
+      if isinstance(loss, BCEWithLogitsLoss):
+        return 'logistic', 0.0
+      raise NotImplementedError('custom loss modules need dense logits and autograd; the B200 path fuses '
+                                "'mse', 'logistic' and 'logloss' (got %s)" % type(loss).__name__)
+    elif loss == 'logistic':
+      if self.loss_params:
+        raise NotImplementedError('BCEWithLogitsLoss extra parameters are not supported on the B200 path')
+      return 'logistic', 0.0
+    elif loss == 'mse':
+      unknown = set(self.loss_params) - {'confidence'}
+      if unknown:
+        raise TypeError("__init__() got an unexpected keyword argument '%s'" % sorted(unknown)[0])
+      return 'mse', float(self.loss_params.get('confidence', 0))
+    elif loss == 'logloss':
+      return 'logloss', 0.0
+    elif loss is None:
+      raise ValueError('No loss function defined')
+    else:
+      raise ValueError('Unknown loss function {}'.format(loss))
+
+  def __init_optimizer(self, lr, weight_decay):
+    # When continuing training on the same Recoder instance (reference model.py:103-107)
+    if self.optimizer is not None:
+      self.__optimizer_state_dict = self.optimizer.state_dict(dense=True)
+      self.__sparse_optimizer_state_dict = self.optimizer.state_dict(dense=False)
+
+    sparse_names = self.model._sparse_param_names()
+    named = [(n, p.data) for n, p in self.model.named_parameters()]
+    self.optimizer = Optimizer(named, self.optimizer_type, lr, weight_decay, sparse_names=sparse_names)
+
+    if self.__optimizer_state_dict is not None:
+      self.optimizer.load_state_dict(self.__optimizer_state_dict, dense=True)
+      self.optimizer.lr = lr
+      self.__optimizer_state_dict = None
+    if self.__sparse_optimizer_state_dict is not None:
+      self.optimizer.load_state_dict(self.__sparse_optimizer_state_dict, dense=False)
+      self.__sparse_optimizer_state_dict = None
+
+  def __init_engine(self):
+    kind, roles, activation, tied = self.model._engine_spec()
+    loss_kind, confidence = self.__loss_spec()
+    pg = self.process_group
+    if pg is None:
+      import torch.distributed as dist
+      if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        pg = dist.group.WORLD
+    self.engine = TrainEngine(kind, roles, loss_kind, confidence, activation, self.optimizer,
+                              gemm_engine=self.gemm_engine, process_group=pg, tied=tied)
+
+  def init_from_model_file(self, model_file):
+    """
+    Initializes the model from a pre-trained model (reference model.py:166-191; same file layout).
+
+    Args:
+       model_file (str): the pre-trained model file path
+    """
+    log.info('Loading model from: {}'.format(model_file))
+    if not os.path.isfile(model_file):
+      raise Exception('No state file found in {}'.format(model_file))
+    model_saved_state = torch.load(model_file, map_location='cpu', weights_only=False)
+    model_params = model_saved_state['model_params']
+    self.current_epoch = model_saved_state['last_epoch']
+    self.loss = model_saved_state.get('loss', self.loss)
+    self.loss_params = model_saved_state.get('loss_params', self.loss_params)
+    self.optimizer_type = model_saved_state['optimizer_type']
+    self.items = model_saved_state.get('items', None)
+    self.users = model_saved_state.get('users', None)
+    self.num_items = model_saved_state.get('num_items', None)
+    self.num_users = model_saved_state.get('num_users', None)
+    self.__optimizer_state_dict = model_saved_state['optimizer']
+    self.__sparse_optimizer_state_dict = model_saved_state.get('sparse_optimizer', None)
+
+    self.model.load_model_params(model_params)
+    self.__init_model()
+    self.model.load_state_dict(model_saved_state['model'])
+
+  def save_state(self, model_checkpoint_prefix):
+    """
+    Saves the model state in the path starting with ``model_checkpoint_prefix`` and appending it
+    with the model current training epoch (reference model.py:193-224; same keys).
+
+    Returns:
+      the model state file path
+    """
+    checkpoint_file = "{}_epoch_{}.model".format(model_checkpoint_prefix, self.current_epoch)
+    log.info("Saving model to {}".format(checkpoint_file))
+    current_state = {
+      'recoder_version': __version__,
+      'model_params': self.model.model_params(),
+      'last_epoch': self.current_epoch,
+      'model': {k: v.detach().cpu() for k, v in self.model.state_dict().items()},
+      'optimizer_type': self.optimizer_type,
+      'optimizer': self.optimizer.state_dict(dense=True),
+      'items': self.items,
+      'users': self.users,
+      'num_items': self.num_items,
+      'num_users': self.num_users
+    }
+    if any(s.sparse for s in self.optimizer.states.values()):
+      # the reference reads this key on load (model.py:187) but never writes it; writing it loses nothing
+      current_state['sparse_optimizer'] = self.optimizer.state_dict(dense=False)
+
+    if type(self.loss) is str:
+      current_state['loss'] = self.loss
+      current_state['loss_params'] = self.loss_params
+
+    torch.save(current_state, checkpoint_file)
+    return checkpoint_file
+
+  def __init_training(self, train_dataset, lr, weight_decay):
+    if self.items is None:
+      self.items = train_dataset.items
+    else:
+      self.items = np.unique(np.append(self.items, train_dataset.items))
+
+    if self.users is None:
+      self.users = train_dataset.users
+    else:
+      self.users = np.unique(np.append(self.users, train_dataset.users))
+
+    if self.item_based and self.num_items is None:
+      self.num_items = int(np.max(self.items)) + 1
+    elif self.item_based:
+      assert self.num_items >= int(np.max(self.items)) + 1, \
+        'The largest item id should be smaller than number of items.' \
+        'If your model is not based on items, set item_based to False in Recoder constructor.'
+
+    if self.user_based and self.num_users is None:
+      self.num_users = int(np.max(self.users)) + 1
+    elif self.user_based:
+      assert self.num_users >= int(np.max(self.users)) + 1, \
+        'The largest user id should be smaller than number of users.' \
+        'If your model is not based on users, set user_based to False in Recoder constructor.'
+
+    self.__loss_spec()  # raises ValueError for unknown / missing losses before touching the device
+    self.__require_cuda()
+    self.__init_model()
+    self.__init_optimizer(lr=lr, weight_decay=weight_decay)
+    self.__init_engine()
+
+  def _world(self):
+    pg = self.engine.pg if self.engine is not None else None
+    if pg is None:
+      return 1, 0
+    import torch.distributed as dist
+    return dist.get_world_size(pg), dist.get_rank(pg)
+
+  def train(self, train_dataset, val_dataset=None,
+            lr=0.001, weight_decay=0, num_epochs=1,
+            iters_per_epoch=None, batch_size=64, lr_milestones=None,
+            negative_sampling=False, num_sampling_users=0, num_data_workers=0,
+            model_checkpoint_prefix=None, checkpoint_freq=0,
+            eval_freq=0, eval_num_recommendations=None,
+            eval_num_users=None, metrics=None, eval_batch_size=None, user_order=None):
+    """
+    Trains the model (reference model.py:256-347; same arguments).  In data-parallel runs ``batch_size`` is the
+    per-rank batch: one optimizer step consumes ``batch_size * world_size`` users and is numerically the
+    reference's step with that global batch size.  ``user_order`` (extension) is an ``epoch -> index array``
+    callable replacing the random sampler, used by tests and benchmarks.
+    """
+    log.info('{} Mode'.format('CPU' if self.device.type == 'cpu' else 'GPU'))
+    model_params = self.model.model_params()
+    for param in model_params:
+      log.info('Model {}: {}'.format(param, model_params[param]))
+    log.info('Initial Learning Rate: {}'.format(lr))
+    log.info('Weight decay: {}'.format(weight_decay))
+    log.info('Batch Size: {}'.format(batch_size))
+    log.info('Optimizer: {}'.format(self.optimizer_type))
+    log.info('LR milestones: {}'.format(lr_milestones))
+    log.info('Loss Function: {}'.format(self.loss))
+    for param in self.loss_params:
+      log.info('Loss {}: {}'.format(param, self.loss_params[param]))
+
+    if num_sampling_users == 0:
+      num_sampling_users = batch_size
+
+    if eval_batch_size is None:
+      eval_batch_size = batch_size
+
+    assert num_sampling_users >= batch_size and num_sampling_users % batch_size == 0, \
+      "number of sampling users should be a multiple of the batch size"
+
+    self.__init_training(train_dataset=train_dataset, lr=lr, weight_decay=weight_decay)
+    world, _ = self._world()
+
+    train_dataloader = RecommendationDataLoader(train_dataset, batch_size=batch_size * world,
+                                                negative_sampling=negative_sampling,
+                                                num_sampling_users=num_sampling_users * world,
+                                                num_workers=num_data_workers, user_order=user_order)
+    if val_dataset is not None:
+      val_dataloader = RecommendationDataLoader(val_dataset, batch_size=batch_size,
+                                                negative_sampling=negative_sampling,
+                                                num_sampling_users=num_sampling_users,
+                                                num_workers=num_data_workers)
+    else:
+      val_dataloader = None
+
+    self._base_lr = lr
+    self._lr_milestones = sorted(lr_milestones) if lr_milestones is not None else None
+
+    self._train(train_dataloader=train_dataloader,
+                val_dataloader=val_dataloader,
+                num_epochs=num_epochs,
+                current_epoch=self.current_epoch,
+                batch_size=batch_size,
+                model_checkpoint_prefix=model_checkpoint_prefix,
+                checkpoint_freq=checkpoint_freq,
+                eval_freq=eval_freq,
+                metrics=metrics,
+                eval_num_recommendations=eval_num_recommendations,
+                iters_per_epoch=iters_per_epoch,
+                eval_num_users=eval_num_users,
+                eval_batch_size=eval_batch_size)
+
+  def _epoch_lr(self, epoch):
+    """MultiStepLR(gamma=0.1) stepped at every epoch start (reference model.py:327-332, 364-366):
+    during epoch e the dense optimizer runs at lr * 0.1 ** #{milestones <= e}."""
+    if self._lr_milestones is None:
+      return self._base_lr
+    k = sum(1 for m in self._lr_milestones if m <= epoch)
+    return self._base_lr * (0.1 ** k)
+
+  def _pool_steps(self, dataloader, batch_size):
+    """Generator over (pool, target_pool, row0, rows, global_rows): one item per optimizer step, in the order the
+    reference's `_default_data_generator` yields slices (data.py:138-144)."""
+    world, rank = self._world()
+    ds = dataloader.dataset
+    csr = ds.device_csr()
+    tcsr = ds.device_target_csr()
+    gstep = batch_size * world
+    for index in dataloader.pools():
+      pool = collate_pool(csr, index, dataloader.negative_sampling)
+      tpool = collate_pool(tcsr, index, dataloader.negative_sampling) if tcsr is not None else None
+      P = pool.num_rows
+      for goff in range(0, P, gstep):
+        grows = min(gstep, P - goff)
+        per = grows // world
+        if per == 0:
+          continue  # ragged tail smaller than the number of ranks
+        yield pool, tpool, goff + rank * per, per, per * world
+
+  def _train(self, train_dataloader, val_dataloader,
+             num_epochs, current_epoch,
+             batch_size, model_checkpoint_prefix, checkpoint_freq,
+             eval_freq, metrics, eval_num_recommendations, iters_per_epoch,
+             eval_num_users, eval_batch_size):
+    num_batches = len(train_dataloader)
+
+    iters_processed = 0
+    if iters_per_epoch is None:
+      iters_per_epoch = num_batches
+    refresh_every = 50
+    iterator = None
+    world, rank = self._world()
+
+    for epoch in range(current_epoch, num_epochs + 1):
+      self.current_epoch = epoch
+      self.model.train()
+      lr = self._epoch_lr(epoch)
+      self.optimizer.lr = lr
+      description = 'Epoch {}/{} (lr={})'.format(epoch, num_epochs, lr)
+
+      if iters_processed == 0 or iters_processed == num_batches:
+        # starting from scratch, or the whole dataloader was consumed: new pass (reference model.py:371-376)
+        iters_processed = 0
+        iterator = enumerate(self._pool_steps(train_dataloader, batch_size), 1)
+
+      iters_to_process = min(iters_per_epoch, num_batches - iters_processed)
+      iters_processed += iters_to_process
+
+      progress_bar = tqdm(range(iters_to_process), desc=description) if (tqdm is not None and rank == 0) \
+        else _NoBar()
+      steps_this_epoch = 0
+      last_loss = None
+      num_items = None
+      for batch_itr, (pool, tpool, row0, rows, global_rows) in iterator:
+        self.engine.train_step(pool, row0, rows, target_pool=tpool, global_rows=global_rows)
+        steps_this_epoch += 1
+        num_items = (tpool or pool).n
+        if steps_this_epoch % refresh_every == 0:
+          last_loss = float(self.engine.losses(1)[0])
+          progress_bar.set_postfix(loss=last_loss, num_items=num_items, refresh=False)
+        progress_bar.update()
+        if batch_itr % iters_per_epoch == 0:
+          break
+
+      if steps_this_epoch:
+        last_loss = float(self.engine.losses(1)[0])
+      self.last_epoch_losses = self.engine.losses(steps_this_epoch).numpy() if steps_this_epoch else np.zeros(0)
+      postfix = {'loss': last_loss}
+      if eval_freq > 0 and epoch % eval_freq == 0 and val_dataloader is not None:
+        val_loss = self._validate(val_dataloader)
+        postfix['val_loss'] = val_loss
+        if metrics is not None and eval_num_recommendations is not None:
+          results = self._evaluate(val_dataloader.dataset,
+                                   num_recommendations=eval_num_recommendations,
+                                   metrics=metrics, batch_size=eval_batch_size,
+                                   num_users=eval_num_users)
+          for metric in results:
+            postfix[str(metric)] = np.mean(results[metric])
+
+      progress_bar.set_postfix(postfix)
+      progress_bar.close()
+
+      if model_checkpoint_prefix and rank == 0 and \
+          ((checkpoint_freq > 0 and epoch % checkpoint_freq == 0) or epoch == num_epochs):
+        self.save_state(model_checkpoint_prefix)
+
+  def _validate(self, val_dataloader):
+    """Average loss over the validation batches (reference model.py:439-452); forward + loss kernels only."""
+    self.model.eval()
+    total_loss = 0.0
+    num_batches = 1
+    ds = val_dataloader.dataset
+    csr, tcsr = ds.device_csr(), ds.device_target_csr()
+    itr = 0
+    for index in val_dataloader.pools():
+      pool = collate_pool(csr, index, val_dataloader.negative_sampling)
+      tpool = collate_pool(tcsr, index, val_dataloader.negative_sampling) if tcsr is not None else None
+      for off in range(0, pool.num_rows, val_dataloader.batch_size):
+        rows = min(val_dataloader.batch_size, pool.num_rows - off)
+        total_loss += self.engine.eval_loss(pool, off, rows, target_pool=tpool)
+        itr += 1
+        num_batches = itr
+    return total_loss / num_batches
+
+  def predict(self, users_interactions, return_input=False):
+    """
+    Predicts the user interactions with all items (reference model.py:487-511).
+
+    Returns:
+      if ``return_input`` is ``True`` a tuple of the predictions and the dense input batch, otherwise the
+      predictions.
+    """
+    if self.model is None:
+      raise Exception('Model not initialized.')
+    self.__require_cuda()
+    self.model.eval()
+    batch_collator = BatchCollator(batch_size=len(users_interactions.users), negative_sampling=False)
+    batch = batch_collator.collate(users_interactions)[0]
+    input_dense = torch.zeros(tuple(batch.size), dtype=torch.float32, device=batch.values.device)
+    idx = batch.indices
+    if idx.numel():
+      input_dense[idx[0], idx[1]] = batch.values
+    output = self.model(input_dense, input_users=batch.users)
+    return (output, input_dense) if return_input else output
+
+  def _evaluate(self, eval_dataset, num_recommendations, metrics, batch_size=1, num_users=None):
+    if self.model is None:
+      raise Exception('Model not initialized')
+    from .metrics import RecommenderEvaluator, InferenceRecommender
+    self.model.eval()
+    recommender = InferenceRecommender(self, num_recommendations)
+    evaluator = RecommenderEvaluator(recommender, metrics)
+    return evaluator.evaluate(eval_dataset, batch_size=batch_size, num_users=num_users)
+
+  def recommend(self, users_interactions, num_recommendations):
+    """
+    Generate list of recommendations for each user in ``users_interactions`` (reference model.py:525-544).
+
+    Returns:
+      list: list of recommended items for each user in users_interactions.
+    """
+    output, input = self.predict(users_interactions, return_input=True)
+    # Set input items output to -inf so that they don't get recommended
+    output = output.clone()
+    output[input > 0] = - float('inf')
+    top_output, top_ind = torch.topk(output, num_recommendations, dim=1, sorted=True)
+    return top_ind.tolist()
+
+  def evaluate(self, eval_dataset, num_recommendations, metrics, batch_size=1, num_users=None):
+    """Evaluates the current model given an evaluation dataset (reference model.py:546-559)."""
+    results = self._evaluate(eval_dataset, num_recommendations, metrics,
+                             batch_size=batch_size, num_users=num_users)
+    for metric in results:
+      log.info('{}: {}'.format(metric, np.mean(results[metric])))
+    return results

@@ -1,0 +1,114 @@
+"""Train-step parity (SURVEY.md §8d parity gates): loss, gradient norms and post-step parameters of the CUDA
+step against (1) golden vectors recorded from the unmodified reference and (2) the CPU oracle on seeded
+synthetic inputs.  Tolerance: 1e-3 relative on loss and gradient L2 norms (north_star); the SIMT engine, which
+shares every kernel except the tensor-core GEMM, is held to the same bar so a failure can be localised."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import recoder_oracle as O
+from recoder_b200 import _native
+from recoder_b200.data import collate_pool
+from recoder_b200.synth import synthetic_csr
+from tests.golden_util import Golden
+from tests.gpu_util import compact_oracle_grads, device_dataset, make_engine, make_model, rel_err
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = [pytest.param(_native.GEMM_SIMT, id='simt'), pytest.param(_native.GEMM_TCGEN05, id='tcgen05')]
+GOLDEN_CASES = ['ae_mse_adam', 'ae_mse_conf_ratings', 'ae_nll_adam', 'ae_bce_adam', 'ae_mse_sgd',
+                'ae_nll_sparseadam', 'ae_mse_noneg', 'ae_nll_pool', 'mf_mse_adam', 'mf_nll_sgd']
+
+# bf16 operands (2^-9 relative rounding, zero mean) against an fp32 reference
+TOL_LOSS = 1e-3
+TOL_GRAD = 1e-3   # on L2 norms
+TOL_GRAD_ELEM = 2e-2  # relative Frobenius distance of whole gradient blocks
+TOL_PARAM = 5e-2  # Adam turns sign flips of near-zero gradients into +-lr moves; grads are the tight gate
+
+
+@pytest.mark.parametrize('engine', ENGINES)
+@pytest.mark.parametrize('name', GOLDEN_CASES)
+def test_step_matches_reference_golden(name, engine):
+  g = Golden(name)
+  m = g.meta
+  kind = m['model']
+  model = make_model(kind, m['num_items'], m['num_users'], m['hidden'], m['act'], g.init_params(), sparse=m['sparse'])
+  eng = make_engine(model, m['loss'], m['loss_params'].get('confidence', 0.0), m['opt'], m['lr'], m['wd'], engine)
+  ds = device_dataset(g.indptr, g.indices, g.data, m['num_items'])
+  csr = ds.device_csr()
+  for users, steps in g.pools():
+    pool = collate_pool(csr, users, m['neg'])
+    for k, s in enumerate(steps):
+      ref = g.step(s)
+      row0 = k * m['batch']
+      rows = ref['size'][0]
+      eng.train_step(pool, row0, rows)
+      loss = float(eng.losses(1)[0])
+      assert loss == pytest.approx(ref['loss'], rel=TOL_LOSS), 'loss step %d' % s
+      items = ref['items'] if ref['items'] is not None else np.arange(m['num_items'])
+      last = {k2: (v.detach().cpu().numpy() if torch.is_tensor(v) else v) for k2, v in eng.last.items()}
+      if kind == 'ae':
+        pairs = [('dWe', ref['grads'][O.AE_EN_W][items]), ('dWd', ref['grads'][O.AE_DE_W][items]),
+                 ('dbe', ref['grads'][O.AE_EN_B]), ('dbd', ref['grads'][O.AE_DE_B][items])]
+      else:
+        pairs = [('dV', ref['grads'][O.MF_ITEM_W][items]), ('dbias', ref['grads'][O.MF_BIAS][items]),
+                 ('dU', ref['grads'][O.MF_USER_W][ref['users']])]
+      for key, want in pairs:
+        got = last[key]
+        nw = np.linalg.norm(want)
+        assert np.linalg.norm(got) == pytest.approx(nw, rel=TOL_GRAD, abs=1e-7), '%s norm step %d' % (key, s)
+        assert rel_err(got, want) < TOL_GRAD_ELEM, '%s step %d' % (key, s)
+      state = {n: p.detach().cpu().numpy() for n, p in model.named_parameters()}
+      for n in g.param_names:
+        assert rel_err(state[n], ref['params'][n]) < TOL_PARAM, '%s after step %d' % (n, s)
+
+
+CONFIGS = [
+  # kind, U, I, nnz, H, B, loss, act
+  ('ae', 2000, 5000, 50, 128, 256, 'mse', 'tanh'),        # BASELINE config C1 shape
+  ('ae', 3000, 26744, 144, 200, 500, 'mse', 'tanh'),      # C2 shape (H=200 is not a multiple of 16/64)
+  ('ae', 4096, 20000, 100, 512, 1024, 'logloss', 'tanh'), # C3-like
+  ('mf', 3000, 20000, 100, 256, 512, 'mse', 'none'),      # C4-like
+  ('ae', 777, 3001, 30, 72, 333, 'logistic', 'sigmoid'),  # ragged everything
+]
+
+
+@pytest.mark.parametrize('engine', ENGINES)
+@pytest.mark.parametrize('kind,U,I,nnz,H,B,loss,act', CONFIGS)
+def test_step_matches_oracle(kind, U, I, nnz, H, B, loss, act, engine):
+  if engine == _native.GEMM_SIMT and B * I > 3e7:
+    pytest.skip('SIMT validation engine is too slow for this size')
+  indptr, indices, data = synthetic_csr(U, I, nnz, seed=11)
+  if kind == 'ae':
+    params = O.init_ae_params(I, [H], seed=3)
+    params[O.AE_EN_B] = torch.randn(H) * 0.05
+    params[O.AE_DE_B] = torch.randn(I) * 0.05
+  else:
+    params = O.init_mf_params(I, U, H, seed=3)
+    params[O.MF_BIAS] = torch.randn(I) * 0.05
+  lr, wd = 1e-3, 2e-5
+  tr = O.OracleTrainer(kind, params, loss=loss, confidence=0.0, optimizer='adam', lr=lr, weight_decay=wd,
+                       activation=act)
+  model = make_model(kind, I, U, [H] if kind == 'ae' else H, act, {k: v.numpy() for k, v in params.items()})
+  eng = make_engine(model, loss, 0.0, 'adam', lr, wd, engine)
+  ds = device_dataset(indptr, indices, data, I)
+  order = np.random.default_rng(5).permutation(U)
+  steps = 3
+  for s in range(steps):
+    users = order[s * B:(s + 1) * B]
+    pool = collate_pool(ds.device_csr(), users, True)
+    ob = O.collate(indptr, indices, data, I, users, B, True)[0]
+    assert np.array_equal(pool.items.cpu().numpy(), ob.items)
+    oloss, ograds = tr.step(ob)
+    eng.train_step(pool, 0, len(users))
+    loss_gpu = float(eng.losses(1)[0])
+    assert loss_gpu == pytest.approx(oloss, rel=TOL_LOSS), 'loss step %d' % s
+    want = compact_oracle_grads(kind, ograds, ob)
+    for key, w in want.items():
+      got = eng.last[key].detach().cpu().numpy()
+      assert np.linalg.norm(got) == pytest.approx(np.linalg.norm(w), rel=TOL_GRAD), '%s norm step %d' % (key, s)
+      assert rel_err(got, w) < TOL_GRAD_ELEM, '%s step %d' % (key, s)
+  state = {n: p.detach().cpu().numpy() for n, p in model.named_parameters()}
+  ost = tr.state()
+  for n in ost:
+    assert rel_err(state[n], ost[n]) < TOL_PARAM, n
