@@ -131,17 +131,30 @@ int rcd_decoder_fwd(const uint16_t* Zb, int ldzb, const uint16_t* Wg, int ldw, c
  *     (recoder/model.py:483-484) and autograd's backward through them.
  *     rcd_softmax_lse : lse[r] = logsumexp_c O[r,c] from the K4 partials (NLL only); adds sum_r lse[r]*row_sum[r]
  *                       * inv_b to loss_acc.
- *     rcd_loss_grad   : dO[r,c] (bf16) from O (bf16) and the sparse target given as the slice CSC,
- *                       db[c] = sum_r dO[r,c] (fp32, deterministic), loss_acc[0] += loss/B (double).
- *        MSE      dO = 2*(1+conf*[t>0])*(o-t)*inv_b
- *        NLL      dO = (exp(o-lse_r)*row_sum_r - t)*inv_b
- *        LOGISTIC dO = (sigmoid(o)-t)*inv_b
+ *     rcd_loss_grad   : dL/dO from O (bf16) and the sparse target given as the slice CSC, produced as
+ *                       a DENSE part dO[r,c] (bf16, the target-free formula at every position) plus an fp32
+ *                       SPARSE part csc_corr[e] at the stored targets (exact minus dense), so that the large,
+ *                       clustered entries at the non-zeros never get quantised to bf16:
+ *        MSE      dense 2*o*inv_b               sparse 2*((w-1)*o - w*t)*inv_b, w = 1+conf*[t>0]
+ *        NLL      dense exp(o-lse_r)*S_r*inv_b  sparse -t*inv_b
+ *        LOGISTIC dense sigmoid(o)*inv_b        sparse -t*inv_b
+ *                       db[c] = sum_r dL/dO[r,c] (fp32, deterministic), loss_acc[0] += loss/B (double).
+ *     The sparse part enters the backward GEMMs through rcd_sparse_dgrad (rows of dZ) and
+ *     rcd_csc_rows_accumulate (rows of dW).
  * ------------------------------------------------------------------------------------------------------- */
 int rcd_softmax_lse(const float* stat_max, const float* stat_sum, int n_tiles, int rows, const float* row_sum,
                     float inv_b, float* lse, double* loss_acc, void* stream);
 int rcd_loss_grad(const uint16_t* O_bf16, int ldo, int rows, int n, int loss, float confidence, float inv_b,
                   const float* lse, const float* row_sum, const int32_t* csc_ptr, const int32_t* csc_row,
-                  const float* csc_val, uint16_t* dO, int lddo, float* db, double* loss_acc, void* stream);
+                  const float* csc_val, uint16_t* dO, int lddo, float* csc_corr, float* db, double* loss_acc,
+                  void* stream);
+/* out[r, 0:H] = sum_{p in row r} sparse(r,p) * W[raw_items[p], :]  (W = fp32 master table; out fp32 [rows, ldp]) */
+int rcd_sparse_dgrad(const float* W, int H, const int32_t* row_ptr, const int32_t* raw_items, const int32_t* cols,
+                     const float* vals, const uint16_t* O_bf16, int ldo, int row0, int rows, int loss,
+                     float confidence, float inv_b, float* out, int ldp, void* stream);
+/* out[c, 0:H] += sum_{e in column c} csc_coef[e] * M[csc_row[e], :]   (M fp32 [rows, H], out fp32 [n, H]) */
+int rcd_csc_rows_accumulate(const float* M, int H, const int32_t* csc_ptr, const int32_t* csc_row,
+                            const float* csc_coef, int n, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K6  decoder backward GEMMs — replace autograd's `mm` nodes of F.linear.

@@ -38,7 +38,10 @@ _SIGNATURES = {
   'rcd_decoder_fwd': (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P]),
   'rcd_softmax_lse': (c_int, [_P, _P, c_int, c_int, _P, c_float, _P, _P, _P]),
   'rcd_loss_grad': (c_int, [_P, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P, c_int, _P, _P,
-                            _P]),
+                            _P, _P]),
+  'rcd_sparse_dgrad': (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, _P, c_int,
+                               _P]),
+  'rcd_csc_rows_accumulate': (c_int, [_P, c_int, _P, _P, _P, c_int, _P, _P]),
   'rcd_decoder_dgrad_splits': (c_int, [c_int, c_int, c_int]),
   'rcd_decoder_dgrad': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
   'rcd_decoder_wgrad': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),

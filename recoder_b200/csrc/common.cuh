@@ -77,6 +77,18 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act) {
   }
 }
 
+// fp32 sparse part of dL/dlogits at a stored target t: exact gradient minus the dense (target = 0) formula.
+//   MSE      2*w*(o-t)/B - 2*o/B = 2*((w-1)*o - w*t)/B,  w = 1 + conf*[t>0]   (recoder/losses.py:44-47)
+//   NLL      (p*S - t)/B - p*S/B = -t/B                                       (recoder/losses.py:69-71)
+//   LOGISTIC (sigmoid(o) - t)/B - sigmoid(o)/B = -t/B
+__device__ __forceinline__ float sparse_corr(int loss, float o, float t, float conf, float inv_b) {
+  if (loss == RCD_LOSS_MSE) {
+    const float w = 1.0f + (t > 0.f ? conf : 0.f);
+    return 2.0f * inv_b * ((w - 1.0f) * o - w * t);
+  }
+  return -t * inv_b;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

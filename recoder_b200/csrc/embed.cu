@@ -120,7 +120,8 @@ template <int VEC, int NV>
 static __global__ void __launch_bounds__(kEmbThreads)
     k_encoder_wgrad(const float* __restrict__ dA, int H, const int32_t* __restrict__ csc_ptr,
                     const int32_t* __restrict__ csc_row, const float* __restrict__ csc_val,
-                    const float* __restrict__ row_inv_norm, int row0, int n, int tpr, float* __restrict__ out) {
+                    const float* __restrict__ row_inv_norm, int row0, int n, int tpr, float* __restrict__ out,
+                    int accumulate) {
   const int rpb = kEmbThreads / tpr;
   const int c = blockIdx.x * rpb + threadIdx.x / tpr;
   const int t = threadIdx.x % tpr;
@@ -131,12 +132,47 @@ static __global__ void __launch_bounds__(kEmbThreads)
   for (int k = 0; k < NV; ++k) acc[k].zero();
   seg_accumulate<VEC, NV>(acc, dA, H, t, tpr, s, e, [&](int p, int& idx, float& cf) {
     idx = csc_row[p];
-    cf = csc_val[p] * row_inv_norm[row0 + idx];
+    cf = row_inv_norm ? csc_val[p] * row_inv_norm[row0 + idx] : csc_val[p];
   });
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     int h = (t + k * tpr) * VEC;
-    if (h < H) acc[k].store(out + (size_t)c * H + h);
+    if (h < H) {
+      if (accumulate) {
+        Vec<VEC> prev;
+        prev.load(out + (size_t)c * H + h);
+        acc[k].fma(1.0f, prev);
+      }
+      acc[k].store(out + (size_t)c * H + h);
+    }
+  }
+}
+
+// out[r,:] = sum_p corr(r,p) * W[raw_items[p],:]  — the fp32 sparse part of dZ = dO @ W (see loss.cu)
+template <int VEC, int NV>
+static __global__ void __launch_bounds__(kEmbThreads)
+    k_sparse_dgrad(const float* __restrict__ W, int H, const int32_t* __restrict__ row_ptr,
+                   const int32_t* __restrict__ raw_items, const int32_t* __restrict__ cols,
+                   const float* __restrict__ vals, const uint16_t* __restrict__ O, int ldo, int row0, int rows,
+                   int loss, float conf, float inv_b, int tpr, float* __restrict__ out, int ldp) {
+  const int rpb = kEmbThreads / tpr;
+  const int r = blockIdx.x * rpb + threadIdx.x / tpr;
+  const int t = threadIdx.x % tpr;
+  if (r >= rows) return;
+  const int s = row_ptr[row0 + r], e = row_ptr[row0 + r + 1];
+  Vec<VEC> acc[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc[k].zero();
+  seg_accumulate<VEC, NV>(acc, W, H, t, tpr, s, e, [&](int p, int& idx, float& cf) {
+    idx = raw_items[p];
+    float o = 0.f;
+    if (loss == RCD_LOSS_MSE) o = __uint_as_float((uint32_t)O[(size_t)r * ldo + cols[p]] << 16);
+    cf = sparse_corr(loss, o, vals[p], conf, inv_b);
+  });
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    int h = (t + k * tpr) * VEC;
+    if (h < H) acc[k].store(out + (size_t)r * ldp + h);
   }
 }
 
@@ -289,10 +325,53 @@ RCD_EXPORT int rcd_ae_encoder_wgrad(const float* dA, int H, const int32_t* csc_p
   const int blocks = rcd_div_up(n, kEmbThreads / tpr);
   if (vec)
     RCD_DISPATCH_NV(k_encoder_wgrad, 4, units, tpr, <<<blocks, kEmbThreads, 0, st>>>(
-        dA, H, csc_ptr, csc_row, csc_val, row_inv_norm, row0, n, tpr, dWe_rows));
+        dA, H, csc_ptr, csc_row, csc_val, row_inv_norm, row0, n, tpr, dWe_rows, 0));
   else
     RCD_DISPATCH_NV(k_encoder_wgrad, 1, units, tpr, <<<blocks, kEmbThreads, 0, st>>>(
-        dA, H, csc_ptr, csc_row, csc_val, row_inv_norm, row0, n, tpr, dWe_rows));
+        dA, H, csc_ptr, csc_row, csc_val, row_inv_norm, row0, n, tpr, dWe_rows, 0));
+  RCD_LAUNCH_CHECK();
+  return RCD_OK;
+}
+
+RCD_EXPORT int rcd_csc_rows_accumulate(const float* M, int H, const int32_t* csc_ptr, const int32_t* csc_row,
+                                       const float* csc_coef, int n, float* out, void* stream) {
+  RCD_CHECK_ARG(M && csc_ptr && csc_row && csc_coef && out, "null pointer");
+  RCD_CHECK_ARG(n > 0 && H > 0, "bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(M) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const int units = vec ? H / 4 : H;
+  const int tpr = pick_tpr(units);
+  const int blocks = rcd_div_up(n, kEmbThreads / tpr);
+  if (vec)
+    RCD_DISPATCH_NV(k_encoder_wgrad, 4, units, tpr, <<<blocks, kEmbThreads, 0, st>>>(
+        M, H, csc_ptr, csc_row, csc_coef, nullptr, 0, n, tpr, out, 1));
+  else
+    RCD_DISPATCH_NV(k_encoder_wgrad, 1, units, tpr, <<<blocks, kEmbThreads, 0, st>>>(
+        M, H, csc_ptr, csc_row, csc_coef, nullptr, 0, n, tpr, out, 1));
+  RCD_LAUNCH_CHECK();
+  return RCD_OK;
+}
+
+RCD_EXPORT int rcd_sparse_dgrad(const float* W, int H, const int32_t* row_ptr, const int32_t* raw_items,
+                                const int32_t* cols, const float* vals, const uint16_t* O_bf16, int ldo, int row0,
+                                int rows, int loss, float confidence, float inv_b, float* out, int ldp,
+                                void* stream) {
+  RCD_CHECK_ARG(W && row_ptr && raw_items && cols && vals && out, "null pointer");
+  RCD_CHECK_ARG(loss != RCD_LOSS_MSE || O_bf16, "MSE needs the logits");
+  RCD_CHECK_ARG(rows > 0 && H > 0 && row0 >= 0 && ldp >= H, "bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (H % 4 == 0) && (ldp % 4 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const int units = vec ? H / 4 : H;
+  const int tpr = pick_tpr(units);
+  const int blocks = rcd_div_up(rows, kEmbThreads / tpr);
+  if (vec)
+    RCD_DISPATCH_NV(k_sparse_dgrad, 4, units, tpr, <<<blocks, kEmbThreads, 0, st>>>(
+        W, H, row_ptr, raw_items, cols, vals, O_bf16, ldo, row0, rows, loss, confidence, inv_b, tpr, out, ldp));
+  else
+    RCD_DISPATCH_NV(k_sparse_dgrad, 1, units, tpr, <<<blocks, kEmbThreads, 0, st>>>(
+        W, H, row_ptr, raw_items, cols, vals, O_bf16, ldo, row0, rows, loss, confidence, inv_b, tpr, out, ldp));
   RCD_LAUNCH_CHECK();
   return RCD_OK;
 }

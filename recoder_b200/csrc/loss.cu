@@ -3,8 +3,12 @@
 // rcd_loss_grad is a column-strip streaming kernel (HBM-bound: reads B*n*2 B of logits, writes B*n*2 B of
 // dlogits).  A block owns 64 columns (one 128-byte line of bf16 per row) and sweeps all rows:
 //   phase 1: dense formula with target 0 for every element, fp32 column sums and loss partial in registers;
-//   phase 2: the strip's non-zero targets (contiguous range of the slice CSC) are patched exactly, one warp per
-//            column, with the column-sum / loss deltas reduced in a fixed order (deterministic results).
+//   phase 2: for the strip's non-zero targets (contiguous range of the slice CSC) the exact-minus-dense
+//            correction is computed in fp32, one warp per column, and written to csc_corr; column-sum and loss
+//            deltas are reduced in a fixed order (deterministic results).  dO itself keeps the dense value: the
+//            large, clustered gradient entries at the non-zeros would otherwise be quantised to bf16 with a
+//            systematic bias; they are applied in fp32 by the sparse kernels (rcd_sparse_dgrad,
+//            rcd_csc_rows_accumulate), i.e. dL/dO = bf16 dense part + fp32 sparse part.
 // This replaces recoder/losses.py:43-47,68-71, BCEWithLogitsLoss (recoder/model.py:91), the /B at
 // recoder/model.py:483-484 and autograd's backward through them; the sparse target never gets densified
 // (recoder/model.py:457-458,473-476 materialise it as a dense [B,n] fp32 matrix).
@@ -54,7 +58,7 @@ static __global__ void __launch_bounds__(kStripWarps * 32)
     k_loss_grad(const uint16_t* __restrict__ O, int ldo, int rows, int n, float conf, float inv_b,
                 const float* __restrict__ lse, const float* __restrict__ row_sum, const int32_t* __restrict__ csc_ptr,
                 const int32_t* __restrict__ csc_row, const float* __restrict__ csc_val, uint16_t* __restrict__ dO,
-                int lddo, float* __restrict__ db, double* __restrict__ loss_acc) {
+                int lddo, float* __restrict__ csc_corr, float* __restrict__ db, double* __restrict__ loss_acc) {
   __shared__ float s_col[kStripWarps][kStripCols];
   __shared__ float s_loss[kStripWarps];
   __shared__ float s_delta[kStripCols];
@@ -88,7 +92,7 @@ static __global__ void __launch_bounds__(kStripWarps * 32)
   s_col[w][2 * lane + 1] = cs1;
   lsum = warp_sum(lsum);
   if (lane == 0) s_loss[w] = lsum;
-  __syncthreads();  // also orders the dO stores of phase 1 before the patches of phase 2
+  __syncthreads();
 
   // phase 2: exact values at the stored targets; warp w owns columns w, w+8, ... of the strip
   float ldelta = 0.f;
@@ -109,8 +113,9 @@ static __global__ void __launch_bounds__(kStripWarps * 32)
         float d_dense, l_dense, d, l;
         dense_term<LOSS>(o, inv_b, l_r, rs_r, d_dense, l_dense);
         exact_term<LOSS>(o, t, conf, inv_b, l_r, rs_r, d, l);
-        reinterpret_cast<__nv_bfloat16*>(dO)[(size_t)r * lddo + cc] = __float2bfloat16_rn(d);
-        dsum += d - d_dense;
+        const float corr = sparse_corr(LOSS, o, t, conf, inv_b);  // == d - d_dense in exact arithmetic
+        csc_corr[p] = corr;
+        dsum += corr;
         ldelta += l - l_dense;
       }
     }
@@ -203,9 +208,9 @@ RCD_EXPORT int rcd_softmax_lse(const float* stat_max, const float* stat_sum, int
 
 RCD_EXPORT int rcd_loss_grad(const uint16_t* O_bf16, int ldo, int rows, int n, int loss, float confidence,
                              float inv_b, const float* lse, const float* row_sum, const int32_t* csc_ptr,
-                             const int32_t* csc_row, const float* csc_val, uint16_t* dO, int lddo, float* db,
-                             double* loss_acc, void* stream) {
-  RCD_CHECK_ARG(O_bf16 && csc_ptr && csc_row && csc_val && dO && db && loss_acc, "null pointer");
+                             const int32_t* csc_row, const float* csc_val, uint16_t* dO, int lddo, float* csc_corr,
+                             float* db, double* loss_acc, void* stream) {
+  RCD_CHECK_ARG(O_bf16 && csc_ptr && csc_row && csc_val && dO && csc_corr && db && loss_acc, "null pointer");
   RCD_CHECK_ARG(rows > 0 && n > 0, "bad shape");
   RCD_CHECK_ARG(ldo % 2 == 0 && lddo % 2 == 0 && ldo >= n && lddo >= n, "ldo/lddo must be even and >= n");
   RCD_CHECK_ARG(loss != RCD_LOSS_NLL || (lse && row_sum), "NLL needs lse and row_sum");
@@ -215,16 +220,16 @@ RCD_EXPORT int rcd_loss_grad(const uint16_t* O_bf16, int ldo, int rows, int n, i
   switch (loss) {
     case RCD_LOSS_MSE:
       k_loss_grad<RCD_LOSS_MSE><<<blocks, threads, 0, st>>>(O_bf16, ldo, rows, n, confidence, inv_b, lse, row_sum,
-                                                             csc_ptr, csc_row, csc_val, dO, lddo, db, loss_acc);
+                                                             csc_ptr, csc_row, csc_val, dO, lddo, csc_corr, db, loss_acc);
       break;
     case RCD_LOSS_NLL:
       k_loss_grad<RCD_LOSS_NLL><<<blocks, threads, 0, st>>>(O_bf16, ldo, rows, n, confidence, inv_b, lse, row_sum,
-                                                             csc_ptr, csc_row, csc_val, dO, lddo, db, loss_acc);
+                                                             csc_ptr, csc_row, csc_val, dO, lddo, csc_corr, db, loss_acc);
       break;
     case RCD_LOSS_LOGISTIC:
       k_loss_grad<RCD_LOSS_LOGISTIC><<<blocks, threads, 0, st>>>(O_bf16, ldo, rows, n, confidence, inv_b, lse,
-                                                                  row_sum, csc_ptr, csc_row, csc_val, dO, lddo, db,
-                                                                  loss_acc);
+                                                                  row_sum, csc_ptr, csc_row, csc_val, dO, lddo,
+                                                                  csc_corr, db, loss_acc);
       break;
     default:
       rcd_set_error("rcd_loss_grad: unknown loss id %d", loss);

@@ -250,16 +250,27 @@ class TrainEngine:
     if nll:
       call('rcd_softmax_lse', ptr(smax), ptr(ssum), n_tiles, rows, ptr(row_sum), inv_b, ptr(lse), ptr(loss_slot))
     csc_ptr, csc_row, csc_val = csc
+    corr = b.get('csc_corr', max(csc_row.numel(), 1), torch.float32)
     call('rcd_loss_grad', ptr(O), ldn, rows, n, self.loss_id, self.confidence, inv_b, ptr(lse), ptr(row_sum),
-         ptr(csc_ptr), ptr(csc_row), ptr(csc_val), ptr(dO), ldn, ptr(db_out), ptr(loss_slot))
-    return dO, ldn
+         ptr(csc_ptr), ptr(csc_row), ptr(csc_val), ptr(dO), ldn, ptr(corr), ptr(db_out), ptr(loss_slot))
+    return dO, ldn, O, corr
 
-  def _dgrad(self, dO, ldn, Wg, ldh, rows, n, H, Zf32, act, dA, db):
+  def _dgrad(self, dO, ldn, O, Wg, ldh, W_master, tpool, row0, rows, n, H, inv_b, Zf32, act, dA, db):
+    """dZ = dense part (tcgen05 split-K GEMM over bf16 dO) + sparse part (fp32, master table) -> dA, db."""
     b = self.buf
     splits = self.lib.rcd_decoder_dgrad_splits(rows, n, H)
-    partials = b.get('dz_partials', splits * rows * H, torch.float32)
+    partials = b.get('dz_partials', (splits + 1) * rows * H, torch.float32)
     call('rcd_decoder_dgrad', ptr(dO), ldn, ptr(Wg), ldh, rows, n, H, splits, ptr(partials), H, self.gemm)
-    call('rcd_dz_act', ptr(partials), splits, H, ptr(Zf32), rows, H, act, ptr(dA), ptr(db))
+    sparse_slot = partials[splits * rows * H:]
+    call('rcd_sparse_dgrad', ptr(W_master), H, ptr(tpool.row_ptr), ptr(tpool.raw_items), ptr(tpool.cols),
+         ptr(tpool.vals), ptr(O), ldn, row0, rows, self.loss_id, self.confidence, inv_b, ptr(sparse_slot), H)
+    call('rcd_dz_act', ptr(partials), splits + 1, H, ptr(Zf32), rows, H, act, ptr(dA), ptr(db))
+
+  def _wgrad(self, dO, ldn, Zb, ldh, Zf32, csc, corr, rows, n, H, dW):
+    """dW rows = dense part (tcgen05 GEMM) + sparse part (fp32 rank-1 updates at the stored targets)."""
+    call('rcd_decoder_wgrad', ptr(dO), ldn, ptr(Zb), ldh, rows, n, H, ptr(dW), H, self.gemm)
+    csc_ptr, csc_row, _ = csc
+    call('rcd_csc_rows_accumulate', ptr(Zf32), H, ptr(csc_ptr), ptr(csc_row), ptr(corr), n, ptr(dW))
 
   def _reduce_slab(self, slab, loss_slot):
     """Data-parallel exchange: ONE all-reduce over the gradient slab; the loss rides in its last 2 floats
@@ -309,13 +320,14 @@ class TrainEngine:
     call('rcd_ae_encoder_fwd', ptr(We), H, ptr(be), ptr(pool.row_ptr), ptr(pool.raw_items), ptr(pool.vals),
          ptr(pool.row_inv_norm), row0, rows, self.act, ptr(Z), ptr(Zb), ldh)
 
-    dO, ldn = self._decoder_and_loss(Zb, ldh, Wg, bg, rows, n, H, inv_b, tpool, row0, csc_t, loss_slot, dbd)
+    dO, ldn, O, corr = self._decoder_and_loss(Zb, ldh, Wg, bg, rows, n, H, inv_b, tpool, row0, csc_t, loss_slot,
+                                              dbd)
     if not train:
       return
 
     dA = b.get('dA', rows * H, torch.float32)
-    self._dgrad(dO, ldn, Wg, ldh, rows, n, H, Z, self.act, dA, dbe)
-    call('rcd_decoder_wgrad', ptr(dO), ldn, ptr(Zb), ldh, rows, n, H, ptr(dWd), H, self.gemm)
+    self._dgrad(dO, ldn, O, Wg, ldh, Wd, tpool, row0, rows, n, H, inv_b, Z, self.act, dA, dbe)
+    self._wgrad(dO, ldn, Zb, ldh, Z, csc_t, corr, rows, n, H, dWd)
     csc_ptr, csc_row, csc_val = csc_in
     call('rcd_ae_encoder_wgrad', ptr(dA), H, ptr(csc_ptr), ptr(csc_row), ptr(csc_val), ptr(pool.row_inv_norm), row0,
          n_in, ptr(dWe))
@@ -329,7 +341,7 @@ class TrainEngine:
     else:
       self.opt.step_param(en_name, dWe, H, pos=pool.pos, ids=pool.items_buf, n_ids=n_in)
       self.opt.step_param(de_name, dWd, H, pos=tpool.pos, ids=tpool.items_buf, n_ids=n)
-    self.opt.step_param(enb_name, dbe, H)
+    self.opt.step_param(enb_name, dbe, 1)
     self.opt.step_param(deb_name, dbd, 1, pos=tpool.pos)
 
   # ------------------------------------------------------------------------------------------------------
@@ -364,11 +376,12 @@ class TrainEngine:
     Ub = b.get('Zb', rows * ldd, torch.bfloat16)
     call('rcd_gather_rows', ptr(U), D, ptr(users), rows, self.act, ptr(Ub), ldd, ptr(Ue))
 
-    dO, ldn = self._decoder_and_loss(Ub, ldd, Vg, bg, rows, n, D, inv_b, tpool, row0, csc, loss_slot, dbias)
+    dO, ldn, O, corr = self._decoder_and_loss(Ub, ldd, Vg, bg, rows, n, D, inv_b, tpool, row0, csc, loss_slot,
+                                              dbias)
     if not train:
       return
-    self._dgrad(dO, ldn, Vg, ldd, rows, n, D, Ue, self.act, dU, None)
-    call('rcd_decoder_wgrad', ptr(dO), ldn, ptr(Ub), ldd, rows, n, D, ptr(dV), D, self.gemm)
+    self._dgrad(dO, ldn, O, Vg, ldd, V, tpool, row0, rows, n, D, inv_b, Ue, self.act, dU, None)
+    self._wgrad(dO, ldn, Ub, ldd, Ue, csc, corr, rows, n, D, dV)
 
     self._reduce_slab(slab, loss_slot)
     self.last = {'n': n, 'dV': dV.view(n, D), 'dbias': dbias, 'dU': dU.view(rows, D)}
