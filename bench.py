@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""Benchmark of the Recoder train-step hot path on B200 (BASELINE.json metric: users/sec of the train step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c3]
+
+A step = GPU collate of one batch of users + forward + loss + backward + optimizer update, through the public
+`recoder_b200.model.Recoder.train()` call.  Prints ONE JSON line (rank 0):
+  value     users/sec with the interaction matrix resident in HBM (whole job, all ranks)
+  e2e       the same through `Recoder.train()` with the matrix in HOST memory: every step stages its rows in pinned
+            memory, copies them H2D and reads the loss back D2H inside the timed region
+  roofline  the dominant kernel of the step against the measured peak (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle port of the reference's step on this box's host cores (rank 0, N=1 only)
+`--impl reference` times that CPU port alone (the reference is a pure-Python library: there is nothing to compile
+into oracle/_ref, so the arm runs the oracle restatement, which executes the same torch CPU ops).
+Under torchrun (N>1) one process per GPU, NCCL; timing = CUDA events, max over ranks, barrier + synchronize on
+both sides of the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+  # BASELINE.json configs: users, items, nnz/user, model, width, loss, per-GPU batch, activation
+  'c1': dict(users=10_000, items=5_000, nnz=50, model='ae', width=128, loss='mse', batch=256,
+             desc='C1 synthetic 10Kx5K, 50 nnz/user, AE[128], MSE'),
+  'c2': dict(users=138_493, items=26_744, nnz=144, model='ae', width=200, loss='mse', batch=500,
+             desc='C2 MovieLens-20M shaped synthetic 138Kx27K, AE[200], MSE'),
+  'c3': dict(users=1_000_000, items=200_000, nnz=100, model='ae', width=512, loss='logloss', batch=2048,
+             desc='C3 synthetic 1Mx200K, ~100 nnz/user, AE[512], multinomial-NLL + mini-batch negative sampling'),
+  'c4': dict(users=1_000_000, items=200_000, nnz=100, model='mf', width=256, loss='mse', batch=2048,
+             desc='C4 synthetic 1Mx200K, MatrixFactorization(256), MSE'),
+  'c5': dict(users=5_000_000, items=500_000, nnz=100, model='ae', width=1024, loss='logloss', batch=2048,
+             desc='C5 synthetic 5Mx500K, AE[1024], multinomial-NLL'),
+}
+LR = 1e-3
+
+
+def log(*a):
+  print(*a, file=sys.stderr, flush=True)
+
+
+def load_peaks():
+  """Measured roofline denominators (driver-written); fallback figures from B200_PROFILING.md otherwise."""
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  try:
+    with open(path) as fh:
+      p = json.load(fh)
+    return dict(hbm=float(p['hbm_gbs']), tensor_burst=float(p['bf16_tflops']),
+                tensor_sustained=float(p.get('bf16_tflops_sustained', p['bf16_tflops'])), source='measured')
+  except Exception:
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source='fallback')
+
+
+def make_matrix(w, users_override=None):
+  from recoder_b200.synth import synthetic_csr
+  U = users_override or w['users']
+  t0 = time.time()
+  indptr, indices, data = synthetic_csr(U, w['items'], w['nnz'], seed=1234)
+  log('[bench] synthetic CSR %d x %d, nnz=%d (%.1fs)' % (U, w['items'], len(indices), time.time() - t0))
+  return U, indptr, indices, data
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's step (collate + __compute_loss + backward + optimizer step)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_threads():
+  try:
+    return len(os.sched_getaffinity(0))
+  except Exception:
+    return os.cpu_count() or 1
+
+
+def run_cpu_port(w, U, indptr, indices, data, steps, warmup, batch, budget_s):
+  """Times `steps` reference train steps on `batch` users each with the CPU oracle; shrinks the per-step sample if
+  the run would exceed `budget_s`.  Returns (users_per_sec, ms_per_step, batch_used, cores, steps_done)."""
+  import torch
+  from oracle import recoder_oracle as O
+  from recoder_b200.synth import epoch_user_order
+  cores = cpu_threads()
+  torch.set_num_threads(cores)
+  I, H = w['items'], w['width']
+  if w['model'] == 'ae':
+    params = O.init_ae_params(I, [H], seed=0)
+    act = 'tanh'
+  else:
+    params = O.init_mf_params(I, U, H, seed=0)
+    act = 'none'
+  tr = O.OracleTrainer(w['model'], params, loss=w['loss'], optimizer='adam', lr=LR, weight_decay=0.0, activation=act)
+  order = epoch_user_order(U, 1)
+
+  def one_step(s, b):
+    users = order[(s * b) % max(U - b, 1):][:b]
+    ob = O.collate(indptr, indices, data, I, users, b, True)[0]
+    tr.step(ob)
+    return ob.size[1]
+
+  # calibrate on one full-size step, then pick the per-step sample so that the whole run fits the budget
+  t0 = time.perf_counter()
+  n_full = one_step(0, batch)
+  t_full = time.perf_counter() - t0
+  total = steps + warmup
+  b = batch
+  while b > 128 and t_full * (b / batch) * total > budget_s:
+    b //= 2
+  log('[bench/cpu] calibration step: B=%d n=%d %.2fs -> per-step sample B=%d' % (batch, n_full, t_full, b))
+  for s in range(max(warmup - 1, 0)):
+    one_step(s + 1, b)
+  t0 = time.perf_counter()
+  for s in range(steps):
+    one_step(s + warmup, b)
+  dt = time.perf_counter() - t0
+  return steps * b / dt, dt / steps * 1e3, b, cores, steps
+
+
+def reference_arm(args, w):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  U, indptr, indices, data = make_matrix(w, args.users)
+  ups, ms, b, cores, _ = run_cpu_port(w, U, indptr, indices, data, args.steps, args.warmup, args.batch or w['batch'],
+                                      budget_s=args.cpu_budget)
+  sample = ('oracle/recoder_oracle.py (CPU port of recoder/data.py collate + model.py __compute_loss + autograd + '
+            'torch.optim.Adam, same torch CPU ops as the reference), %d users per step on the full matrix' % b)
+  line = {
+    'impl': 'reference', 'metric': 'users/sec (train step)', 'value': ups, 'unit': 'users/s', 'n_gpus': args.gpus,
+    'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+    'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+    'config': workload_config(args, w, U, b, 1),
+    'cpu_baseline': {'value': ups, 'unit': 'users/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+    'e2e': {'value': ups, 'unit': 'users/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+  }
+  print(json.dumps(line), flush=True)
+
+
+def workload_config(args, w, U, batch, world):
+  return {'workload': w['desc'], 'users': U, 'items': w['items'], 'nnz_per_user': w['nnz'], 'model': w['model'],
+          'width': w['width'], 'loss': w['loss'], 'optimizer': 'adam (dense, torch.optim.Adam semantics)',
+          'batch_per_gpu': batch, 'global_batch': batch * world, 'negative_sampling': True,
+          'parallelism': 'dp%d' % world,
+          'l2': 'per-step working set (embedding tables + Adam state + logits) is larger than the 126 MB L2'}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+  FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+            'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+            'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, gpu_index):
+    self.gpu = gpu_index
+    self.proc = None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits',
+                                    '-lms', '100', '-i', str(self.gpu)], stdout=subprocess.PIPE,
+                                   stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+      self.proc = None
+
+  def stop(self):
+    if self.proc is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    time.sleep(0.15)
+    self.proc.terminate()
+    try:
+      out, _ = self.proc.communicate(timeout=5)
+    except Exception:
+      self.proc.kill()
+      out = ''
+    sm, mx, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for ln in out.strip().splitlines():
+      parts = [p.strip() for p in ln.split(',')]
+      if len(parts) < 8:
+        continue
+      try:
+        sm.append(float(parts[1]))
+        mx.append(float(parts[2]))
+      except ValueError:
+        continue
+      for nm, val in zip(names, parts[4:8]):
+        if val.lower().startswith('active'):
+          reasons.add(nm)
+    return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+            'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def kernel_work(name, w, rows, n, n_in, nnz_rows, tables):
+  """Algorithmic work of ONE optimizer step for entry point `name`: ('hbm', bytes) or ('tensor', flops).
+  Figures are the per-unit numbers of DESIGN.md §4."""
+  H, I = w['width'], w['items']
+  dense = 2.0 * rows * n * H
+  if name in ('rcd_decoder_fwd', 'rcd_decoder_dgrad', 'rcd_decoder_wgrad'):
+    return 'tensor', dense
+  if name == 'rcd_adam_step':
+    params, grads = tables
+    return 'hbm', 24.0 * params + 4.0 * grads
+  if name == 'rcd_loss_grad':
+    return 'hbm', 4.0 * rows * n            # read bf16 logits, write bf16 dlogits
+  if name == 'rcd_gather_rows':
+    return 'hbm', n * H * (4.0 + 2.0)       # fp32 master rows in, bf16 operand out
+  if name == 'rcd_ae_encoder_fwd':
+    return 'hbm', nnz_rows * H * 4.0 + rows * H * 6.0
+  if name == 'rcd_ae_encoder_wgrad':
+    return 'hbm', nnz_rows * H * 4.0 + n_in * H * 4.0
+  if name == 'rcd_csc_rows_accumulate':
+    return 'hbm', nnz_rows * H * 4.0 + 2 * n * H * 4.0
+  if name == 'rcd_sparse_dgrad':
+    return 'hbm', nnz_rows * H * 4.0 + rows * H * 4.0
+  if name == 'rcd_dz_act':
+    return 'hbm', None
+  return 'hbm', None
+
+
+def b200_arm(args, w):
+  import torch
+  import torch.distributed as dist
+  from recoder_b200 import _native
+  from recoder_b200 import data as rdata
+  from recoder_b200.data import RecommendationDataset
+  from recoder_b200.model import Recoder
+  from recoder_b200.nn import DynamicAutoencoder, MatrixFactorization
+  from recoder_b200.synth import epoch_user_order, to_scipy
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if world != args.gpus:
+    log('[bench] warning: --gpus %d but WORLD_SIZE=%d (launch with torchrun for N>1); using %d' %
+        (args.gpus, world, world))
+  torch.cuda.set_device(local_rank)
+  if world > 1:
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+  lib = _native.load()
+  peaks = load_peaks()
+  K, W = args.steps, max(args.warmup, 3)
+  B = args.batch or w['batch']
+  U, indptr, indices, data = make_matrix(w, args.users)
+  I, H = w['items'], w['width']
+  matrix = to_scipy(indptr, indices, data, I)
+  assert (K + W) * B * world <= U, 'not enough users for %d steps' % (K + W)
+
+  def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+      torch.cuda.synchronize()
+
+  def run(device_resident, sync_loss, profile):
+    """One `Recoder.train()` call of W+K steps; returns (elapsed_ms max over ranks, stats)."""
+    torch.manual_seed(0)
+    if w['model'] == 'ae':
+      model = DynamicAutoencoder(hidden_layers=[H], activation_type='tanh')
+    else:
+      model = MatrixFactorization(embedding_size=H, activation_type='none')
+    trainer = Recoder(model=model, use_cuda=True, optimizer_type='adam', loss=w['loss'])
+    ds = RecommendationDataset(matrix, device_resident=device_resident)
+    st = {'n': [], 'launch0': 0, 'launch1': 0, 'bytes0': None, 'bytes1': None, 'clocks': None, 'warm': {},
+          'dominant': None}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    if profile:
+      _native.PROFILE = 'all'
+      _native.TIMINGS.clear()
+
+    def cb(step):
+      if step > W:
+        st['n'].append(trainer.engine.last.get('n', 0))
+      if step == W:
+        torch.cuda.synchronize()
+        if profile:
+          # per entry point: mean device time per step over the warm-up steps (first step excluded)
+          warm = {}
+          for name, evs in _native.TIMINGS.items():
+            per_step = len(evs) // W if W else 0
+            use = evs[per_step:] if per_step and len(evs) > per_step else evs
+            tot = sum(a.elapsed_time(b) for a, b in use)
+            warm[name] = tot / max(W - 1, 1)
+          st['warm'] = warm
+          cand = {k: v for k, v in warm.items() if k != 'rcd_collate'}
+          st['dominant'] = max(cand, key=cand.get) if cand else None
+          _native.PROFILE = {st['dominant']} if st['dominant'] else None
+          _native.TIMINGS.clear()
+        barrier()
+        sampler.start()
+        st['launch0'] = lib.rcd_launch_count()
+        st['bytes0'] = dict(rdata.TRANSFER_BYTES)
+        ev0.record()
+      elif step == W + K:
+        ev1.record()
+        torch.cuda.synchronize()
+        st['launch1'] = lib.rcd_launch_count()
+        st['bytes1'] = dict(rdata.TRANSFER_BYTES)
+        st['clocks'] = sampler.stop()
+        barrier()
+
+    trainer.train(ds, lr=LR, weight_decay=0, num_epochs=1, iters_per_epoch=W + K, batch_size=B,
+                  negative_sampling=True, user_order=lambda e: epoch_user_order(U, e), step_callback=cb,
+                  sync_loss_every_step=sync_loss)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+      t = torch.tensor([ms], device='cuda', dtype=torch.float64)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      ms = float(t.item())
+    st['dom_ms'] = None
+    if profile and st['dominant'] and _native.TIMINGS.get(st['dominant']):
+      evs = _native.TIMINGS[st['dominant']]
+      st['dom_ms'] = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+      st['dom_launches_per_step'] = len(evs) / K
+    _native.PROFILE = None
+    _native.TIMINGS.clear()
+    st['loss'] = float(trainer.engine.losses(1)[0])
+    st['params'] = sum(p.numel() for p in model.parameters())
+    del trainer, model, ds
+    torch.cuda.empty_cache()
+    return ms, st
+
+  # ---- leg 1: matrix resident in HBM (value) ------------------------------------------------------------------
+  ms_dev, s_dev = run(device_resident=True, sync_loss=False, profile=not args.no_profile)
+  # ---- leg 2: host-resident matrix, H2D staging + loss readback every step (e2e) ------------------------------
+  if args.skip_e2e:
+    ms_e2e, s_e2e = ms_dev, {'bytes0': {'h2d': 0, 'd2h': 0}, 'bytes1': {'h2d': 0, 'd2h': 0}}
+  else:
+    ms_e2e, s_e2e = run(device_resident=False, sync_loss=True, profile=False)
+
+  users_per_step = B * world
+  value = K * users_per_step / (ms_dev / 1e3)
+  e2e = K * users_per_step / (ms_e2e / 1e3)
+  n_avg = float(np.mean(s_dev['n'])) if s_dev['n'] else 0.0
+  nnz_rows = float(B * (len(indices) / U))
+
+  # ---- roofline of the dominant kernel ------------------------------------------------------------------------
+  dom = s_dev['dominant']
+  n_tab = 2 if w['model'] == 'ae' else 1
+  if w['model'] == 'ae':
+    grads = 2 * n_avg * H + n_avg + H
+  else:
+    grads = n_avg * H + n_avg + users_per_step * H
+  kinds = {}
+  for name, ms in sorted(s_dev['warm'].items(), key=lambda kv: -kv[1]):
+    bound, work = kernel_work(name, w, B, n_avg, n_avg, nnz_rows, (s_dev['params'], grads))
+    entry = {'ms_per_step': round(ms, 4), 'bound': bound}
+    if work:
+      if bound == 'tensor':
+        entry['achieved_tflops'] = round(work / (ms * 1e-3) / 1e12, 2)
+        entry['frac_of_measured_sustained'] = round(entry['achieved_tflops'] / peaks['tensor_sustained'], 4)
+      else:
+        entry['achieved_gbs'] = round(work / (ms * 1e-3) / 1e9, 1)
+        entry['frac_of_measured'] = round(entry['achieved_gbs'] / peaks['hbm'], 4)
+    kinds[name] = entry
+  roofline = None
+  if dom and s_dev['dom_ms']:
+    bound, work = kernel_work(dom, w, B, n_avg, n_avg, nnz_rows, (s_dev['params'], grads))
+    lps = s_dev.get('dom_launches_per_step', 1.0)
+    if work:
+      per_launch = work / lps
+      sec = s_dev['dom_ms'] * 1e-3
+      if bound == 'tensor':
+        ach, peak, unit = per_launch / sec / 1e12, peaks['tensor_sustained'], 'TFLOP/s'
+      else:
+        ach, peak, unit = per_launch / sec / 1e9, peaks['hbm'], 'GB/s'
+      roofline = {'kernel': dom, 'bound': 'tensor' if bound == 'tensor' else 'hbm', 'achieved': round(ach, 2),
+                  'peak': peak, 'unit': unit, 'frac': round(ach / peak, 4), 'traffic': None,
+                  'peak_source': peaks['source'] + (' (sustained)' if bound == 'tensor' else ''),
+                  'launches_per_step': lps, 'avg_launch_ms': round(s_dev['dom_ms'], 4)}
+
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return
+
+  # ---- CPU baseline beside it (rank 0, N=1 only) ----------------------------------------------------------------
+  cpu = None
+  if world == 1 and not args.no_cpu_baseline:
+    try:
+      ups, ms_cpu, b_cpu, cores, nsteps = run_cpu_port(w, U, indptr, indices, data, steps=2, warmup=1, batch=B,
+                                                       budget_s=args.cpu_budget / 6.0)
+      cpu = {'value': ups, 'unit': 'users/s', 'cores': cores, 'kind': 'port', 'ms_per_step': ms_cpu,
+             'sample': '%d timed steps of %d users each on the same matrix/model (oracle/recoder_oracle.py, torch CPU '
+                       'fp32, %d threads)' % (nsteps, b_cpu, cores)}
+    except Exception as exc:  # pragma: no cover
+      cpu = {'value': None, 'unit': 'users/s', 'cores': cpu_threads(), 'kind': 'port', 'sample': 'failed: %r' % exc}
+
+  h2d = (s_e2e['bytes1']['h2d'] - s_e2e['bytes0']['h2d']) / K
+  d2h = (s_e2e['bytes1']['d2h'] - s_e2e['bytes0']['d2h']) / K
+  line = {
+    'metric': 'users/sec (train step)', 'value': value, 'unit': 'users/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+    'ms_per_step': ms_dev / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+    'dtype': 'bf16 tensor-core operands, fp32 accumulate / master weights / optimizer', 'data': 'synthetic',
+    'config': workload_config(args, w, U, B, world),
+    'e2e': {'value': e2e, 'unit': 'users/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+            'ms_per_step': ms_e2e / K},
+    'gpu_launches': int(s_dev['launch1'] - s_dev['launch0']),
+    'clocks': s_dev['clocks'],
+    'roofline': roofline,
+    'cpu_baseline': cpu,
+    'items_per_batch': n_avg,
+    'final_loss': s_dev['loss'],
+    'kernels': kinds,
+  }
+  print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=30)
+  ap.add_argument('--warmup', type=int, default=5)
+  ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  ap.add_argument('--config', default='c3', choices=sorted(WORKLOADS))
+  ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (default: the config\'s)')
+  ap.add_argument('--users', type=int, default=0, help='use a user prefix of the matrix (0 = all)')
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--skip-e2e', action='store_true', help='profiling runs only: skip the host-staged leg')
+  ap.add_argument('--no-profile', action='store_true', help='no CUDA-event kernel breakdown during warm-up')
+  ap.add_argument('--cpu-budget', type=float, default=150.0, help='seconds the CPU arm may take')
+  args = ap.parse_args()
+  w = WORKLOADS[args.config]
+  if args.impl == 'reference':
+    reference_arm(args, w)
+  else:
+    b200_arm(args, w)
+
+
+if __name__ == '__main__':
+  main()

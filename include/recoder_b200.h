@@ -51,6 +51,18 @@ int rcd_abi_version(void);
 const char* rcd_last_error(void);
 /* number of SMs of the current device (148 on B200); <0 on error */
 int rcd_device_sms(void);
+/* number of CUDA kernels this library has launched in the calling process (bench.py's `gpu_launches`) */
+long long rcd_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K0  host staging — replaces the SciPy fancy row indexing of RecommendationDataset._extract
+ *     (recoder/data.py:66-81) when the interaction matrix stays in HOST memory: copies the CSR rows `users`
+ *     (stored order) into caller-provided (pinned) buffers that are then shipped H2D and collated by K1 with
+ *     users = 0..P-1.  ALL pointers are HOST pointers.  Returns the pool's nnz, or a negative RCD_ERR_*.
+ * ------------------------------------------------------------------------------------------------------- */
+long long rcd_host_stage_rows(const int64_t* indptr_host, const int32_t* indices_host, const float* data_host,
+                              const int64_t* users_host, int pool_rows, long long num_users, long long capacity,
+                              int64_t* row_ptr_out_host, int32_t* indices_out_host, float* data_out_host);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K1  collate — replaces RecommendationDataset.__getitem__/_extract (recoder/data.py:50-83) and

@@ -23,6 +23,8 @@ _SIGNATURES = {
   'rcd_abi_version': (c_int, []),
   'rcd_last_error': (ctypes.c_char_p, []),
   'rcd_device_sms': (c_int, []),
+  'rcd_launch_count': (c_longlong, []),
+  'rcd_host_stage_rows': (c_longlong, [_P, _P, _P, _P, c_int, c_longlong, c_longlong, _P, _P, _P]),
   'rcd_collate_scratch_bytes': (c_size_t, [c_int, c_int]),
   'rcd_collate': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                           c_size_t, _P]),
@@ -103,8 +105,21 @@ def check(status, what):
     raise RuntimeError('recoder_b200: %s failed (status %d): %s' % (what, status, msg))
 
 
+# Optional CUDA-event timing of entry points (bench.py): PROFILE is None, 'all', or a set of entry-point names;
+# TIMINGS maps entry-point name -> list of (start_event, end_event) recorded on the current stream.
+PROFILE = None
+TIMINGS = {}
+
+
 def call(name, *args):
   """Calls an `int`-status entry point on the current stream (stream appended automatically)."""
   lib = load()
-  status = getattr(lib, name)(*args, stream_ptr())
+  if PROFILE is not None and (PROFILE == 'all' or name in PROFILE):
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    status = getattr(lib, name)(*args, stream_ptr())
+    end.record()
+    TIMINGS.setdefault(name, []).append((start, end))
+  else:
+    status = getattr(lib, name)(*args, stream_ptr())
   check(status, name)

@@ -246,6 +246,7 @@ RCD_EXPORT int rcd_collate(const int64_t* indptr, const int32_t* indices, const 
   RCD_LAUNCH_CHECK();
   RCD_CUDA(exclusive_scan_i32(row_len, P, row_ptr, nullptr, scan_tmp, st));
   k_set_nnz<<<1, 1, 0, st>>>(row_ptr, P, counts);
+  RCD_LAUNCH_CHECK();
   if (negative_sampling) {
     RCD_CUDA(exclusive_scan_i32(flag, I, rank, counts, scan_tmp, st));
     k_compact_items<<<rcd_div_up(I, 256), 256, 0, st>>>(flag, rank, I, items, pos);

@@ -29,7 +29,13 @@ void rcd_set_error(const char* fmt, ...);
     }                                                                                \
   } while (0)
 
-#define RCD_LAUNCH_CHECK() RCD_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this macro; the counter feeds bench.py's `gpu_launches`
+extern unsigned long long g_rcd_launches;
+#define RCD_LAUNCH_CHECK()             \
+  do {                                 \
+    ++g_rcd_launches;                  \
+    RCD_CUDA(cudaGetLastError());      \
+  } while (0)
 
 static inline int rcd_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -3,7 +3,10 @@
 
 #include "common.cuh"
 
+#include <string.h>
+
 static thread_local char g_err[512] = "";
+unsigned long long g_rcd_launches = 0;
 
 void rcd_set_error(const char* fmt, ...) {
   va_list ap;
@@ -35,4 +38,40 @@ RCD_EXPORT int rcd_device_sms(void) {
     return RCD_ERR_CUDA;
   }
   return v;
+}
+
+RCD_EXPORT long long rcd_launch_count(void) { return (long long)g_rcd_launches; }
+
+// Host-side staging of one pool for the host-resident data path: copies the CSR rows `users` of a HOST matrix
+// into (pinned) staging buffers in stored order — the work scipy's fancy row indexing does at
+// recoder/data.py:66-81.  row_ptr_out int64[P+1] is the pool's own indptr.  Returns the pool's nnz (<0 on error).
+RCD_EXPORT long long rcd_host_stage_rows(const int64_t* indptr_host, const int32_t* indices_host,
+                                         const float* data_host, const int64_t* users_host, int pool_rows,
+                                         long long num_users, long long capacity, int64_t* row_ptr_out_host,
+                                         int32_t* indices_out_host, float* data_out_host) {
+  if (!indptr_host || !indices_host || !data_host || !users_host || !row_ptr_out_host || !indices_out_host ||
+      !data_out_host || pool_rows <= 0) {
+    rcd_set_error("rcd_host_stage_rows: invalid argument");
+    return RCD_ERR_INVALID;
+  }
+  long long at = 0;
+  row_ptr_out_host[0] = 0;
+  for (int r = 0; r < pool_rows; ++r) {
+    const int64_t u = users_host[r];
+    if (u < 0 || u >= num_users) {
+      rcd_set_error("rcd_host_stage_rows: user index %lld out of range", (long long)u);
+      return RCD_ERR_INVALID;
+    }
+    const int64_t s = indptr_host[u], e = indptr_host[u + 1];
+    const long long len = (long long)(e - s);
+    if (at + len > capacity) {
+      rcd_set_error("rcd_host_stage_rows: staging capacity %lld exceeded", capacity);
+      return RCD_ERR_INVALID;
+    }
+    memcpy(indices_out_host + at, indices_host + s, (size_t)len * sizeof(int32_t));
+    memcpy(data_out_host + at, data_host + s, (size_t)len * sizeof(float));
+    at += len;
+    row_ptr_out_host[r + 1] = at;
+  }
+  return at;
 }

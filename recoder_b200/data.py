@@ -26,6 +26,10 @@ def _isintlike(x):
   return isinstance(x, np.ndarray) and x.ndim == 0 and np.issubdtype(x.dtype, np.integer)
 
 
+# bytes moved over PCIe by the data path since import (bench.py reports them per step)
+TRANSFER_BYTES = {'h2d': 0, 'd2h': 0}
+
+
 class DeviceCSR:
   """A CSR matrix resident in HBM: indptr int64[U+1], indices int32[nnz], data fp32[nnz]."""
 
@@ -43,6 +47,64 @@ class DeviceCSR:
 
   def pool_nnz(self, users: np.ndarray) -> int:
     return int((self.indptr_host[users + 1] - self.indptr_host[users]).sum())
+
+
+class HostStagedCSR:
+  """A CSR matrix kept in HOST memory (the reference's layout: the dataset is a SciPy matrix and every batch
+  is shipped to the device, recoder/model.py:457-462).  `stage(users)` copies the pool's rows into pinned
+  staging buffers (K0, `rcd_host_stage_rows`) and sends them H2D; the result is a pool-local DeviceCSR whose
+  row r is user `users[r]`."""
+
+  RING = 2
+
+  def __init__(self, matrix: sparse.csr_matrix, device=None):
+    _native.require_cuda()
+    self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    self.shape = matrix.shape
+    self.indptr_host = np.ascontiguousarray(matrix.indptr, dtype=np.int64)
+    self.indices_host = np.ascontiguousarray(matrix.indices, dtype=np.int32)
+    self.data_host = np.ascontiguousarray(matrix.data, dtype=np.float32)
+    self._ring = [None] * self.RING
+    self._turn = 0
+
+  def _slot(self, P, nnz):
+    i = self._turn % self.RING
+    self._turn += 1
+    slot = self._ring[i]
+    if slot is None or slot['ptr'].numel() < P + 1 or slot['idx'].numel() < nnz:
+      cap_p, cap_n = int(P * 1.25) + 1, int(nnz * 1.25) + 16
+      slot = {'ptr': torch.empty(cap_p, dtype=torch.int64).pin_memory(),
+              'idx': torch.empty(cap_n, dtype=torch.int32).pin_memory(),
+              'val': torch.empty(cap_n, dtype=torch.float32).pin_memory(),
+              'event': None}
+      self._ring[i] = slot
+    elif slot['event'] is not None:
+      slot['event'].synchronize()  # the previous H2D copy out of this slot has finished
+    return slot
+
+  def stage(self, users: np.ndarray):
+    lib = _native.load()
+    P = int(users.size)
+    nnz = int((self.indptr_host[users + 1] - self.indptr_host[users]).sum())
+    slot = self._slot(P, max(nnz, 1))
+    got = lib.rcd_host_stage_rows(self.indptr_host.ctypes.data, self.indices_host.ctypes.data,
+                                  self.data_host.ctypes.data, users.ctypes.data, P, int(self.shape[0]),
+                                  int(slot['idx'].numel()), slot['ptr'].data_ptr(), slot['idx'].data_ptr(),
+                                  slot['val'].data_ptr())
+    if got < 0:
+      _native.check(int(got), 'rcd_host_stage_rows')
+    mini = DeviceCSR.__new__(DeviceCSR)
+    mini.device = self.device
+    mini.shape = (P, self.shape[1])
+    mini.indptr_host = slot['ptr'][:P + 1].numpy()
+    mini.indptr = slot['ptr'][:P + 1].to(self.device, non_blocking=True)
+    mini.indices = slot['idx'][:max(nnz, 1)].to(self.device, non_blocking=True)
+    mini.data = slot['val'][:max(nnz, 1)].to(self.device, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    slot['event'] = ev
+    TRANSFER_BYTES['h2d'] += (P + 1) * 8 + 2 * max(nnz, 1) * 4
+    return mini
 
 
 class UsersInteractions:
@@ -91,9 +153,11 @@ class RecommendationDataset:
       matrix. Mainly used for evaluation, representing the items to recommend.
   """
 
-  def __init__(self, interactions_matrix, target_interactions_matrix=None):
+  def __init__(self, interactions_matrix, target_interactions_matrix=None, device_resident=True):
     self.interactions_matrix = interactions_matrix
     self.target_interactions_matrix = target_interactions_matrix
+    # extension: False keeps the matrix in host memory and stages every pool over PCIe (HostStagedCSR)
+    self.device_resident = device_resident
     self.users = np.arange(self.interactions_matrix.shape[0])
     self.items = np.arange(self.interactions_matrix.shape[1])
     self._device_csr = None
@@ -104,14 +168,16 @@ class RecommendationDataset:
 
   def device_csr(self):
     if self._device_csr is None:
-      self._device_csr = DeviceCSR(self.interactions_matrix)
+      cls = DeviceCSR if self.device_resident else HostStagedCSR
+      self._device_csr = cls(self.interactions_matrix)
     return self._device_csr
 
   def device_target_csr(self):
     if self.target_interactions_matrix is None:
       return None
     if self._device_target_csr is None:
-      self._device_target_csr = DeviceCSR(self.target_interactions_matrix)
+      cls = DeviceCSR if self.device_resident else HostStagedCSR
+      self._device_target_csr = cls(self.target_interactions_matrix)
     return self._device_target_csr
 
   def __getitem__(self, index):
@@ -185,17 +251,25 @@ class PoolBatch:
     return self.items_buf[:self.n]
 
 
-def collate_pool(csr: DeviceCSR, users, negative_sampling: bool) -> PoolBatch:
-  """Runs K1 on the rows `users` of `csr` and returns the pool's compute layout."""
+def collate_pool(csr, users, negative_sampling: bool) -> PoolBatch:
+  """Runs K1 on the rows `users` of `csr` (DeviceCSR, or HostStagedCSR: staged over PCIe first) and returns the
+  pool's compute layout."""
   users = np.ascontiguousarray(np.asarray(users).reshape(-1), dtype=np.int64)
   assert users.size > 0
   assert users.min() >= 0 and users.max() < csr.shape[0], 'user index out of range'
   dev = csr.device
   P, I = int(users.size), int(csr.shape[1])
+  users_dev = torch.from_numpy(users).to(dev, non_blocking=True)
+  TRANSFER_BYTES['h2d'] += P * 8
+  rows_dev = users_dev
+  if isinstance(csr, HostStagedCSR):
+    csr = csr.stage(users)
+    users = np.arange(P, dtype=np.int64)
+    rows_dev = torch.arange(P, dtype=torch.int64, device=dev)
   lens = csr.indptr_host[users + 1] - csr.indptr_host[users]
   nnz = int(lens.sum())
   assert nnz < 2 ** 31, 'pool too large'
-  pb = PoolBatch(torch.from_numpy(users).to(dev), P, I, negative_sampling)
+  pb = PoolBatch(users_dev, P, I, negative_sampling)
   row_ptr_host = np.zeros(P + 1, dtype=np.int64)
   np.cumsum(lens, out=row_ptr_host[1:])
   pb.row_ptr_host = row_ptr_host
@@ -213,11 +287,12 @@ def collate_pool(csr: DeviceCSR, users, negative_sampling: bool) -> PoolBatch:
   sbytes = lib.rcd_collate_scratch_bytes(P, I)
   scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
   _native.call('rcd_collate', _native.ptr(csr.indptr), _native.ptr(csr.indices), _native.ptr(csr.data),
-               _native.ptr(pb.users), P, I, int(bool(negative_sampling)), cap, _native.ptr(pb.row_ptr),
+               _native.ptr(rows_dev), P, I, int(bool(negative_sampling)), cap, _native.ptr(pb.row_ptr),
                _native.ptr(pb.raw_items), _native.ptr(pb.cols), _native.ptr(pb.vals), _native.ptr(pb.row_inv_norm),
                _native.ptr(pb.row_sum), _native.ptr(pb.pos), _native.ptr(pb.items_buf), _native.ptr(pb.counts),
                _native.ptr(scratch), sbytes)
   counts = pb.counts.cpu()  # the one host sync of the collate: n decides every downstream shape
+  TRANSFER_BYTES['d2h'] += 8
   pb.n = int(counts[0])
   pb.nnz = int(counts[1])
   assert pb.nnz == nnz, 'device/host nnz mismatch'

@@ -26,6 +26,33 @@ def _round_up(x, m):
   return (x + m - 1) // m * m
 
 
+def reduce_slab(slab, loss_slot, pg):
+  """Data-parallel exchange: ONE sum all-reduce over the contiguous fp32 gradient slab of a step.
+  The step loss (float64 [1]) rides in the slab's last two floats as a hi/lo split, so nothing is lost to fp32
+  and no second collective is needed.  Works on any backend (NCCL on the GPUs, gloo in the CPU tests)."""
+  import torch.distributed as dist
+  tail = slab[-2:]
+  hi = loss_slot.to(torch.float32)
+  lo = (loss_slot - hi.to(torch.float64)).to(torch.float32)
+  tail[0:1].copy_(hi)
+  tail[1:2].copy_(lo)
+  dist.all_reduce(slab, op=dist.ReduceOp.SUM, group=pg)
+  loss_slot.copy_(tail[0:1].to(torch.float64) + tail[1:2].to(torch.float64))
+
+
+def shard_rows(pool_rows, global_step_rows, world, rank):
+  """Row ranges of one collated pool for data-parallel training: the pool is cut into global steps of
+  `global_step_rows` rows (the reference's `batch_size` slices, recoder/data.py:231-249) and every global step
+  into `world` equal contiguous blocks.  Yields (row0, rows, global_rows) for `rank`; a ragged tail keeps
+  floor(rows/world) rows per rank (the remainder rows are dropped so that every rank runs the same shapes)."""
+  for goff in range(0, pool_rows, global_step_rows):
+    grows = min(global_step_rows, pool_rows - goff)
+    per = grows // world
+    if per == 0:
+      continue
+    yield goff + rank * per, per, per * world
+
+
 class _Buffers:
   """Grow-only named device buffers (a step never allocates once shapes have been seen)."""
 
@@ -175,6 +202,7 @@ class TrainEngine:
     self.lib = _native.load()
     self.tile_n = self.lib.rcd_decoder_tile_n()
     self.last = {}                # views of the last step's compact gradients (tests / telemetry)
+    self._loss_host = None
 
   # ------------------------------------------------------------------------------------------------------
   def _loss_slot(self):
@@ -188,6 +216,17 @@ class TrainEngine:
     k = min(last_k, self.steps_done, self.LOSS_RING)
     idx = [(self.steps_done - k + j) % self.LOSS_RING for j in range(k)]
     return self.loss_ring[torch.tensor(idx, device=self.device, dtype=torch.long)].cpu() if k else torch.zeros(0)
+
+  def last_loss_to_host(self):
+    """Loss of the last step read back through a pinned 8-byte buffer (the reference's `loss.item()`)."""
+    if self._loss_host is None:
+      self._loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+    i = (self.steps_done - 1) % self.LOSS_RING
+    self._loss_host.copy_(self.loss_ring[i:i + 1], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    from . import data as _data
+    _data.TRANSFER_BYTES['d2h'] += 8
+    return float(self._loss_host[0])
 
   def _world(self):
     if self.pg is None:
@@ -277,14 +316,7 @@ class TrainEngine:
     (hi/lo split of the double, so nothing is lost to fp32)."""
     if self.pg is None:
       return
-    import torch.distributed as dist
-    tail = slab[-2:]
-    hi = loss_slot.to(torch.float32)
-    lo = (loss_slot - hi.to(torch.float64)).to(torch.float32)
-    tail[0:1].copy_(hi)
-    tail[1:2].copy_(lo)
-    dist.all_reduce(slab, op=dist.ReduceOp.SUM, group=self.pg)
-    loss_slot.copy_(tail[0:1].to(torch.float64) + tail[1:2].to(torch.float64))
+    reduce_slab(slab, loss_slot, self.pg)
 
   # ------------------------------------------------------------------------------------------------------
   def _ae_step(self, pool, tpool, row0, rows, inv_b, loss_slot, train):

@@ -18,7 +18,7 @@ from torch.nn import BCEWithLogitsLoss
 from . import __version__
 from . import _native
 from .data import RecommendationDataLoader, BatchCollator, collate_pool
-from .engine import Optimizer, TrainEngine
+from .engine import Optimizer, TrainEngine, shard_rows
 from .losses import MSELoss, MultinomialNLLLoss
 from .nn import FactorizationModel
 
@@ -269,12 +269,15 @@ class Recoder(object):
             negative_sampling=False, num_sampling_users=0, num_data_workers=0,
             model_checkpoint_prefix=None, checkpoint_freq=0,
             eval_freq=0, eval_num_recommendations=None,
-            eval_num_users=None, metrics=None, eval_batch_size=None, user_order=None):
+            eval_num_users=None, metrics=None, eval_batch_size=None, user_order=None, step_callback=None,
+            sync_loss_every_step=False):
     """
     Trains the model (reference model.py:256-347; same arguments).  In data-parallel runs ``batch_size`` is the
     per-rank batch: one optimizer step consumes ``batch_size * world_size`` users and is numerically the
-    reference's step with that global batch size.  ``user_order`` (extension) is an ``epoch -> index array``
-    callable replacing the random sampler, used by tests and benchmarks.
+    reference's step with that global batch size.  Extensions used by tests and benchmarks: ``user_order`` is an
+    ``epoch -> index array`` callable replacing the random sampler; ``step_callback(step_count)`` is called after
+    every optimizer step has been enqueued; ``sync_loss_every_step=True`` reads the loss back to the host after
+    every step like the reference's ``loss.item()`` (model.py:404) instead of every 50 steps.
     """
     log.info('{} Mode'.format('CPU' if self.device.type == 'cpu' else 'GPU'))
     model_params = self.model.model_params()
@@ -315,6 +318,8 @@ class Recoder(object):
 
     self._base_lr = lr
     self._lr_milestones = sorted(lr_milestones) if lr_milestones is not None else None
+    self._step_callback = step_callback
+    self._sync_loss_every_step = bool(sync_loss_every_step)
 
     self._train(train_dataloader=train_dataloader,
                 val_dataloader=val_dataloader,
@@ -349,13 +354,8 @@ class Recoder(object):
     for index in dataloader.pools():
       pool = collate_pool(csr, index, dataloader.negative_sampling)
       tpool = collate_pool(tcsr, index, dataloader.negative_sampling) if tcsr is not None else None
-      P = pool.num_rows
-      for goff in range(0, P, gstep):
-        grows = min(gstep, P - goff)
-        per = grows // world
-        if per == 0:
-          continue  # ragged tail smaller than the number of ranks
-        yield pool, tpool, goff + rank * per, per, per * world
+      for row0, rows, global_rows in shard_rows(pool.num_rows, gstep, world, rank):
+        yield pool, tpool, row0, rows, global_rows
 
   def _train(self, train_dataloader, val_dataloader,
              num_epochs, current_epoch,
@@ -395,9 +395,14 @@ class Recoder(object):
         self.engine.train_step(pool, row0, rows, target_pool=tpool, global_rows=global_rows)
         steps_this_epoch += 1
         num_items = (tpool or pool).n
+        if self._sync_loss_every_step:
+          last_loss = self.engine.last_loss_to_host()
         if steps_this_epoch % refresh_every == 0:
-          last_loss = float(self.engine.losses(1)[0])
+          if not self._sync_loss_every_step:
+            last_loss = float(self.engine.losses(1)[0])
           progress_bar.set_postfix(loss=last_loss, num_items=num_items, refresh=False)
+        if self._step_callback is not None:
+          self._step_callback(self.engine.steps_done)
         progress_bar.update()
         if batch_itr % iters_per_epoch == 0:
           break

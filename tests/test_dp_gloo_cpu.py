@@ -1,0 +1,78 @@
+"""Host-side logic of the data-parallel path on CPU with the gloo backend, world_size 2: the row sharding of a
+global batch and the single slab all-reduce that also carries the float64 loss."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from recoder_b200.engine import reduce_slab, shard_rows
+
+
+def _free_port():
+  s = socket.socket()
+  s.bind(('127.0.0.1', 0))
+  p = s.getsockname()[1]
+  s.close()
+  return p
+
+
+def _worker(rank, world, port, out):
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  try:
+    g = torch.Generator().manual_seed(100 + rank)
+    slab = torch.randn(1001 + 4, generator=g, dtype=torch.float32)
+    mine = slab.clone()
+    loss = torch.tensor([1234.5678901234567 * (rank + 1) + 1e-9 * rank], dtype=torch.float64)
+    mine_loss = loss.clone()
+    reduce_slab(slab, loss, dist.group.WORLD)
+    gathered = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    losses = [torch.zeros_like(mine_loss) for _ in range(world)]
+    dist.all_gather(losses, mine_loss)
+    want = sum(gathered)[:-2]
+    ok_grad = torch.allclose(slab[:-2], want, rtol=0, atol=1e-6)
+    want_loss = float(sum(losses).item())
+    ok_loss = abs(float(loss.item()) - want_loss) <= 1e-9 * abs(want_loss)  # far below fp32 resolution (6e-8)
+    # sharding: both ranks agree on shapes, ranges are disjoint and contiguous
+    mine_rows = list(shard_rows(100, 32, world, rank))
+    out[rank] = (ok_grad, ok_loss, mine_rows)
+  finally:
+    dist.destroy_process_group()
+
+
+def test_slab_allreduce_and_sharding_world2():
+  world = 2
+  mgr = mp.Manager()
+  out = mgr.dict()
+  mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+  assert all(out[r][0] for r in range(world)), 'gradient slab sum mismatch'
+  assert all(out[r][1] for r in range(world)), 'loss hi/lo transport lost precision'
+  r0, r1 = out[0][2], out[1][2]
+  assert len(r0) == len(r1) == 4
+  for (a0, an, ag), (b0, bn, bg) in zip(r0, r1):
+    assert an == bn and ag == bg == an * 2
+    assert b0 == a0 + an
+  assert r0[0] == (0, 16, 32) and r0[-1] == (96, 2, 4)
+
+
+@pytest.mark.parametrize('P,g,world', [(2048, 2048, 1), (4096, 1024, 4), (1000, 512, 8), (7, 16, 8)])
+def test_shard_rows_partition(P, g, world):
+  covered = []
+  shapes = None
+  for rank in range(world):
+    rows = list(shard_rows(P, g, world, rank))
+    sig = [(n, gr) for _, n, gr in rows]
+    shapes = sig if shapes is None else shapes
+    assert sig == shapes
+    for r0, n, _ in rows:
+      covered.extend(range(r0, r0 + n))
+  assert len(covered) == len(set(covered))
+  assert all(0 <= r < P for r in covered)
+  dropped = P - len(covered)
+  assert dropped < world * ((P + g - 1) // g)
