@@ -88,13 +88,14 @@ int rcd_collate(const int64_t* indptr, const int32_t* indices, const float* data
 int rcd_collate_coo(const int32_t* row_ptr, const int32_t* cols, int row0, int rows, int64_t* indices_out,
                     void* stream);
 
-/* Column-major view (CSC) of one slice of the pool, used by the encoder weight gradient and by the
- * loss kernel: csc_ptr int32[n+1], csc_row int32[nnz_slice] (row relative to row0, ascending inside a column),
- * csc_val fp32[nnz_slice] (raw interaction value). */
+/* Column-major view (CSC) of one slice of the pool, used by the weight gradients:
+ * csc_ptr int32[n+1], csc_row int32[nnz_slice] (row relative to row0, ascending inside a column),
+ * csc_val fp32[nnz_slice] (raw interaction value), csc_src int32[nnz_slice] (position of the entry in the slice's
+ * CSR order, i.e. relative to row_ptr[row0]; optional). */
 size_t rcd_slice_csc_scratch_bytes(int n, int nnz_slice);
 int rcd_slice_csc(const int32_t* row_ptr, const int32_t* cols, const float* vals, int row0, int rows, int n,
-                  int32_t* csc_ptr, int32_t* csc_row, float* csc_val, void* scratch, size_t scratch_bytes,
-                  void* stream);
+                  int32_t* csc_ptr, int32_t* csc_row, float* csc_val, int32_t* csc_src, void* scratch,
+                  size_t scratch_bytes, void* stream);
 
 /* dense [rows, n] fp32 input (the `input` argument of FactorizationModel.forward, recoder/nn.py:49-65)
  * -> CSR of its non-zeros (row_ptr int32[rows+1], cols, vals, row_inv_norm, row_sum). */
@@ -125,69 +126,80 @@ int rcd_ae_encoder_fwd(const float* We, int H, const float* be, const int32_t* r
                        uint16_t* Zb, int ldzb, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
- * K4  decoder forward GEMM — replaces LinearEmbedding(de).forward `F.linear(z, W_d[items], b_d[items])`
- *     (recoder/nn.py:280; MF: recoder/nn.py:361).
- *     O[r, c] = sum_h Zb[r,h] * Wg[c,h] + bias[c]   (bf16 operands, fp32 accumulate in TMEM)
- *     stored as bf16 [rows, ldo]; when stat_max/stat_sum are non-NULL also per-(n-tile,row) online-softmax
- *     partials (max, sum exp) laid out [n_tiles, rows] for the multinomial NLL.
- *     `out_f32` (optional) stores O in fp32 [rows, ldo] instead of bf16 (inference / tests).
+ * K4  decoder forward fused with the loss — replaces LinearEmbedding(de).forward
+ *     `F.linear(z, W_d[items], b_d[items])` (recoder/nn.py:280; MF: recoder/nn.py:361), MSELoss.forward
+ *     (recoder/losses.py:43-47), MultinomialNLLLoss.forward (recoder/losses.py:68-71), BCEWithLogitsLoss('sum')
+ *     (recoder/model.py:91), the `/ B` (recoder/model.py:483-484) and the first node of autograd's backward.
+ *     Logits o[r,c] = sum_h Zb[r,h]*Wg[c,h] + bias[c] (bf16 operands, fp32 accumulate in TMEM) never reach memory;
+ *     the epilogue writes G bf16 [rows, ldg], the DENSE (target-free) part of dL/dlogits:
+ *        MSE      G = 2*o/B                      dL/dO = G + sparse
+ *        LOGISTIC G = sigmoid(o)/B               dL/dO = G + sparse
+ *        NLL      G = exp(o - row_ref[r])        dL/dO = alpha[r]*G + sparse,  alpha[r] = S_r/(B*sum_c G[r,c])
+ *     and per-row partials stat fp32 [rows, stat_ld] (2 per 256-column tile): sum G (NLL), sum o^2 (MSE),
+ *     sum softplus(o) (LOGISTIC).  The SPARSE part at the stored targets (fp32, never quantised to bf16) comes
+ *     from rcd_sddmm:  MSE 2*((w-1)*o - w*t)/B with w = 1+conf*[t>0];  NLL / LOGISTIC -t/B.
+ *     row_ref (NLL): any per-row reference; rcd_sddmm supplies the largest logit among the row's own targets.
+ *
+ *     rcd_decoder_fwd is the plain logits GEMM (fp32 or bf16 out, optional online-softmax partials laid out
+ *     [n_tiles, rows]) used by the inference path (recoder/model.py:487-511) and the kernel tests.
  * ------------------------------------------------------------------------------------------------------- */
-int rcd_decoder_tile_n(void); /* n-tile width the stats are laid out for (256) */
+int rcd_decoder_tile_n(void); /* n-tile width of rcd_decoder_fwd's stats (256) */
 int rcd_decoder_fwd(const uint16_t* Zb, int ldzb, const uint16_t* Wg, int ldw, const float* bias, int rows, int n,
                     int H, uint16_t* O_bf16, float* out_f32, int ldo, float* stat_max, float* stat_sum, int engine,
                     void* stream);
+int rcd_decoder_stat_cols(int n); /* number of per-row partials rcd_decoder_fwd_loss writes for n items */
+int rcd_decoder_fwd_loss(const uint16_t* Zb, int ldzb, const uint16_t* Wg, int ldw, const float* bias, int rows, int n,
+                         int H, int loss, float inv_b, const float* row_ref, uint16_t* G, int ldg, float* stat,
+                         int stat_ld, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
- * K5  loss + dL/dlogits — replaces MSELoss.forward (recoder/losses.py:43-47), MultinomialNLLLoss.forward
- *     (recoder/losses.py:68-71), BCEWithLogitsLoss('sum') (recoder/model.py:91), the `/ B` normalisation
- *     (recoder/model.py:483-484) and autograd's backward through them.
- *     rcd_softmax_lse : lse[r] = logsumexp_c O[r,c] from the K4 partials (NLL only); adds sum_r lse[r]*row_sum[r]
- *                       * inv_b to loss_acc.
- *     rcd_loss_grad   : dL/dO from O (bf16) and the sparse target given as the slice CSC, produced as
- *                       a DENSE part dO[r,c] (bf16, the target-free formula at every position) plus an fp32
- *                       SPARSE part csc_corr[e] at the stored targets (exact minus dense), so that the large,
- *                       clustered entries at the non-zeros never get quantised to bf16:
- *        MSE      dense 2*o*inv_b               sparse 2*((w-1)*o - w*t)*inv_b, w = 1+conf*[t>0]
- *        NLL      dense exp(o-lse_r)*S_r*inv_b  sparse -t*inv_b
- *        LOGISTIC dense sigmoid(o)*inv_b        sparse -t*inv_b
- *                       db[c] = sum_r dL/dO[r,c] (fp32, deterministic), loss_acc[0] += loss/B (double).
- *     The sparse part enters the backward GEMMs through rcd_sparse_dgrad (rows of dZ) and
- *     rcd_csc_rows_accumulate (rows of dW).
+ * K5  sparse side of the loss (fp32) — the stored targets of the slice rows [row0, row0+rows).
+ *     rcd_sddmm       : o_nnz[p] = Zb[r,:].Wg[cols[p],:] + bias_g[cols[p]], corr[p] = sparse part of dL/dlogits,
+ *                       row_ref[r] = max_p o_nnz[p] (0 for an empty row; optional).  p is relative to
+ *                       row_ptr[row0].  cols index Wg/bias_g (gathered rows).
+ *     rcd_loss_finish : reduces stat, adds the loss of the slice (divided by B) to loss_acc (double), writes
+ *                       row_scale[r] = alpha[r] (1 for MSE/LOGISTIC) and, when Zs != NULL, Zs = bf16(alpha*Z)
+ *                       [rows, ldzs] — the operand of the decoder weight gradient.  bad_flag |= 1 when a softmax
+ *                       row sum is not positive/finite, |= 2 when the loss is not finite.
+ *     rcd_sparse_dgrad: out[r,0:H] = sum_p corr[p] * W[raw_items[p],:]  (fp32 master table; out fp32 [rows, ldp])
+ *     rcd_csc_rows_accumulate: out[c,0:H] += sum_{e in column c} coef[csc_src[e]] * M[csc_row[e],:] and
+ *                       db[c] += sum_e coef[csc_src[e]]  (csc_src == NULL: coef is already in CSC order)
  * ------------------------------------------------------------------------------------------------------- */
-int rcd_softmax_lse(const float* stat_max, const float* stat_sum, int n_tiles, int rows, const float* row_sum,
-                    float inv_b, float* lse, double* loss_acc, void* stream);
-int rcd_loss_grad(const uint16_t* O_bf16, int ldo, int rows, int n, int loss, float confidence, float inv_b,
-                  const float* lse, const float* row_sum, const int32_t* csc_ptr, const int32_t* csc_row,
-                  const float* csc_val, uint16_t* dO, int lddo, float* csc_corr, float* db, double* loss_acc,
-                  void* stream);
-/* out[r, 0:H] = sum_{p in row r} sparse(r,p) * W[raw_items[p], :]  (W = fp32 master table; out fp32 [rows, ldp]) */
-int rcd_sparse_dgrad(const float* W, int H, const int32_t* row_ptr, const int32_t* raw_items, const int32_t* cols,
-                     const float* vals, const uint16_t* O_bf16, int ldo, int row0, int rows, int loss,
-                     float confidence, float inv_b, float* out, int ldp, void* stream);
-/* out[c, 0:H] += sum_{e in column c} csc_coef[e] * M[csc_row[e], :]   (M fp32 [rows, H], out fp32 [n, H]) */
+int rcd_sddmm(const uint16_t* Zb, int ldzb, const uint16_t* Wg, int ldw, const float* bias_g, int H,
+              const int32_t* row_ptr, const int32_t* cols, const float* vals, int row0, int rows, int loss,
+              float confidence, float inv_b, float* o_nnz, float* corr, float* row_ref, void* stream);
+int rcd_loss_finish(const float* stat, int stat_ld, int stat_cols, int rows, int loss, float confidence, float inv_b,
+                    const float* row_ref, const float* row_sum, const int32_t* row_ptr, const float* vals,
+                    const float* o_nnz, int row0, float* row_scale, const float* Z, int H, uint16_t* Zs, int ldzs,
+                    double* loss_acc, int32_t* bad_flag, void* stream);
+int rcd_sparse_dgrad(const float* W, int H, const int32_t* row_ptr, const int32_t* raw_items, const float* corr,
+                     int row0, int rows, float* out, int ldp, void* stream);
 int rcd_csc_rows_accumulate(const float* M, int H, const int32_t* csc_ptr, const int32_t* csc_row,
-                            const float* csc_coef, int n, float* out, void* stream);
+                            const int32_t* csc_src, const float* coef, int n, float* out, float* db, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K6  decoder backward GEMMs — replace autograd's `mm` nodes of F.linear.
- *     rcd_decoder_dgrad : dZ[r,h]  = sum_c dO[r,c] * Wg[c,h]     (K = n, split-K; partials fp32
- *                         [splits, rows, ldp]); the caller reduces them with rcd_dz_act.
- *     rcd_decoder_wgrad : dW[c,h]  = sum_r dO[r,c] * Zb[r,h]     (K = rows) -> fp32 [n, H] compact row grads
+ *     rcd_decoder_dgrad : P[r,h]  = sum_c G[r,c] * Wg[c,h]      (K = n, split-K; partials fp32
+ *                         [splits, rows, ldp]); the caller reduces/scales them with rcd_dz_act.
+ *     rcd_decoder_wgrad : dW[c,h] = sum_r G[r,c] * Zs[r,h]      (K = rows) -> fp32 [n, H] compact row grads;
+ *                         side product (optional): db[c] = sum_r col_weight[r] * G[r,c]  (col_weight NULL = 1),
+ *                         computed from the operand tiles already staged in shared memory.
  * ------------------------------------------------------------------------------------------------------- */
 int rcd_decoder_dgrad_splits(int rows, int n, int H);
-int rcd_decoder_dgrad(const uint16_t* dO, int lddo, const uint16_t* Wg, int ldw, int rows, int n, int H,
-                      int splits, float* partials, int ldp, int engine, void* stream);
-int rcd_decoder_wgrad(const uint16_t* dO, int lddo, const uint16_t* Zb, int ldzb, int rows, int n, int H,
-                      float* dW, int lddw, int engine, void* stream);
+int rcd_decoder_dgrad(const uint16_t* G, int ldg, const uint16_t* Wg, int ldw, int rows, int n, int H, int splits,
+                      float* partials, int ldp, int engine, void* stream);
+int rcd_decoder_wgrad(const uint16_t* G, int ldg, const uint16_t* Zs, int ldzs, int rows, int n, int H, float* dW,
+                      int lddw, const float* col_weight, float* db, int engine, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K7  encoder backward — replaces tanh_backward + the `mm`/`sum` nodes of the encoder F.linear and
  *     embedding_dense_backward.
- *     rcd_dz_act        : dA = (sum_s partials[s]) * act'(Z)  -> fp32 [rows, H]; db_e[h] = sum_r dA[r,h]
+ *     rcd_dz_act        : dA = (row_scale[r] * sum_{s<n_scaled} partials[s] + sum_{s>=n_scaled} partials[s]) * act'(Z)
+ *                         -> fp32 [rows, H] (row_scale NULL = 1); db_e[h] = sum_r dA[r,h]
  *     rcd_ae_encoder_wgrad : dWe_rows[c,:] = sum_{(r,x) in column c} x * row_inv_norm[row0+r] * dA[r,:]
  * ------------------------------------------------------------------------------------------------------- */
-int rcd_dz_act(const float* partials, int splits, int ldp, const float* Z, int rows, int H, int act, float* dA,
-               float* db, void* stream);
+int rcd_dz_act(const float* partials, int splits, int n_scaled, const float* row_scale, int ldp, const float* Z,
+               int rows, int H, int act, float* dA, float* db, void* stream);
 int rcd_ae_encoder_wgrad(const float* dA, int H, const int32_t* csc_ptr, const int32_t* csc_row,
                          const float* csc_val, const float* row_inv_norm, int row0, int n, float* dWe_rows,
                          void* stream);

@@ -30,7 +30,7 @@ _SIGNATURES = {
                           c_size_t, _P]),
   'rcd_collate_coo': (c_int, [_P, _P, c_int, c_int, _P, _P]),
   'rcd_slice_csc_scratch_bytes': (c_size_t, [c_int, c_int]),
-  'rcd_slice_csc': (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
+  'rcd_slice_csc': (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
   'rcd_dense_to_csr_scratch_bytes': (c_size_t, [c_int]),
   'rcd_dense_to_csr': (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
   'rcd_gather_rows': (c_int, [_P, c_int, _P, c_int, c_int, _P, c_int, _P, _P]),
@@ -38,16 +38,19 @@ _SIGNATURES = {
   'rcd_ae_encoder_fwd': (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, c_int, _P]),
   'rcd_decoder_tile_n': (c_int, []),
   'rcd_decoder_fwd': (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P]),
-  'rcd_softmax_lse': (c_int, [_P, _P, c_int, c_int, _P, c_float, _P, _P, _P]),
-  'rcd_loss_grad': (c_int, [_P, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P, c_int, _P, _P,
-                            _P, _P]),
-  'rcd_sparse_dgrad': (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, _P, c_int,
-                               _P]),
-  'rcd_csc_rows_accumulate': (c_int, [_P, c_int, _P, _P, _P, c_int, _P, _P]),
+  'rcd_decoder_stat_cols': (c_int, [c_int]),
+  'rcd_decoder_fwd_loss': (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, c_int, _P,
+                                   c_int, _P]),
+  'rcd_sddmm': (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P,
+                        _P]),
+  'rcd_loss_finish': (c_int, [_P, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P, c_int, _P, _P,
+                              c_int, _P, c_int, _P, _P, _P]),
+  'rcd_sparse_dgrad': (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, _P, c_int, _P]),
+  'rcd_csc_rows_accumulate': (c_int, [_P, c_int, _P, _P, _P, _P, c_int, _P, _P, _P]),
   'rcd_decoder_dgrad_splits': (c_int, [c_int, c_int, c_int]),
   'rcd_decoder_dgrad': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
-  'rcd_decoder_wgrad': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
-  'rcd_dz_act': (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P]),
+  'rcd_decoder_wgrad': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int, _P]),
+  'rcd_dz_act': (c_int, [_P, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P]),
   'rcd_ae_encoder_wgrad': (c_int, [_P, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P]),
   'rcd_adam_step': (c_int, [_P, _P, _P, c_longlong, c_int, _P, c_int, _P, c_double, c_double, c_double, c_double,
                             c_double, c_longlong, _P]),

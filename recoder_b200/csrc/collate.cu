@@ -113,43 +113,82 @@ static __global__ void k_col_count(const int32_t* __restrict__ row_ptr, const in
 static __global__ void k_col_fill(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
                                   const float* __restrict__ vals, int row0, int rows,
                                   const int32_t* __restrict__ csc_ptr, int* __restrict__ cursor,
-                                  int32_t* __restrict__ tmp_row, float* __restrict__ tmp_val) {
+                                  int32_t* __restrict__ tmp_row, int32_t* __restrict__ tmp_src) {
   int r = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
+  const int base = row_ptr[row0];
   const int s = row_ptr[row0 + r], e = row_ptr[row0 + r + 1];
   for (int p = s + lane; p < e; p += 32) {
     int c = cols[p];
     int slot = csc_ptr[c] + atomicAdd(&cursor[c], 1);
     tmp_row[slot] = r;
-    tmp_val[slot] = vals[p];
+    tmp_src[slot] = p - base;
   }
 }
 
 // One warp per column: order the column's entries by row so every later reduction is deterministic.
-// (row, col) pairs are unique, so the rank of an entry = number of entries with a smaller row.
-static __global__ void k_col_sort(const int32_t* __restrict__ csc_ptr, int n, const int32_t* __restrict__ tmp_row,
-                                  const float* __restrict__ tmp_val, int32_t* __restrict__ csc_row,
-                                  float* __restrict__ csc_val) {
+// (row, col) pairs are unique, so the rank of an entry = number of entries of the column with a smaller row.
+// Short columns: all-pairs compare through shuffles.  Long columns (popular items: up to `rows` entries): a
+// per-warp row bitmap in shared memory, rank = popcount of the bits below the row (O(L + rows/32)).
+static __global__ void k_col_sort(const int32_t* __restrict__ csc_ptr, int n, int rows, int words,
+                                  const int32_t* __restrict__ tmp_row, const int32_t* __restrict__ tmp_src,
+                                  const int32_t* __restrict__ row_ptr, int row0, const float* __restrict__ vals,
+                                  int32_t* __restrict__ csc_row, float* __restrict__ csc_val,
+                                  int32_t* __restrict__ csc_src) {
+  extern __shared__ uint32_t s_bits[];  // [kRowWarps][2*words]: bitmap, then exclusive popcount prefix
   int c = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   if (c >= n) return;
   const int lane = threadIdx.x & 31;
+  const float* vals_slice = vals + row_ptr[row0];
   const int s = csc_ptr[c], L = csc_ptr[c + 1] - s;
   if (L <= 32) {
     int row = (lane < L) ? tmp_row[s + lane] : 0x7fffffff;
-    float v = (lane < L) ? tmp_val[s + lane] : 0.f;
+    int src = (lane < L) ? tmp_src[s + lane] : 0;
     int rank = 0;
     for (int j = 0; j < L; ++j) rank += (__shfl_sync(0xffffffffu, row, j) < row) ? 1 : 0;
     if (lane < L) {
       csc_row[s + rank] = row;
-      csc_val[s + rank] = v;
+      csc_val[s + rank] = vals_slice[src];
+      if (csc_src) csc_src[s + rank] = src;
+    }
+  } else if (words > 0) {
+    uint32_t* bm = s_bits + (size_t)(threadIdx.x >> 5) * 2 * words;
+    uint32_t* pre = bm + words;
+    for (int i = lane; i < words; i += 32) bm[i] = 0u;
+    __syncwarp();
+    for (int i = lane; i < L; i += 32) {
+      const int row = tmp_row[s + i];
+      atomicOr(&bm[row >> 5], 1u << (row & 31));
+    }
+    __syncwarp();
+    int carry = 0;
+    for (int b0 = 0; b0 < words; b0 += 32) {
+      const int i = b0 + lane;
+      const int cnt = (i < words) ? __popc(bm[i]) : 0;
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (i < words) pre[i] = (uint32_t)(carry + incl - cnt);
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+    for (int i = lane; i < L; i += 32) {
+      const int row = tmp_row[s + i], src = tmp_src[s + i];
+      const int rank = (int)pre[row >> 5] + __popc(bm[row >> 5] & ((1u << (row & 31)) - 1u));
+      csc_row[s + rank] = row;
+      csc_val[s + rank] = vals_slice[src];
+      if (csc_src) csc_src[s + rank] = src;
     }
   } else {
     const int iters = (L + 31) / 32;  // all lanes iterate together (shuffles below are warp-wide)
     for (int it = 0; it < iters; ++it) {
       const int i = it * 32 + lane;
       int row = (i < L) ? tmp_row[s + i] : 0x7fffffff;
-      float v = (i < L) ? tmp_val[s + i] : 0.f;
+      int src = (i < L) ? tmp_src[s + i] : 0;
       int rank = 0;
       for (int j0 = 0; j0 < L; j0 += 32) {
         int other = (j0 + lane < L) ? tmp_row[s + j0 + lane] : 0x7fffffff;
@@ -158,7 +197,8 @@ static __global__ void k_col_sort(const int32_t* __restrict__ csc_ptr, int n, co
       }
       if (i < L) {
         csc_row[s + rank] = row;
-        csc_val[s + rank] = v;
+        csc_val[s + rank] = vals_slice[src];
+        if (csc_src) csc_src[s + rank] = src;
       }
     }
   }
@@ -275,13 +315,13 @@ RCD_EXPORT size_t rcd_slice_csc_scratch_bytes(int n, int nnz_slice) {
 }
 
 RCD_EXPORT int rcd_slice_csc(const int32_t* row_ptr, const int32_t* cols, const float* vals, int row0, int rows,
-                             int n, int32_t* csc_ptr, int32_t* csc_row, float* csc_val, void* scratch,
-                             size_t scratch_bytes, void* stream) {
+                             int n, int32_t* csc_ptr, int32_t* csc_row, float* csc_val, int32_t* csc_src,
+                             void* scratch, size_t scratch_bytes, void* stream) {
   RCD_CHECK_ARG(row_ptr && cols && vals && csc_ptr && csc_row && csc_val, "null pointer");
   RCD_CHECK_ARG(rows > 0 && n > 0 && row0 >= 0, "bad slice");
   RCD_CHECK_ARG(scratch && scratch_bytes >= 256, "scratch too small");
   cudaStream_t st = (cudaStream_t)stream;
-  // scratch: cnt[n+1] | cursor[n+1] | scan tmp | tmp_row[nnz] | tmp_val[nnz]   (nnz bounded by scratch size)
+  // scratch: cnt[n+1] | cursor[n+1] | scan tmp | tmp_row[nnz] | tmp_src[nnz]   (nnz bounded by scratch size)
   int* cnt = (int*)scratch;
   int* cursor = cnt + (n + 1);
   int* scan_tmp = cursor + (n + 1);
@@ -289,16 +329,23 @@ RCD_EXPORT int rcd_slice_csc(const int32_t* row_ptr, const int32_t* cols, const 
   size_t used_ints = (size_t)(tmp_row - cnt);
   RCD_CHECK_ARG(scratch_bytes / sizeof(int) > used_ints, "scratch too small");
   size_t nnz_cap = (scratch_bytes / sizeof(int) - used_ints) / 2;
-  float* tmp_val = (float*)(tmp_row + nnz_cap);
+  int* tmp_src = tmp_row + nnz_cap;
   RCD_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)(n + 1) * 2, st));
   const int row_blocks = rcd_div_up(rows, kRowWarps);
   k_col_count<<<row_blocks, kRowWarps * 32, 0, st>>>(row_ptr, cols, row0, rows, cnt);
   RCD_LAUNCH_CHECK();
   RCD_CUDA(exclusive_scan_i32(cnt, n, csc_ptr, nullptr, scan_tmp, st));
   k_col_fill<<<row_blocks, kRowWarps * 32, 0, st>>>(row_ptr, cols, vals, row0, rows, csc_ptr, cursor, tmp_row,
-                                                   tmp_val);
+                                                   tmp_src);
   RCD_LAUNCH_CHECK();
-  k_col_sort<<<rcd_div_up(n, kRowWarps), kRowWarps * 32, 0, st>>>(csc_ptr, n, tmp_row, tmp_val, csc_row, csc_val);
+  int words = rcd_div_up(rows, 32);
+  size_t smem = (size_t)kRowWarps * 2 * words * sizeof(uint32_t);
+  if (smem > 40 * 1024) {  // very tall slices: all-pairs fallback inside the kernel
+    words = 0;
+    smem = 0;
+  }
+  k_col_sort<<<rcd_div_up(n, kRowWarps), kRowWarps * 32, smem, st>>>(csc_ptr, n, rows, words, tmp_row, tmp_src,
+                                                                    row_ptr, row0, vals, csc_row, csc_val, csc_src);
   RCD_LAUNCH_CHECK();
   return RCD_OK;
 }

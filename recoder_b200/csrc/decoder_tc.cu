@@ -1,0 +1,311 @@
+// K4+K5 fused: decoder forward GEMM with the loss / dL/dlogits epilogue, tcgen05 + TMEM + TMA, sm_100a.
+//
+//   acc[r,c] = sum_h Zb[r,h] * Wg[c,h]          (bf16 operands, fp32 accumulate in TMEM), o = acc + bias[c]
+//   G[r,c]   = NLL      exp(o - ref[r])          (unnormalised softmax numerator; dL/dO = alpha[r]*G - t/B)
+//              MSE      2*o/B                     (dense, target-free part of dL/dO)
+//              LOGISTIC sigmoid(o)/B
+//   stat[r, 2*n_tile+half] = row partial of       NLL: sum G   MSE: sum o^2   LOGISTIC: sum softplus(o)
+//
+// The logits never go to memory: this replaces F.linear (recoder/nn.py:280, :361), the loss modules
+// (recoder/losses.py:43-47, 68-71; BCEWithLogitsLoss, recoder/model.py:91) and the first node of their backward.
+// For the multinomial NLL the usual two passes (row max/sum, then softmax) collapse into one because any per-row
+// reference value `ref` gives exp(o-ref)/sum exp(o-ref) = softmax; the caller passes the largest logit among the
+// row's own positives (rcd_sddmm), so exp() stays far from the fp32 range and the row sum is >= 1.
+//
+// One persistent CTA per SM, 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer (tcgen05.mma cta_group::1,
+// M=128, N=256, K=16) + TMEM allocator, warps 2-9 = epilogue.  Tile 128 rows x 256 items, K = H in 64-wide blocks
+// through a 3-stage smem ring; accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i
+// overlaps the MMAs of tile i+1.  Epilogue warp (q = warp%4 -> TMEM lanes 32q.., half = columns 128*half..):
+// tcgen05.ld 32x32b (lane = row) -> math -> bf16 -> 128B-swizzled smem box [32 rows x 64 cols] -> TMA store
+// (full 128-byte lines to HBM instead of row-per-thread 16-byte stores), double-buffered per warp.
+#include <cuda.h>
+
+#include "gemm_internal.cuh"
+#include "tc_ptx.cuh"
+
+namespace rcd {
+
+constexpr int kDecStages = 3;
+constexpr int kDecEpiWarps = 8;
+constexpr int kDecThreads = 64 + 32 * kDecEpiWarps;  // 320
+constexpr int kDecTileN = 256;
+constexpr int kDecAStage = kTileM * kTileK * 2;       // 16 KB
+constexpr int kDecBStage = kDecTileN * kTileK * 2;    // 32 KB
+constexpr int kDecStage = kDecAStage + kDecBStage;
+constexpr int kDecBoxBytes = 32 * 64 * 2;             // staging box: 32 rows x 64 bf16 columns
+constexpr int kDecStaging = kDecEpiWarps * 2 * kDecBoxBytes;
+constexpr int kDecBiasBytes = 2 * kDecTileN * 4;
+constexpr int kDecSmem = kDecStages * kDecStage + kDecStaging + kDecBiasBytes + 256 + 1024;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+struct DecFusedParams {
+  int M, N;             // rows, items
+  float inv_b;
+  const float* bias;    // [N]
+  const float* row_ref; // [M] or nullptr (NLL only)
+  float* stat;          // [M, stat_ld]
+  int stat_ld;
+};
+
+// 32 accumulator values of one row -> 32 outputs (packed bf16x2) + row partial.  MASK: columns >= n_valid are dead.
+template <int LOSS, bool MASK>
+__device__ __forceinline__ void dec_chunk32(const float (&v)[32], const float* __restrict__ bias_s, float m2,
+                                            float scale, int n_valid, uint32_t (&packed)[16], float& racc) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias_s + i);  // warp-wide broadcast read
+    const float bb[4] = {b.x, b.y, b.z, b.w};
+    float g[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = v[i + k];
+      float out, part;
+      if (LOSS == RCD_LOSS_NLL) {
+        out = ex2_approx(fmaf(a, kLog2e, bb[k]) - m2);  // bias and ref arrive pre-multiplied by log2(e)
+        part = out;
+      } else if (LOSS == RCD_LOSS_MSE) {
+        const float o = a + bb[k];
+        out = o * scale;  // 2/B
+        part = o * o;
+      } else {
+        const float o = a + bb[k];
+        const float e = ex2_approx(-fabsf(o) * kLog2e);  // exp(-|o|) in (0, 1]
+        const float r = rcp_approx(1.0f + e);
+        out = (o >= 0.f ? r : e * r) * scale;            // sigmoid(o)/B
+        part = fmaxf(o, 0.f) + kLn2 * lg2_approx(1.0f + e);
+      }
+      if (MASK && i + k >= n_valid) {
+        out = 0.f;
+        part = 0.f;
+      }
+      g[k] = out;
+      racc += part;
+    }
+    packed[i >> 1] = pack_bf16x2(g[0], g[1]);
+    packed[(i >> 1) + 1] = pack_bf16x2(g[2], g[3]);
+  }
+}
+
+template <int LOSS>
+static __global__ void __launch_bounds__(kDecThreads, 1)
+    k_decoder_fused(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmG, DecFusedParams p, int m_tiles, int n_tiles, int kblocks,
+                    uint32_t idesc) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t tiles = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (tiles - raw_addr);
+  const uint32_t staging = tiles + kDecStages * kDecStage;
+  float* bias_s = reinterpret_cast<float*>(smem + kDecStages * kDecStage + kDecStaging);
+  const uint32_t bars = staging + kDecStaging + kDecBiasBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kDecStages + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * kDecStages + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * kDecStages + 2 + a); };
+  uint32_t* tmem_slot =
+      reinterpret_cast<uint32_t*>(smem + kDecStages * kDecStage + kDecStaging + kDecBiasBytes + 8 * (2 * kDecStages + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmG);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kDecStages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), kDecEpiWarps);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int units = m_tiles * n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        const int mt = unit % m_tiles, nt = unit / m_tiles;  // m fastest: concurrent CTAs share the Wg tile in L2
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, 10);
+          mbar_arrive_expect_tx(full_bar(stage), (uint32_t)kDecStage);
+          const uint32_t a_dst = tiles + stage * kDecStage;
+          tma_load_2d(a_dst, &tmA, full_bar(stage), kb * kTileK, mt * kTileM);
+          tma_load_2d(a_dst + kDecAStage, &tmB, full_bar(stage), kb * kTileK, nt * kDecTileN);
+          if (++stage == kDecStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 11);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kDecTileN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase, 12);
+          tc_fence_after();
+          const uint32_t a_addr = tiles + stage * kDecStage, b_addr = a_addr + kDecAStage;
+#pragma unroll
+          for (int k = 0; k < kTileK / 16; ++k)
+            tc_mma_bf16(tmem_d, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024),
+                        idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit(empty_bar(stage));
+          if (++stage == kDecStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    // ---------------- epilogue warps 2..9 ----------------
+    const int e = warp - 2;
+    const int q = warp & 3;   // TMEM lane quarter this warp may read
+    const int half = e >> 2;  // column half of the tile
+    const uint32_t my_staging = staging + (uint32_t)(e * 2 * kDecBoxBytes);
+    const int et = threadIdx.x - 64;  // 0..255
+    const float scale = (LOSS == RCD_LOSS_MSE) ? 2.0f * p.inv_b : p.inv_b;
+    int sbuf = 0;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+      const int mt = unit % m_tiles, nt = unit / m_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int n0 = nt * kDecTileN;
+      {
+        const int c = n0 + et;
+        float b = (c < p.N) ? __ldg(p.bias + c) : 0.f;
+        if (LOSS == RCD_LOSS_NLL) b *= kLog2e;
+        bias_s[acc * kDecTileN + et] = b;
+      }
+      named_bar_sync(1, kDecEpiWarps * 32);
+      const int row = mt * kTileM + q * 32 + lane;
+      float m2 = 0.f;
+      if (LOSS == RCD_LOSS_NLL && p.row_ref && row < p.M) m2 = __ldg(p.row_ref + row) * kLog2e;
+      mbar_wait(tfull_bar(acc), acc_phase, 13);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kDecTileN + half * 128);
+      float racc = 0.f;
+#pragma unroll 1
+      for (int box = 0; box < 2; ++box) {
+        const int col0 = n0 + half * 128 + box * 64;
+        if (col0 >= p.N) break;  // warp-uniform
+        const uint32_t sdst = my_staging + (uint32_t)(sbuf * kDecBoxBytes);
+        if (lane == 0) tma_store_wait_read<1>();  // the store that last used this buffer has read it
+        __syncwarp();
+#pragma unroll
+        for (int c32 = 0; c32 < 2; ++c32) {
+          float v[32];
+          tc_ld_32x32(taddr + (uint32_t)(box * 64 + c32 * 32), v);
+          uint32_t packed[16];
+          const float* bs = bias_s + acc * kDecTileN + half * 128 + box * 64 + c32 * 32;
+          const int n_valid = p.N - (col0 + c32 * 32);
+          if (n_valid >= 32) dec_chunk32<LOSS, false>(v, bs, m2, scale, 32, packed, racc);
+          else dec_chunk32<LOSS, true>(v, bs, m2, scale, n_valid, packed, racc);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t chunk = (uint32_t)(c32 * 4 + j);
+            const uint32_t addr = sdst + (uint32_t)lane * 128u + ((chunk ^ ((uint32_t)lane & 7u)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[j * 4]),
+                         "r"(packed[j * 4 + 1]), "r"(packed[j * 4 + 2]), "r"(packed[j * 4 + 3])
+                         : "memory");
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmG, sdst, col0, mt * kTileM + q * 32);
+          tma_store_commit();
+        }
+        sbuf ^= 1;
+      }
+      if (row < p.M) p.stat[(size_t)row * p.stat_ld + nt * 2 + half] = racc;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace rcd
+
+using namespace rcd;
+
+RCD_EXPORT int rcd_decoder_stat_cols(int n) { return 2 * rcd_div_up(n > 0 ? n : 1, kDecTileN); }
+
+RCD_EXPORT int rcd_decoder_fwd_loss(const uint16_t* Zb, int ldzb, const uint16_t* Wg, int ldw, const float* bias,
+                                    int rows, int n, int H, int loss, float inv_b, const float* row_ref, uint16_t* G,
+                                    int ldg, float* stat, int stat_ld, void* stream) {
+  RCD_CHECK_ARG(Zb && Wg && bias && G && stat, "null pointer");
+  RCD_CHECK_ARG(rows > 0 && n > 0 && H > 0, "bad shape");
+  RCD_CHECK_ARG(ldzb >= H && ldw >= H && ldg >= n && ldg % 8 == 0, "bad leading dimension");
+  RCD_CHECK_ARG(stat_ld >= rcd_decoder_stat_cols(n), "stat_ld too small");
+  CUtensorMap tmA, tmB, tmG;
+  int rc = encode_map(&tmA, Zb, H, rows, ldzb, kTileK, kTileM);
+  if (rc != RCD_OK) return rc;
+  rc = encode_map(&tmB, Wg, H, n, ldw, kTileK, kDecTileN);
+  if (rc != RCD_OK) return rc;
+  rc = encode_map(&tmG, G, n, rows, ldg, 64, 32);
+  if (rc != RCD_OK) return rc;
+  const int m_tiles = rcd_div_up(rows, kTileM), n_tiles = rcd_div_up(n, kDecTileN), kblocks = rcd_div_up(H, kTileK);
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kDecTileN >> 3) << 17) |
+                         ((uint32_t)(kTileM >> 4) << 24);
+  DecFusedParams p{};
+  p.M = rows; p.N = n; p.inv_b = inv_b; p.bias = bias; p.row_ref = row_ref; p.stat = stat; p.stat_ld = stat_ld;
+  const int units = m_tiles * n_tiles;
+  const int sms = rcd_num_sms();
+  const int grid = units < sms ? units : sms;
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr_set[3] = {false, false, false};
+#define RCD_DEC_LAUNCH(L)                                                                                         \
+  do {                                                                                                            \
+    if (!attr_set[L]) {                                                                                           \
+      RCD_CUDA(cudaFuncSetAttribute(k_decoder_fused<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmem));  \
+      attr_set[L] = true;                                                                                         \
+    }                                                                                                             \
+    k_decoder_fused<L><<<grid, kDecThreads, kDecSmem, st>>>(tmA, tmB, tmG, p, m_tiles, n_tiles, kblocks, idesc);  \
+  } while (0)
+  switch (loss) {
+    case RCD_LOSS_MSE: RCD_DEC_LAUNCH(RCD_LOSS_MSE); break;
+    case RCD_LOSS_NLL: RCD_DEC_LAUNCH(RCD_LOSS_NLL); break;
+    case RCD_LOSS_LOGISTIC: RCD_DEC_LAUNCH(RCD_LOSS_LOGISTIC); break;
+    default:
+      rcd_set_error("rcd_decoder_fwd_loss: unknown loss id %d", loss);
+      return RCD_ERR_INVALID;
+  }
+#undef RCD_DEC_LAUNCH
+  RCD_LAUNCH_CHECK();
+  return RCD_OK;
+}

@@ -116,12 +116,15 @@ static __global__ void __launch_bounds__(kEmbThreads)
     for (int h = H + t; h < ldzb; h += tpr) Zb[(size_t)r * ldzb + h] = 0;
 }
 
+// out[c,:] (+)= sum_{entries e of column c} coef(e) * M[csc_row[e],:], coef(e) = csc_val[e] * row_scale[row0+row]  (encoder
+// weight gradient) or, when `src` is given, coef(e) = csc_val[src[e]] looked up through the CSC->CSR permutation
+// (sparse part of the decoder weight gradient); db[c] += sum_e coef(e) when db is given.
 template <int VEC, int NV>
 static __global__ void __launch_bounds__(kEmbThreads)
     k_encoder_wgrad(const float* __restrict__ dA, int H, const int32_t* __restrict__ csc_ptr,
                     const int32_t* __restrict__ csc_row, const float* __restrict__ csc_val,
-                    const float* __restrict__ row_inv_norm, int row0, int n, int tpr, float* __restrict__ out,
-                    int accumulate) {
+                    const int32_t* __restrict__ src, const float* __restrict__ row_inv_norm, int row0, int n, int tpr,
+                    float* __restrict__ out, int accumulate, float* __restrict__ db) {
   const int rpb = kEmbThreads / tpr;
   const int c = blockIdx.x * rpb + threadIdx.x / tpr;
   const int t = threadIdx.x % tpr;
@@ -132,7 +135,8 @@ static __global__ void __launch_bounds__(kEmbThreads)
   for (int k = 0; k < NV; ++k) acc[k].zero();
   seg_accumulate<VEC, NV>(acc, dA, H, t, tpr, s, e, [&](int p, int& idx, float& cf) {
     idx = csc_row[p];
-    cf = row_inv_norm ? csc_val[p] * row_inv_norm[row0 + idx] : csc_val[p];
+    if (src) cf = csc_val[src[p]];
+    else cf = row_inv_norm ? csc_val[p] * row_inv_norm[row0 + idx] : csc_val[p];
   });
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -146,28 +150,32 @@ static __global__ void __launch_bounds__(kEmbThreads)
       acc[k].store(out + (size_t)c * H + h);
     }
   }
+  if (db && t == 0) {
+    float sum = 0.f;
+    for (int p = s; p < e; ++p) sum += src ? csc_val[src[p]] : csc_val[p];  // fixed order
+    db[c] += sum;
+  }
 }
 
-// out[r,:] = sum_p corr(r,p) * W[raw_items[p],:]  — the fp32 sparse part of dZ = dO @ W (see loss.cu)
+// out[r,:] = sum_p corr[p] * W[raw_items[p],:]  — the fp32 sparse part of dZ = dO @ W (corr from rcd_sddmm,
+// indexed relative to the first stored entry of the slice)
 template <int VEC, int NV>
 static __global__ void __launch_bounds__(kEmbThreads)
     k_sparse_dgrad(const float* __restrict__ W, int H, const int32_t* __restrict__ row_ptr,
-                   const int32_t* __restrict__ raw_items, const int32_t* __restrict__ cols,
-                   const float* __restrict__ vals, const uint16_t* __restrict__ O, int ldo, int row0, int rows,
-                   int loss, float conf, float inv_b, int tpr, float* __restrict__ out, int ldp) {
+                   const int32_t* __restrict__ raw_items, const float* __restrict__ corr, int row0, int rows, int tpr,
+                   float* __restrict__ out, int ldp) {
   const int rpb = kEmbThreads / tpr;
   const int r = blockIdx.x * rpb + threadIdx.x / tpr;
   const int t = threadIdx.x % tpr;
   if (r >= rows) return;
+  const int base = row_ptr[row0];
   const int s = row_ptr[row0 + r], e = row_ptr[row0 + r + 1];
   Vec<VEC> acc[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) acc[k].zero();
   seg_accumulate<VEC, NV>(acc, W, H, t, tpr, s, e, [&](int p, int& idx, float& cf) {
     idx = raw_items[p];
-    float o = 0.f;
-    if (loss == RCD_LOSS_MSE) o = __uint_as_float((uint32_t)O[(size_t)r * ldo + cols[p]] << 16);
-    cf = sparse_corr(loss, o, vals[p], conf, inv_b);
+    cf = corr[p - base];
   });
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -220,13 +228,17 @@ static __global__ void k_gather_vec(const float* __restrict__ vec, const int64_t
   if (i < n) out[i] = vec[ids ? ids[i] : i];
 }
 
-static __global__ void k_dz_act(const float* __restrict__ partials, int splits, long long split_stride, int ldp,
+// dA = (row_scale[r] * sum_{k < n_scaled} partials[k] + sum_{k >= n_scaled} partials[k]) * act'(Z)
+static __global__ void k_dz_act(const float* __restrict__ partials, int splits, int n_scaled,
+                                const float* __restrict__ row_scale, long long split_stride, int ldp,
                                 const float* __restrict__ Z, int rows, int H, int act, float* __restrict__ dA) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)rows * H) return;
   const int r = (int)(i / H), h = (int)(i % H);
   float s = 0.f;
-  for (int k = 0; k < splits; ++k) s += partials[k * split_stride + (size_t)r * ldp + h];  // fixed order
+  for (int k = 0; k < n_scaled; ++k) s += partials[k * split_stride + (size_t)r * ldp + h];  // fixed order
+  if (row_scale) s *= row_scale[r];
+  for (int k = n_scaled; k < splits; ++k) s += partials[k * split_stride + (size_t)r * ldp + h];
   dA[i] = s * act_grad_from_out(Z[i], act);
 }
 
@@ -325,17 +337,18 @@ RCD_EXPORT int rcd_ae_encoder_wgrad(const float* dA, int H, const int32_t* csc_p
   const int blocks = rcd_div_up(n, kEmbThreads / tpr);
   if (vec)
     RCD_DISPATCH_NV(k_encoder_wgrad, 4, units, tpr, <<<blocks, kEmbThreads, 0, st>>>(
-        dA, H, csc_ptr, csc_row, csc_val, row_inv_norm, row0, n, tpr, dWe_rows, 0));
+        dA, H, csc_ptr, csc_row, csc_val, nullptr, row_inv_norm, row0, n, tpr, dWe_rows, 0, nullptr));
   else
     RCD_DISPATCH_NV(k_encoder_wgrad, 1, units, tpr, <<<blocks, kEmbThreads, 0, st>>>(
-        dA, H, csc_ptr, csc_row, csc_val, row_inv_norm, row0, n, tpr, dWe_rows, 0));
+        dA, H, csc_ptr, csc_row, csc_val, nullptr, row_inv_norm, row0, n, tpr, dWe_rows, 0, nullptr));
   RCD_LAUNCH_CHECK();
   return RCD_OK;
 }
 
 RCD_EXPORT int rcd_csc_rows_accumulate(const float* M, int H, const int32_t* csc_ptr, const int32_t* csc_row,
-                                       const float* csc_coef, int n, float* out, void* stream) {
-  RCD_CHECK_ARG(M && csc_ptr && csc_row && csc_coef && out, "null pointer");
+                                       const int32_t* csc_src, const float* coef, int n, float* out, float* db,
+                                       void* stream) {
+  RCD_CHECK_ARG(M && csc_ptr && csc_row && coef && out, "null pointer");
   RCD_CHECK_ARG(n > 0 && H > 0, "bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(M) & 15) == 0) &&
@@ -345,20 +358,17 @@ RCD_EXPORT int rcd_csc_rows_accumulate(const float* M, int H, const int32_t* csc
   const int blocks = rcd_div_up(n, kEmbThreads / tpr);
   if (vec)
     RCD_DISPATCH_NV(k_encoder_wgrad, 4, units, tpr, <<<blocks, kEmbThreads, 0, st>>>(
-        M, H, csc_ptr, csc_row, csc_coef, nullptr, 0, n, tpr, out, 1));
+        M, H, csc_ptr, csc_row, coef, csc_src, nullptr, 0, n, tpr, out, 1, db));
   else
     RCD_DISPATCH_NV(k_encoder_wgrad, 1, units, tpr, <<<blocks, kEmbThreads, 0, st>>>(
-        M, H, csc_ptr, csc_row, csc_coef, nullptr, 0, n, tpr, out, 1));
+        M, H, csc_ptr, csc_row, coef, csc_src, nullptr, 0, n, tpr, out, 1, db));
   RCD_LAUNCH_CHECK();
   return RCD_OK;
 }
 
 RCD_EXPORT int rcd_sparse_dgrad(const float* W, int H, const int32_t* row_ptr, const int32_t* raw_items,
-                                const int32_t* cols, const float* vals, const uint16_t* O_bf16, int ldo, int row0,
-                                int rows, int loss, float confidence, float inv_b, float* out, int ldp,
-                                void* stream) {
-  RCD_CHECK_ARG(W && row_ptr && raw_items && cols && vals && out, "null pointer");
-  RCD_CHECK_ARG(loss != RCD_LOSS_MSE || O_bf16, "MSE needs the logits");
+                                const float* corr, int row0, int rows, float* out, int ldp, void* stream) {
+  RCD_CHECK_ARG(W && row_ptr && raw_items && corr && out, "null pointer");
   RCD_CHECK_ARG(rows > 0 && H > 0 && row0 >= 0 && ldp >= H, "bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (H % 4 == 0) && (ldp % 4 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0) &&
@@ -368,21 +378,22 @@ RCD_EXPORT int rcd_sparse_dgrad(const float* W, int H, const int32_t* row_ptr, c
   const int blocks = rcd_div_up(rows, kEmbThreads / tpr);
   if (vec)
     RCD_DISPATCH_NV(k_sparse_dgrad, 4, units, tpr, <<<blocks, kEmbThreads, 0, st>>>(
-        W, H, row_ptr, raw_items, cols, vals, O_bf16, ldo, row0, rows, loss, confidence, inv_b, tpr, out, ldp));
+        W, H, row_ptr, raw_items, corr, row0, rows, tpr, out, ldp));
   else
     RCD_DISPATCH_NV(k_sparse_dgrad, 1, units, tpr, <<<blocks, kEmbThreads, 0, st>>>(
-        W, H, row_ptr, raw_items, cols, vals, O_bf16, ldo, row0, rows, loss, confidence, inv_b, tpr, out, ldp));
+        W, H, row_ptr, raw_items, corr, row0, rows, tpr, out, ldp));
   RCD_LAUNCH_CHECK();
   return RCD_OK;
 }
 
-RCD_EXPORT int rcd_dz_act(const float* partials, int splits, int ldp, const float* Z, int rows, int H, int act,
-                          float* dA, float* db, void* stream) {
+RCD_EXPORT int rcd_dz_act(const float* partials, int splits, int n_scaled, const float* row_scale, int ldp,
+                          const float* Z, int rows, int H, int act, float* dA, float* db, void* stream) {
   RCD_CHECK_ARG(partials && Z && dA, "null pointer");
-  RCD_CHECK_ARG(rows > 0 && H > 0 && splits > 0 && ldp >= H, "bad shape");
+  RCD_CHECK_ARG(rows > 0 && H > 0 && splits > 0 && ldp >= H && n_scaled >= 0 && n_scaled <= splits, "bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   long long total = (long long)rows * H;
-  k_dz_act<<<rcd_div_up(total, 256), 256, 0, st>>>(partials, splits, (long long)rows * ldp, ldp, Z, rows, H, act, dA);
+  k_dz_act<<<rcd_div_up(total, 256), 256, 0, st>>>(partials, splits, row_scale ? n_scaled : splits, row_scale,
+                                                   (long long)rows * ldp, ldp, Z, rows, H, act, dA);
   RCD_LAUNCH_CHECK();
   if (db) {
     k_colsum_f32<<<rcd_div_up(H, 32), 256, 0, st>>>(dA, rows, H, db);

@@ -61,22 +61,39 @@ RCD_EXPORT int rcd_decoder_dgrad(const uint16_t* dO, int lddo, const uint16_t* W
   RCD_CHECK_ARG(lddo >= n && ldw >= H && ldp >= H, "bad leading dimension");
   GemmProblem g{};
   g.mode = 1; g.A = dO; g.lda = lddo; g.B = Wg; g.ldb = ldw; g.M = rows; g.N = H; g.K = n;
-  g.bn = pick_bn(H); g.splits = splits; g.n_fastest = 1;
+  g.bn = pick_bn(H); g.splits = splits; g.n_fastest = 1; g.split_major = 1;
   EpiParams e{};
   e.kind = EPI_F32; e.M = rows; e.N = H; e.C = partials; e.ldc = ldp; e.split_stride = (long long)rows * ldp;
   return launch(g, e, engine, (cudaStream_t)stream);
 }
 
-RCD_EXPORT int rcd_decoder_wgrad(const uint16_t* dO, int lddo, const uint16_t* Zb, int ldzb, int rows, int n, int H,
-                                 float* dW, int lddw, int engine, void* stream) {
-  RCD_CHECK_ARG(dO && Zb && dW, "null pointer");
+// validation-engine path of the wgrad side product: db[c] = sum_r w[r] * G[r,c]
+static __global__ void k_colsum_weighted(const uint16_t* __restrict__ G, int ldg, int rows, int n,
+                                         const float* __restrict__ w, float* __restrict__ db) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r)
+    s = fmaf(w ? w[r] : 1.0f, __uint_as_float((uint32_t)G[(size_t)r * ldg + c] << 16), s);
+  db[c] = s;
+}
+
+RCD_EXPORT int rcd_decoder_wgrad(const uint16_t* G, int ldg, const uint16_t* Zs, int ldzs, int rows, int n, int H,
+                                 float* dW, int lddw, const float* col_weight, float* db, int engine, void* stream) {
+  RCD_CHECK_ARG(G && Zs && dW, "null pointer");
   RCD_CHECK_ARG(rows > 0 && n > 0 && H > 0, "bad shape");
-  RCD_CHECK_ARG(lddo >= n && ldzb >= H && lddw >= H, "bad leading dimension");
+  RCD_CHECK_ARG(ldg >= n && ldzs >= H && lddw >= H, "bad leading dimension");
   GemmProblem g{};
-  g.mode = 2; g.A = dO; g.lda = lddo; g.B = Zb; g.ldb = ldzb; g.M = n; g.N = H; g.K = rows;
-  g.bn = pick_bn(H); g.splits = 1; g.n_fastest = 1;  // the n-tiles of one dO^T tile run back to back (L2 reuse)
+  g.mode = 2; g.A = G; g.lda = ldg; g.B = Zs; g.ldb = ldzs; g.M = n; g.N = H; g.K = rows;
+  g.bn = pick_bn(H); g.splits = 1; g.n_fastest = 1;  // the n-tiles of one G^T tile run back to back (L2 reuse)
   EpiParams e{};
   e.kind = EPI_F32; e.M = n; e.N = H; e.C = dW; e.ldc = lddw; e.split_stride = 0;
+  if (engine == RCD_GEMM_TCGEN05) {
+    e.colw = col_weight; e.colsum = db;
+  } else if (db) {
+    k_colsum_weighted<<<rcd_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(G, ldg, rows, n, col_weight, db);
+    RCD_LAUNCH_CHECK();
+  }
   return launch(g, e, engine, (cudaStream_t)stream);
 }
 

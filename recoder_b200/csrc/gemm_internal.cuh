@@ -8,6 +8,8 @@
 #pragma once
 #include "common.cuh"
 
+struct CUtensorMap_st;
+
 namespace rcd {
 
 constexpr int kTileM = 128;
@@ -26,6 +28,8 @@ struct GemmProblem {
   int bn;        // n-tile width (multiple of 16, <= 256)
   int splits;    // k-splits (each non-empty)
   int n_fastest; // tile order
+  int split_major; // 1: unit = split * tiles + tile — CTAs in flight work on the SAME k-range of different tiles, so
+                   // the A/B k-slabs they stream are shared through L2 (split-K over a K that does not fit L2)
 };
 
 struct EpiParams {
@@ -37,6 +41,8 @@ struct EpiParams {
   const float* bias;
   uint16_t* Obf; float* Of32; int ldo;
   float* stat_max; float* stat_sum;  // [n_tiles, M]
+  // side product of mode 2 (A MN-major): colsum[m] = sum_k colw[k] * A[k, m]  (colw == nullptr: weights 1)
+  const float* colw; float* colsum;
 };
 
 struct RowEpilogue {
@@ -126,10 +132,11 @@ struct UnitCoord {
   int mt, nt, split, kb0, kb1;
 };
 __device__ __forceinline__ UnitCoord decode_unit(int unit, int m_tiles, int n_tiles, int splits, int kblocks,
-                                                 int n_fastest) {
+                                                 int n_fastest, int split_major = 0) {
   UnitCoord u;
-  const int tile = unit / splits;
-  u.split = unit % splits;
+  const int tiles = m_tiles * n_tiles;
+  const int tile = split_major ? unit % tiles : unit / splits;
+  u.split = split_major ? unit / tiles : unit % splits;
   if (n_fastest) {
     u.nt = tile % n_tiles;
     u.mt = tile / n_tiles;
@@ -144,6 +151,9 @@ __device__ __forceinline__ UnitCoord decode_unit(int unit, int m_tiles, int n_ti
 }
 
 int gemm_tc_launch(const GemmProblem& g, const EpiParams& e, cudaStream_t st);
+// TMA descriptor of a 2D bf16 tensor [outer, inner] (row-major, leading dimension ld elements), 128B swizzle
+int encode_map(::CUtensorMap_st* map, const void* base, long long inner, long long outer, long long ld, int box_inner,
+               int box_outer);
 int gemm_simt_launch(const GemmProblem& g, const EpiParams& e, cudaStream_t st);
 
 }  // namespace rcd

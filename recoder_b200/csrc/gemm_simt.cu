@@ -11,7 +11,7 @@ static __global__ void __launch_bounds__(kTileM)
     k_gemm_simt(GemmProblem g, EpiParams e, int m_tiles, int n_tiles, int kblocks) {
   const int units = m_tiles * n_tiles * g.splits;
   for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
-    const UnitCoord u = decode_unit(unit, m_tiles, n_tiles, g.splits, kblocks, g.n_fastest);
+    const UnitCoord u = decode_unit(unit, m_tiles, n_tiles, g.splits, kblocks, g.n_fastest, g.split_major);
     const int row = u.mt * kTileM + threadIdx.x;
     const int k0 = u.kb0 * kTileK, k1 = min(u.kb1 * kTileK, g.K);
     RowEpilogue epi;

@@ -6,6 +6,9 @@
 //                                      accumulators double-buffered in TMEM (2 x 256 columns); also owns
 //                                      tcgen05.alloc/dealloc
 //   warps 2-5          epilogue     : tcgen05.ld 32x32b (TMEM lane == output row) -> row epilogue -> global
+//   warps 6-9          side product : (mode 2 only, optional) weighted column sums of the A operand read from the
+//                                      smem stages the MMA consumes: colsum[m] = sum_k colw[k]*A[k,m] — the decoder
+//                                      bias gradient db = dO^T alpha without another pass over dO
 // Three mbarrier pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue).
 //
 // Operand layouts (smem, 128B swizzle, one 64-wide K block per stage):
@@ -27,8 +30,11 @@ constexpr int kAStageBytes = kTileM * kTileK * 2;     // 16 KB
 constexpr int kBStageBytes = kTileNMax * kTileK * 2;  // 32 KB
 constexpr int kStageBytes = kAStageBytes + kBStageBytes;
 constexpr int kBarrierBytes = 256;
-constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;  // + slack for 1024 B alignment
-constexpr int kGemmThreads = 192;
+constexpr int kSideWarps = 4;
+constexpr int kSideSmemBytes = 8 * kTileM * 4;  // [8 k-groups][128 columns] partial sums
+constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + kSideSmemBytes + 1024;  // + 1024 B alignment slack
+constexpr int kGemmThreads = 320;  // warps 0/1 TMA/MMA, 2-5 epilogue, 6-9 column-sum side product
+
 constexpr int kTmemCols = 512;
 constexpr int kBoxBytes = 64 * 64 * 2;  // MN-major box
 
@@ -48,6 +54,7 @@ static __global__ void __launch_bounds__(kGemmThreads, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kStages * kStageBytes + 8 * (2 * kStages + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool do_colsum = (e.colsum != nullptr) && (g.mode == 2);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -56,7 +63,7 @@ static __global__ void __launch_bounds__(kGemmThreads, 1)
     if (lane == 0) {
       for (int s = 0; s < kStages; ++s) {
         mbar_init(full_bar(s), 1);
-        mbar_init(empty_bar(s), 1);
+        mbar_init(empty_bar(s), do_colsum ? 1 + kSideWarps : 1);  // tcgen05.commit (+ one arrive per side warp)
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(a), 1);
@@ -83,7 +90,7 @@ static __global__ void __launch_bounds__(kGemmThreads, 1)
       // ---------------- TMA producer ----------------
       uint32_t stage = 0, phase = 0;
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
-        const UnitCoord u = decode_unit(unit, m_tiles, n_tiles, g.splits, kblocks, g.n_fastest);
+        const UnitCoord u = decode_unit(unit, m_tiles, n_tiles, g.splits, kblocks, g.n_fastest, g.split_major);
         const int m0 = u.mt * kTileM, n0 = u.nt * g.bn;
         for (int kb = u.kb0; kb < u.kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, 0);
@@ -114,7 +121,7 @@ static __global__ void __launch_bounds__(kGemmThreads, 1)
       uint32_t stage = 0, phase = 0;
       int it = 0;
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
-        const UnitCoord u = decode_unit(unit, m_tiles, n_tiles, g.splits, kblocks, g.n_fastest);
+        const UnitCoord u = decode_unit(unit, m_tiles, n_tiles, g.splits, kblocks, g.n_fastest, g.split_major);
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 1);
@@ -141,12 +148,70 @@ static __global__ void __launch_bounds__(kGemmThreads, 1)
         tc_commit(tfull_bar(acc));  // accumulator complete
       }
     }
+  } else if (warp >= 6) {
+    // ---------------- side product warps (6..9): colsum[m] = sum_k colw[k] * A[k, m] ----------------
+    // 128 threads; thread t reads the 16-byte chunk (8 columns) c = t%16 of the k rows kg, kg+8, ... (kg = t/16) of
+    // every A stage, straight from the swizzled smem the MMA consumes; the 8 k-groups are summed through smem once per
+    // tile.  Only the nt == 0 unit of a tile does the work (the other n-tiles see the same A slab).
+    if (do_colsum) {
+      const int t = (warp - 6) * 32 + lane;  // 0..127
+      const uint32_t c = (uint32_t)t & 15u, kgrp = (uint32_t)t >> 4;
+      const uint32_t box_off = (c >> 3) * kBoxBytes;
+      float* side = reinterpret_cast<float*>(smem + kStages * kStageBytes + kBarrierBytes);
+      uint32_t stage = 0, phase = 0;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        const UnitCoord u = decode_unit(unit, m_tiles, n_tiles, g.splits, kblocks, g.n_fastest, g.split_major);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int kb = u.kb0; kb < u.kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase, 4);
+          if (u.nt == 0) {
+            const int kg0 = kb * kTileK + lane, kg1 = kg0 + 32;
+            const float w_lo = (kg0 < g.K) ? (e.colw ? __ldg(e.colw + kg0) : 1.0f) : 0.f;
+            const float w_hi = (kg1 < g.K) ? (e.colw ? __ldg(e.colw + kg1) : 1.0f) : 0.f;
+            const uint8_t* a_ptr = smem + stage * kStageBytes + box_off;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t k = kgrp + 8u * (uint32_t)i;
+              const float w = __shfl_sync(0xffffffffu, (i < 4) ? w_lo : w_hi, (int)(k & 31u));
+              const uint4 v = *reinterpret_cast<const uint4*>(a_ptr + k * 128u + (((c & 7u) ^ (k & 7u)) << 4));
+              acc[0] = fmaf(w, bf16_lo(v.x), acc[0]);
+              acc[1] = fmaf(w, bf16_hi(v.x), acc[1]);
+              acc[2] = fmaf(w, bf16_lo(v.y), acc[2]);
+              acc[3] = fmaf(w, bf16_hi(v.y), acc[3]);
+              acc[4] = fmaf(w, bf16_lo(v.z), acc[4]);
+              acc[5] = fmaf(w, bf16_hi(v.z), acc[5]);
+              acc[6] = fmaf(w, bf16_lo(v.w), acc[6]);
+              acc[7] = fmaf(w, bf16_hi(v.w), acc[7]);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_bar(stage));
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (u.nt == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) side[kgrp * kTileM + c * 8 + j] = acc[j];
+          named_bar_sync(2, kSideWarps * 32);
+          float sum = 0.f;
+#pragma unroll
+          for (int q2 = 0; q2 < 8; ++q2) sum += side[q2 * kTileM + t];  // fixed order
+          const int m = u.mt * kTileM + t;
+          if (m < g.M) e.colsum[m] = sum;
+          named_bar_sync(2, kSideWarps * 32);
+        }
+      }
+    }
   } else {
     // ---------------- epilogue warps (2..5): TMEM lane quarter = warp % 4 ----------------
     const int q = warp & 3;
     int it = 0;
     for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
-      const UnitCoord u = decode_unit(unit, m_tiles, n_tiles, g.splits, kblocks, g.n_fastest);
+      const UnitCoord u = decode_unit(unit, m_tiles, n_tiles, g.splits, kblocks, g.n_fastest, g.split_major);
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase, 3);
@@ -194,8 +259,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2D bf16 tensor [outer, inner] row-major with leading dimension ld (elements), box {box_inner, box_outer}
-static int encode_map(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld,
-                      int box_inner, int box_outer) {
+int encode_map(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld, int box_inner,
+               int box_outer) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     rcd_set_error("gemm_tc: cuTensorMapEncodeTiled not available from the driver");

@@ -23,33 +23,67 @@ __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float 
   p = p - a.step_size * (m / denom);                     // param.addcdiv_(exp_avg, denom, value=-step_size)
 }
 
-// VEC = 4: one thread per float4; requires H % 4 == 0 and 16-byte aligned pointers.
+// VEC = 4: one thread per float4; requires H % 4 == 0 and 16-byte aligned pointers.  p/m/v are touched exactly once
+// per step and are far larger than L2: streaming (evict-first) loads and stores keep them from flushing the
+// operands the GEMMs re-read.  Two independent vectors per thread are in flight.
+__device__ __forceinline__ void adam_vec4(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                          size_t off, const float4& gg, const AdamScalars& a, float4 pp, float4 mm,
+                                          float4 vv) {
+  float4 g = gg;
+  adam_update(pp.x, mm.x, vv.x, g.x, a);
+  adam_update(pp.y, mm.y, vv.y, g.y, a);
+  adam_update(pp.z, mm.z, vv.z, g.z, a);
+  adam_update(pp.w, mm.w, vv.w, g.w, a);
+  __stcs(reinterpret_cast<float4*>(p + off), pp);
+  __stcs(reinterpret_cast<float4*>(m + off), mm);
+  __stcs(reinterpret_cast<float4*>(v + off), vv);
+}
+
 template <int VEC>
 static __global__ void __launch_bounds__(256)
     k_adam(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, long long rows, int H,
            const float* __restrict__ grad_rows, int ldg, const int32_t* __restrict__ pos, AdamScalars a) {
   const int vpr = H / VEC;
   const long long total = rows * vpr;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / vpr;
-    const int h = (int)(i % vpr) * VEC;
-    long long gr = pos ? (long long)pos[r] : r;
-    const size_t off = (size_t)r * H + h;
-    if (VEC == 4) {
-      float4 pp = *reinterpret_cast<float4*>(p + off);
-      float4 mm = *reinterpret_cast<float4*>(m + off);
-      float4 vv = *reinterpret_cast<float4*>(v + off);
-      float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gr >= 0 && grad_rows) gg = __ldg(reinterpret_cast<const float4*>(grad_rows + (size_t)gr * ldg + h));
-      adam_update(pp.x, mm.x, vv.x, gg.x, a);
-      adam_update(pp.y, mm.y, vv.y, gg.y, a);
-      adam_update(pp.z, mm.z, vv.z, gg.z, a);
-      adam_update(pp.w, mm.w, vv.w, gg.w, a);
-      *reinterpret_cast<float4*>(p + off) = pp;
-      *reinterpret_cast<float4*>(m + off) = mm;
-      *reinterpret_cast<float4*>(v + off) = vv;
-    } else {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (VEC == 4) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < total; i += 2 * stride) {
+      const long long i1 = i + stride;
+      const long long r0 = i / vpr, r1 = i1 / vpr;
+      const int h0 = (int)(i - r0 * vpr) * 4, h1 = (int)(i1 - r1 * vpr) * 4;
+      const size_t o0 = (size_t)r0 * H + h0, o1 = (size_t)r1 * H + h1;
+      const long long g0 = pos ? (long long)__ldg(pos + r0) : r0, g1 = pos ? (long long)__ldg(pos + r1) : r1;
+      const float4 p0 = __ldcs(reinterpret_cast<const float4*>(p + o0));
+      const float4 p1 = __ldcs(reinterpret_cast<const float4*>(p + o1));
+      const float4 m0 = __ldcs(reinterpret_cast<const float4*>(m + o0));
+      const float4 m1 = __ldcs(reinterpret_cast<const float4*>(m + o1));
+      const float4 v0 = __ldcs(reinterpret_cast<const float4*>(v + o0));
+      const float4 v1 = __ldcs(reinterpret_cast<const float4*>(v + o1));
+      float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
+      if (g0 >= 0 && grad_rows) ga = __ldcs(reinterpret_cast<const float4*>(grad_rows + (size_t)g0 * ldg + h0));
+      if (g1 >= 0 && grad_rows) gb = __ldcs(reinterpret_cast<const float4*>(grad_rows + (size_t)g1 * ldg + h1));
+      adam_vec4(p, m, v, o0, ga, a, p0, m0, v0);
+      adam_vec4(p, m, v, o1, gb, a, p1, m1, v1);
+    }
+    if (i < total) {
+      const long long r0 = i / vpr;
+      const int h0 = (int)(i - r0 * vpr) * 4;
+      const size_t o0 = (size_t)r0 * H + h0;
+      const long long g0 = pos ? (long long)__ldg(pos + r0) : r0;
+      const float4 p0 = __ldcs(reinterpret_cast<const float4*>(p + o0));
+      const float4 m0 = __ldcs(reinterpret_cast<const float4*>(m + o0));
+      const float4 v0 = __ldcs(reinterpret_cast<const float4*>(v + o0));
+      float4 ga = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g0 >= 0 && grad_rows) ga = __ldcs(reinterpret_cast<const float4*>(grad_rows + (size_t)g0 * ldg + h0));
+      adam_vec4(p, m, v, o0, ga, a, p0, m0, v0);
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+      const long long r = i / vpr;
+      const int h = (int)(i % vpr);
+      const long long gr = pos ? (long long)pos[r] : r;
+      const size_t off = (size_t)r * H + h;
       float pp = p[off], mm = m[off], vv = v[off];
       float gg = (gr >= 0 && grad_rows) ? grad_rows[(size_t)gr * ldg + h] : 0.f;
       adam_update(pp, mm, vv, gg, a);

@@ -245,15 +245,18 @@ class PoolBatch:
     self.n = 0
     self.nnz = 0
     self.row_ptr_host = None
+    self._pending = None
 
   @property
   def items(self):
     return self.items_buf[:self.n]
 
 
-def collate_pool(csr, users, negative_sampling: bool) -> PoolBatch:
-  """Runs K1 on the rows `users` of `csr` (DeviceCSR, or HostStagedCSR: staged over PCIe first) and returns the
-  pool's compute layout."""
+def collate_pool_launch(csr, users, negative_sampling: bool) -> PoolBatch:
+  """Enqueues K1 on the rows `users` of `csr` (DeviceCSR, or HostStagedCSR: staged over PCIe first) and an
+  asynchronous read-back of the two counts (n, nnz) every downstream shape depends on.  The returned PoolBatch is
+  usable after `collate_pool_finish`.  Launching the collate of pool i+1 before the training step of pool i is
+  enqueued hides the read-back behind that step (Recoder._pool_steps)."""
   users = np.ascontiguousarray(np.asarray(users).reshape(-1), dtype=np.int64)
   assert users.size > 0
   assert users.min() >= 0 and users.max() < csr.shape[0], 'user index out of range'
@@ -291,12 +294,43 @@ def collate_pool(csr, users, negative_sampling: bool) -> PoolBatch:
                _native.ptr(pb.raw_items), _native.ptr(pb.cols), _native.ptr(pb.vals), _native.ptr(pb.row_inv_norm),
                _native.ptr(pb.row_sum), _native.ptr(pb.pos), _native.ptr(pb.items_buf), _native.ptr(pb.counts),
                _native.ptr(scratch), sbytes)
-  counts = pb.counts.cpu()  # the one host sync of the collate: n decides every downstream shape
+  counts_host = _pinned_counts()
+  counts_host.copy_(pb.counts, non_blocking=True)
+  ev = torch.cuda.Event()
+  ev.record()
   TRANSFER_BYTES['d2h'] += 8
-  pb.n = int(counts[0])
-  pb.nnz = int(counts[1])
+  pb._pending = (counts_host, ev, nnz, (csr, rows_dev, scratch))  # keeps the kernel inputs alive until finish
+  return pb
+
+
+_COUNTS_RING = []
+_COUNTS_TURN = [0]
+
+
+def _pinned_counts():
+  if not _COUNTS_RING:
+    for _ in range(8):
+      _COUNTS_RING.append(torch.zeros(2, dtype=torch.int32).pin_memory())
+  _COUNTS_TURN[0] += 1
+  return _COUNTS_RING[_COUNTS_TURN[0] % len(_COUNTS_RING)]
+
+
+def collate_pool_finish(pb: PoolBatch) -> PoolBatch:
+  """Waits for the counts of a launched collate (the one host sync of the collate)."""
+  if pb._pending is None:
+    return pb
+  counts_host, ev, nnz, _ = pb._pending
+  ev.synchronize()
+  pb.n = int(counts_host[0])
+  pb.nnz = int(counts_host[1])
+  pb._pending = None
   assert pb.nnz == nnz, 'device/host nnz mismatch'
   return pb
+
+
+def collate_pool(csr, users, negative_sampling: bool) -> PoolBatch:
+  """Runs K1 on the rows `users` of `csr` and returns the pool's compute layout."""
+  return collate_pool_finish(collate_pool_launch(csr, users, negative_sampling))
 
 
 class BatchCollator:

@@ -7,8 +7,10 @@ sums one contiguous gradient slab with a single all-reduce.
 
 Launch sequence of an autoencoder step (names are include/recoder_b200.h entry points):
   rcd_slice_csc -> rcd_gather_rows/rcd_gather_vec (W_d, b_d of the n batch items) -> rcd_ae_encoder_fwd ->
-  rcd_decoder_fwd [-> rcd_softmax_lse] -> rcd_loss_grad -> rcd_decoder_dgrad -> rcd_dz_act ->
-  rcd_decoder_wgrad -> rcd_ae_encoder_wgrad -> [all-reduce] -> rcd_adam_step x4 (or SGD / SparseAdam)
+  rcd_sddmm (logits at the stored targets, softmax reference) -> rcd_decoder_fwd_loss (tcgen05 GEMM, loss/dlogits
+  epilogue) -> rcd_loss_finish -> rcd_decoder_dgrad + rcd_sparse_dgrad -> rcd_dz_act -> rcd_decoder_wgrad (+ bias
+  gradient side product) -> rcd_csc_rows_accumulate -> rcd_ae_encoder_wgrad -> [all-reduce] -> rcd_adam_step x4
+  (or SGD / SparseAdam)
 """
 import math
 
@@ -202,6 +204,7 @@ class TrainEngine:
     self.lib = _native.load()
     self.tile_n = self.lib.rcd_decoder_tile_n()
     self.last = {}                # views of the last step's compact gradients (tests / telemetry)
+    self.bad_flag = torch.zeros(1, dtype=torch.int32, device=dev)   # set by rcd_loss_finish on non-finite rows
     self._loss_host = None
 
   # ------------------------------------------------------------------------------------------------------
@@ -214,19 +217,45 @@ class TrainEngine:
   def losses(self, last_k):
     """The last `last_k` step losses as a CPU float64 tensor (one sync)."""
     k = min(last_k, self.steps_done, self.LOSS_RING)
+    self.check_finite()
     idx = [(self.steps_done - k + j) % self.LOSS_RING for j in range(k)]
     return self.loss_ring[torch.tensor(idx, device=self.device, dtype=torch.long)].cpu() if k else torch.zeros(0)
 
-  def last_loss_to_host(self):
-    """Loss of the last step read back through a pinned 8-byte buffer (the reference's `loss.item()`)."""
-    if self._loss_host is None:
-      self._loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
-    i = (self.steps_done - 1) % self.LOSS_RING
-    self._loss_host.copy_(self.loss_ring[i:i + 1], non_blocking=True)
-    torch.cuda.current_stream().synchronize()
+  def check_finite(self):
+    """Raises if a step produced a non-finite loss / softmax row sum (synchronises)."""
+    flag = int(self.bad_flag.item())
+    if flag:
+      self.bad_flag.zero_()
+      raise FloatingPointError('recoder_b200: non-finite loss in a training step (flag %d: 1 = softmax row sum, '
+                               '2 = loss value)' % flag)
+
+  def loss_to_host_deferred(self):
+    """Per-step loss read-back without stalling the pipeline: enqueues the D2H copy of the loss of the step just
+    launched (8 bytes, pinned ring) and returns the loss of the PREVIOUS step (None on the first call)."""
     from . import data as _data
+    if self._loss_host is None:
+      self._loss_host = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(4)]
+      self._loss_pending = []
+    i = (self.steps_done - 1) % self.LOSS_RING
+    buf = self._loss_host[self.steps_done % len(self._loss_host)]
+    buf.copy_(self.loss_ring[i:i + 1], non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
     _data.TRANSFER_BYTES['d2h'] += 8
-    return float(self._loss_host[0])
+    self._loss_pending.append((buf, ev))
+    if len(self._loss_pending) < 2:
+      return None
+    pbuf, pev = self._loss_pending.pop(0)
+    pev.synchronize()
+    return float(pbuf[0])
+
+  def drain_deferred_loss(self):
+    out = None
+    while getattr(self, '_loss_pending', None):
+      pbuf, pev = self._loss_pending.pop(0)
+      pev.synchronize()
+      out = float(pbuf[0])
+    return out
 
   def _world(self):
     if self.pg is None:
@@ -264,52 +293,55 @@ class TrainEngine:
     csc_ptr = b.get(tag + 'csc_ptr', n + 1, torch.int32)
     csc_row = b.get(tag + 'csc_row', max(nnz, 1), torch.int32)
     csc_val = b.get(tag + 'csc_val', max(nnz, 1), torch.float32)
+    csc_src = b.get(tag + 'csc_src', max(nnz, 1), torch.int32)
     sbytes = self.lib.rcd_slice_csc_scratch_bytes(n, max(nnz, 1))
     scratch = b.get('csc_scratch', sbytes, torch.uint8)
     call('rcd_slice_csc', ptr(pool.row_ptr), ptr(pool.cols), ptr(pool.vals), row0, rows, n, ptr(csc_ptr),
-         ptr(csc_row), ptr(csc_val), ptr(scratch), sbytes)
-    return csc_ptr, csc_row, csc_val
+         ptr(csc_row), ptr(csc_val), ptr(csc_src), ptr(scratch), sbytes)
+    return csc_ptr, csc_row, csc_val, csc_src
 
-  def _decoder_and_loss(self, Zb, ldh, Wg, bias_g, rows, n, H, inv_b, tpool, row0, csc, loss_slot, db_out):
-    """K4 + K5: logits (bf16) -> dO (bf16), db, loss.  Returns (dO, ldn)."""
+  def _decoder_and_loss(self, Zb, ldh, Zf32, Wg, bias_g, rows, n, H, inv_b, tpool, row0, loss_slot, train):
+    """K5 (sparse side) + K4 (fused decoder GEMM / loss epilogue) + row finish.
+    Returns (G bf16 [rows, ldn], ldn, corr fp32 [nnz], alpha fp32 [rows] or None, Zs bf16 operand for dW_d)."""
     b = self.buf
     ldn = _round_up(n, 8)
-    O = b.get('O', rows * ldn, torch.bfloat16)
-    dO = b.get('dO', rows * ldn, torch.bfloat16)
+    nnz = max(int(tpool.row_ptr_host[row0 + rows] - tpool.row_ptr_host[row0]), 1)
     nll = self.loss_id == _native.LOSS_IDS['logloss']
-    n_tiles = (n + self.tile_n - 1) // self.tile_n
-    smax = ssum = lse = None
-    if nll:
-      smax = b.get('stat_max', n_tiles * rows, torch.float32)
-      ssum = b.get('stat_sum', n_tiles * rows, torch.float32)
-      lse = b.get('lse', rows, torch.float32)
-    call('rcd_decoder_fwd', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bias_g), rows, n, H, ptr(O), None, ldn, ptr(smax),
-         ptr(ssum), self.gemm)
-    row_sum = tpool.row_sum[row0:row0 + rows]
-    if nll:
-      call('rcd_softmax_lse', ptr(smax), ptr(ssum), n_tiles, rows, ptr(row_sum), inv_b, ptr(lse), ptr(loss_slot))
-    csc_ptr, csc_row, csc_val = csc
-    corr = b.get('csc_corr', max(csc_row.numel(), 1), torch.float32)
-    call('rcd_loss_grad', ptr(O), ldn, rows, n, self.loss_id, self.confidence, inv_b, ptr(lse), ptr(row_sum),
-         ptr(csc_ptr), ptr(csc_row), ptr(csc_val), ptr(dO), ldn, ptr(corr), ptr(db_out), ptr(loss_slot))
-    return dO, ldn, O, corr
+    G = b.get('G', rows * ldn, torch.bfloat16)
+    o_nnz = b.get('o_nnz', nnz, torch.float32)
+    corr = b.get('corr', nnz, torch.float32)
+    row_ref = b.get('row_ref', rows, torch.float32) if nll else None
+    call('rcd_sddmm', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bias_g), H, ptr(tpool.row_ptr), ptr(tpool.cols),
+         ptr(tpool.vals), row0, rows, self.loss_id, self.confidence, inv_b, ptr(o_nnz), ptr(corr), ptr(row_ref))
+    stat_cols = self.lib.rcd_decoder_stat_cols(n)
+    stat = b.get('stat', rows * stat_cols, torch.float32)
+    call('rcd_decoder_fwd_loss', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bias_g), rows, n, H, self.loss_id, inv_b,
+         ptr(row_ref), ptr(G), ldn, ptr(stat), stat_cols)
+    alpha = b.get('alpha', rows, torch.float32) if nll else None
+    Zs = b.get('Zs', rows * ldh, torch.bfloat16) if (nll and train) else None
+    call('rcd_loss_finish', ptr(stat), stat_cols, stat_cols, rows, self.loss_id, self.confidence, inv_b,
+         ptr(row_ref), ptr(tpool.row_sum), ptr(tpool.row_ptr), ptr(tpool.vals), ptr(o_nnz), row0, ptr(alpha),
+         ptr(Zf32), H, ptr(Zs), ldh, ptr(loss_slot), ptr(self.bad_flag))
+    return G, ldn, corr, alpha, (Zs if Zs is not None else Zb)
 
-  def _dgrad(self, dO, ldn, O, Wg, ldh, W_master, tpool, row0, rows, n, H, inv_b, Zf32, act, dA, db):
-    """dZ = dense part (tcgen05 split-K GEMM over bf16 dO) + sparse part (fp32, master table) -> dA, db."""
+  def _dgrad(self, G, ldn, corr, alpha, Wg, ldh, W_master, tpool, row0, rows, n, H, Zf32, act, dA, db):
+    """dZ = alpha * (dense part: tcgen05 split-K GEMM over bf16 G) + sparse part (fp32, master table) -> dA, db."""
     b = self.buf
     splits = self.lib.rcd_decoder_dgrad_splits(rows, n, H)
     partials = b.get('dz_partials', (splits + 1) * rows * H, torch.float32)
-    call('rcd_decoder_dgrad', ptr(dO), ldn, ptr(Wg), ldh, rows, n, H, splits, ptr(partials), H, self.gemm)
+    call('rcd_decoder_dgrad', ptr(G), ldn, ptr(Wg), ldh, rows, n, H, splits, ptr(partials), H, self.gemm)
     sparse_slot = partials[splits * rows * H:]
-    call('rcd_sparse_dgrad', ptr(W_master), H, ptr(tpool.row_ptr), ptr(tpool.raw_items), ptr(tpool.cols),
-         ptr(tpool.vals), ptr(O), ldn, row0, rows, self.loss_id, self.confidence, inv_b, ptr(sparse_slot), H)
-    call('rcd_dz_act', ptr(partials), splits + 1, H, ptr(Zf32), rows, H, act, ptr(dA), ptr(db))
+    call('rcd_sparse_dgrad', ptr(W_master), H, ptr(tpool.row_ptr), ptr(tpool.raw_items), ptr(corr), row0, rows,
+         ptr(sparse_slot), H)
+    call('rcd_dz_act', ptr(partials), splits + 1, splits, ptr(alpha), H, ptr(Zf32), rows, H, act, ptr(dA), ptr(db))
 
-  def _wgrad(self, dO, ldn, Zb, ldh, Zf32, csc, corr, rows, n, H, dW):
-    """dW rows = dense part (tcgen05 GEMM) + sparse part (fp32 rank-1 updates at the stored targets)."""
-    call('rcd_decoder_wgrad', ptr(dO), ldn, ptr(Zb), ldh, rows, n, H, ptr(dW), H, self.gemm)
-    csc_ptr, csc_row, _ = csc
-    call('rcd_csc_rows_accumulate', ptr(Zf32), H, ptr(csc_ptr), ptr(csc_row), ptr(corr), n, ptr(dW))
+  def _wgrad(self, G, ldn, Zs, ldh, Zf32, csc, corr, alpha, rows, n, H, dW, db):
+    """dW rows = dense part (tcgen05 GEMM, bias gradient as a side product) + sparse part (fp32 rank-1 updates at
+    the stored targets)."""
+    call('rcd_decoder_wgrad', ptr(G), ldn, ptr(Zs), ldh, rows, n, H, ptr(dW), H, ptr(alpha), ptr(db), self.gemm)
+    csc_ptr, csc_row, _, csc_src = csc
+    call('rcd_csc_rows_accumulate', ptr(Zf32), H, ptr(csc_ptr), ptr(csc_row), ptr(csc_src), ptr(corr), n, ptr(dW),
+         ptr(db))
 
   def _reduce_slab(self, slab, loss_slot):
     """Data-parallel exchange: ONE all-reduce over the gradient slab; the loss rides in its last 2 floats
@@ -330,7 +362,7 @@ class TrainEngine:
     if self.tied and not same:
       raise NotImplementedError('tied weights with a separate target matrix are not supported')
     t_items = tpool.items if tpool.negative_sampling else None
-    csc_t = self._slice_csc(tpool, row0, rows, n, 't_')
+    csc_t = self._slice_csc(tpool, row0, rows, n, 't_') if train else None
     csc_in = csc_t if same else (self._slice_csc(pool, row0, rows, n_in, 'i_') if train else None)
 
     # gradient slab: [dWe_rows n_in*H | dWd_rows n*H | dbd n (pad 4) | dbe H (pad 4) | pad 2 | loss hi, lo]
@@ -352,15 +384,15 @@ class TrainEngine:
     call('rcd_ae_encoder_fwd', ptr(We), H, ptr(be), ptr(pool.row_ptr), ptr(pool.raw_items), ptr(pool.vals),
          ptr(pool.row_inv_norm), row0, rows, self.act, ptr(Z), ptr(Zb), ldh)
 
-    dO, ldn, O, corr = self._decoder_and_loss(Zb, ldh, Wg, bg, rows, n, H, inv_b, tpool, row0, csc_t, loss_slot,
-                                              dbd)
+    G, ldn, corr, alpha, Zs = self._decoder_and_loss(Zb, ldh, Z, Wg, bg, rows, n, H, inv_b, tpool, row0, loss_slot,
+                                                     train)
     if not train:
       return
 
     dA = b.get('dA', rows * H, torch.float32)
-    self._dgrad(dO, ldn, O, Wg, ldh, Wd, tpool, row0, rows, n, H, inv_b, Z, self.act, dA, dbe)
-    self._wgrad(dO, ldn, Zb, ldh, Z, csc_t, corr, rows, n, H, dWd)
-    csc_ptr, csc_row, csc_val = csc_in
+    self._dgrad(G, ldn, corr, alpha, Wg, ldh, Wd, tpool, row0, rows, n, H, Z, self.act, dA, dbe)
+    self._wgrad(G, ldn, Zs, ldh, Z, csc_t, corr, alpha, rows, n, H, dWd, dbd)
+    csc_ptr, csc_row, csc_val, _ = csc_in
     call('rcd_ae_encoder_wgrad', ptr(dA), H, ptr(csc_ptr), ptr(csc_row), ptr(csc_val), ptr(pool.row_inv_norm), row0,
          n_in, ptr(dWe))
 
@@ -385,7 +417,7 @@ class TrainEngine:
     n = tpool.n
     world, rank = self._world()
     t_items = tpool.items if tpool.negative_sampling else None
-    csc = self._slice_csc(tpool, row0, rows, n, 't_')
+    csc = self._slice_csc(tpool, row0, rows, n, 't_') if train else None
     users = pool.users[row0:row0 + rows]
 
     # slab: [dV_rows n*D | dbias n (pad 4) | dU rows of ALL ranks (other ranks' blocks zero) | pad 2 | loss hi, lo]
@@ -408,12 +440,12 @@ class TrainEngine:
     Ub = b.get('Zb', rows * ldd, torch.bfloat16)
     call('rcd_gather_rows', ptr(U), D, ptr(users), rows, self.act, ptr(Ub), ldd, ptr(Ue))
 
-    dO, ldn, O, corr = self._decoder_and_loss(Ub, ldd, Vg, bg, rows, n, D, inv_b, tpool, row0, csc, loss_slot,
-                                              dbias)
+    G, ldn, corr, alpha, Us = self._decoder_and_loss(Ub, ldd, Ue, Vg, bg, rows, n, D, inv_b, tpool, row0, loss_slot,
+                                                     train)
     if not train:
       return
-    self._dgrad(dO, ldn, O, Vg, ldd, V, tpool, row0, rows, n, D, inv_b, Ue, self.act, dU, None)
-    self._wgrad(dO, ldn, Ub, ldd, Ue, csc, corr, rows, n, D, dV)
+    self._dgrad(G, ldn, corr, alpha, Vg, ldd, V, tpool, row0, rows, n, D, Ue, self.act, dU, None)
+    self._wgrad(G, ldn, Us, ldd, Ue, csc, corr, alpha, rows, n, D, dV, dbias)
 
     self._reduce_slab(slab, loss_slot)
     self.last = {'n': n, 'dV': dV.view(n, D), 'dbias': dbias, 'dU': dU.view(rows, D)}

@@ -17,7 +17,7 @@ from torch.nn import BCEWithLogitsLoss
 
 from . import __version__
 from . import _native
-from .data import RecommendationDataLoader, BatchCollator, collate_pool
+from .data import RecommendationDataLoader, BatchCollator, collate_pool, collate_pool_launch, collate_pool_finish
 from .engine import Optimizer, TrainEngine, shard_rows
 from .losses import MSELoss, MultinomialNLLLoss
 from .nn import FactorizationModel
@@ -351,9 +351,26 @@ class Recoder(object):
     csr = ds.device_csr()
     tcsr = ds.device_target_csr()
     gstep = batch_size * world
-    for index in dataloader.pools():
-      pool = collate_pool(csr, index, dataloader.negative_sampling)
-      tpool = collate_pool(tcsr, index, dataloader.negative_sampling) if tcsr is not None else None
+    ns = dataloader.negative_sampling
+
+    def launch(index):
+      pool = collate_pool_launch(csr, index, ns)
+      tpool = collate_pool_launch(tcsr, index, ns) if tcsr is not None else None
+      return pool, tpool
+
+    # One-pool-ahead software pipeline: the collate of pool i+1 is enqueued BEFORE the training steps of pool i, so
+    # its (n, nnz) read-back — the only host sync of the data path — is hidden behind those steps and the host can
+    # enqueue step i+1 while step i still runs.
+    pools = iter(dataloader.pools())
+    first = next(pools, None)
+    nxt = launch(first) if first is not None else None
+    while nxt is not None:
+      pool, tpool = nxt
+      collate_pool_finish(pool)
+      if tpool is not None:
+        collate_pool_finish(tpool)
+      index = next(pools, None)
+      nxt = launch(index) if index is not None else None
       for row0, rows, global_rows in shard_rows(pool.num_rows, gstep, world, rank):
         yield pool, tpool, row0, rows, global_rows
 
@@ -396,7 +413,10 @@ class Recoder(object):
         steps_this_epoch += 1
         num_items = (tpool or pool).n
         if self._sync_loss_every_step:
-          last_loss = self.engine.last_loss_to_host()
+          # the reference's per-step `loss.item()` (model.py:404), read one step late so that the host never waits
+          # for the step it has just enqueued
+          prev = self.engine.loss_to_host_deferred()
+          last_loss = prev if prev is not None else last_loss
         if steps_this_epoch % refresh_every == 0:
           if not self._sync_loss_every_step:
             last_loss = float(self.engine.losses(1)[0])
@@ -407,6 +427,8 @@ class Recoder(object):
         if batch_itr % iters_per_epoch == 0:
           break
 
+      if self._sync_loss_every_step:
+        self.engine.drain_deferred_loss()
       if steps_this_epoch:
         last_loss = float(self.engine.losses(1)[0])
       self.last_epoch_losses = self.engine.losses(steps_this_epoch).numpy() if steps_this_epoch else np.zeros(0)

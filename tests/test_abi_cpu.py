@@ -28,7 +28,7 @@ def lib():
 def test_header_declares_entry_points():
   syms = declared_symbols()
   assert len(syms) >= 25
-  for must in ('rcd_collate', 'rcd_gather_rows', 'rcd_ae_encoder_fwd', 'rcd_decoder_fwd', 'rcd_loss_grad',
+  for must in ('rcd_collate', 'rcd_gather_rows', 'rcd_ae_encoder_fwd', 'rcd_decoder_fwd', 'rcd_decoder_fwd_loss', 'rcd_sddmm', 'rcd_loss_finish',
                'rcd_decoder_dgrad', 'rcd_decoder_wgrad', 'rcd_adam_step', 'rcd_sgd_step', 'rcd_host_stage_rows'):
     assert must in syms
 

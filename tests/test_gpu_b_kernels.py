@@ -116,3 +116,135 @@ def test_gather_rows(H):
   assert torch.equal(out[:, :H], ref.to(torch.bfloat16)) or \
       (out[:, :H].float() - ref).abs().max() < 1e-2
   assert (out[:, H:] == 0).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused decoder forward / loss epilogue, sparse loss side, CSC view, bias-gradient side product
+# ---------------------------------------------------------------------------------------------------------------
+def _bf16_mat(r, c, g, scale=1.0):
+  ld = (c + 7) // 8 * 8
+  t = torch.zeros(r, ld, dtype=torch.bfloat16, device='cuda')
+  t[:, :c] = (torch.randn(r, c, generator=g, device='cuda') * scale).to(torch.bfloat16)
+  return t, ld
+
+
+def _sparse_targets(rows, n, per_row, g, ratings=False):
+  """Random CSR targets with unique sorted columns per row (row 3 left empty)."""
+  ptr_, cols, vals = [0], [], []
+  for r in range(rows):
+    k = 0 if r == 3 else int(torch.randint(1, per_row * 2, (1,), generator=g).item())
+    c = torch.randperm(n, generator=g)[:min(k, n)].sort().values
+    cols.append(c)
+    vals.append(torch.randint(1, 6, (len(c),), generator=g).float() if ratings else torch.ones(len(c)))
+    ptr_.append(ptr_[-1] + len(c))
+  return (torch.tensor(ptr_, dtype=torch.int32, device='cuda'), torch.cat(cols).to(torch.int32).cuda(),
+          torch.cat(vals).cuda())
+
+
+@pytest.mark.parametrize('loss', ['mse', 'logloss', 'logistic'])
+@pytest.mark.parametrize('rows,n,H', [(128, 256, 64), (333, 3001, 72), (1024, 20000, 512), (40, 100, 16)])
+def test_decoder_fwd_loss_and_finish(loss, rows, n, H):
+  gcpu = torch.Generator().manual_seed(rows + n)
+  g = torch.Generator(device='cuda').manual_seed(rows * 7 + H)
+  Zb, ldh = _bf16_mat(rows, H, g, 0.5)
+  Wg, _ = _bf16_mat(n, H, g, 0.3)
+  bias = torch.randn(n, generator=g, device='cuda') * 0.2
+  row_ptr, cols, vals = _sparse_targets(rows, n, 12, gcpu, ratings=(loss == 'mse'))
+  nnz = int(row_ptr[-1])
+  conf = 2.0 if loss == 'mse' else 0.0
+  inv_b = 1.0 / rows
+  lid = _native.LOSS_IDS[loss]
+  lib = _native.load()
+  # reference on the same bf16 operands, fp32 math
+  O = Zb[:, :H].float() @ Wg[:, :H].float().t() + bias
+  T = torch.zeros(rows, n, device='cuda')
+  rix = torch.repeat_interleave(torch.arange(rows, device='cuda'), (row_ptr[1:] - row_ptr[:-1]).long())
+  T[rix, cols.long()] = vals
+  if loss == 'mse':
+    w = 1 + conf * (T > 0).float()
+    ref_loss = (w * (O - T) ** 2).sum() * inv_b
+    ref_dense = 2 * O * inv_b
+    ref_full = 2 * w * (O - T) * inv_b
+  elif loss == 'logloss':
+    ref_loss = (-T * torch.log_softmax(O, dim=1)).sum() * inv_b
+    ref_full = (torch.softmax(O, dim=1) * T.sum(1, keepdim=True) - T) * inv_b
+    ref_dense = None
+  else:
+    ref_loss = torch.nn.functional.binary_cross_entropy_with_logits(O, T, reduction='sum') * inv_b
+    ref_dense = torch.sigmoid(O) * inv_b
+    ref_full = (torch.sigmoid(O) - T) * inv_b
+  o_nnz = torch.empty(max(nnz, 1), device='cuda'); corr = torch.empty(max(nnz, 1), device='cuda')
+  row_ref = torch.empty(rows, device='cuda')
+  call('rcd_sddmm', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bias), H, ptr(row_ptr), ptr(cols), ptr(vals), 0, rows, lid, conf,
+       inv_b, ptr(o_nnz), ptr(corr), ptr(row_ref))
+  torch.testing.assert_close(o_nnz[:nnz], O[rix, cols.long()], rtol=1e-4, atol=1e-4)
+  ldn = (n + 7) // 8 * 8
+  G = torch.full((rows, ldn), float('nan'), dtype=torch.bfloat16, device='cuda')
+  sc = lib.rcd_decoder_stat_cols(n)
+  stat = torch.full((rows, sc), float('nan'), device='cuda')
+  call('rcd_decoder_fwd_loss', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bias), rows, n, H, lid, inv_b,
+       ptr(row_ref) if loss == 'logloss' else None, ptr(G), ldn, ptr(stat), sc)
+  alpha = torch.empty(rows, device='cuda')
+  Zf = Zb[:, :H].float().contiguous()
+  Zs = torch.empty(rows, ldh, dtype=torch.bfloat16, device='cuda')
+  acc = torch.zeros(1, dtype=torch.float64, device='cuda')
+  bad = torch.zeros(1, dtype=torch.int32, device='cuda')
+  row_sum = T.sum(1).contiguous()
+  call('rcd_loss_finish', ptr(stat), sc, sc, rows, lid, conf, inv_b, ptr(row_ref), ptr(row_sum), ptr(row_ptr),
+       ptr(vals), ptr(o_nnz), 0, ptr(alpha), ptr(Zf), H, ptr(Zs), ldh, ptr(acc), ptr(bad))
+  torch.cuda.synchronize()
+  assert int(bad.item()) == 0
+  assert not torch.isnan(G[:, :n].float()).any()
+  assert float(acc.item()) == pytest.approx(float(ref_loss.item()), rel=2e-4)
+  # full dL/dlogits = alpha * G + sparse part scattered at the stored targets
+  full = G[:, :n].float() * (alpha[:, None] if loss == 'logloss' else 1.0)
+  full[rix, cols.long()] += corr[:nnz]
+  err = (full - ref_full).norm() / ref_full.norm()
+  assert err < 4e-3, err   # bf16 storage of G: 2^-9 relative per element
+  if ref_dense is not None:
+    torch.testing.assert_close(G[:, :n].float(), ref_dense, rtol=1e-2, atol=1e-6)
+  if loss == 'logloss':
+    torch.testing.assert_close(Zs[:, :H].float(), (alpha[:, None] * Zf), rtol=1e-2, atol=1e-7)
+    assert (Zs[:, H:] == 0).all()
+
+
+@pytest.mark.parametrize('rows,n,per_row', [(64, 50, 10), (2048, 300, 40), (500, 4000, 30)])
+def test_slice_csc_matches_scipy(rows, n, per_row):
+  import scipy.sparse as sp
+  g = torch.Generator().manual_seed(rows)
+  row_ptr, cols, vals = _sparse_targets(rows, n, per_row, g, ratings=True)
+  nnz = int(row_ptr[-1])
+  lib = _native.load()
+  csc_ptr = torch.empty(n + 1, dtype=torch.int32, device='cuda')
+  csc_row = torch.empty(nnz, dtype=torch.int32, device='cuda')
+  csc_val = torch.empty(nnz, device='cuda')
+  csc_src = torch.empty(nnz, dtype=torch.int32, device='cuda')
+  sb = lib.rcd_slice_csc_scratch_bytes(n, nnz)
+  scratch = torch.empty(sb, dtype=torch.uint8, device='cuda')
+  call('rcd_slice_csc', ptr(row_ptr), ptr(cols), ptr(vals), 0, rows, n, ptr(csc_ptr), ptr(csc_row), ptr(csc_val),
+       ptr(csc_src), ptr(scratch), sb)
+  m = sp.csr_matrix((vals.cpu().numpy(), cols.cpu().numpy(), row_ptr.cpu().numpy()), shape=(rows, n)).tocsc()
+  m.sort_indices()
+  assert np.array_equal(csc_ptr.cpu().numpy(), m.indptr)
+  assert np.array_equal(csc_row.cpu().numpy(), m.indices)
+  assert np.array_equal(csc_val.cpu().numpy(), m.data)
+  src = csc_src.cpu().numpy()
+  assert np.array_equal(vals.cpu().numpy()[src], m.data) and np.array_equal(cols.cpu().numpy()[src],
+                                                                           np.repeat(np.arange(n), np.diff(m.indptr)))
+
+
+@pytest.mark.parametrize('engine', [_native.GEMM_SIMT, _native.GEMM_TCGEN05])
+@pytest.mark.parametrize('rows,n,H,weighted', [(256, 1000, 64, True), (300, 777, 200, False), (2048, 5000, 512, True)])
+def test_wgrad_bias_side_product(engine, rows, n, H, weighted):
+  g = torch.Generator(device='cuda').manual_seed(n)
+  G, ldn = _bf16_mat(rows, n, g, 0.1)
+  Zs, ldh = _bf16_mat(rows, H, g, 0.5)
+  w = torch.rand(rows, generator=g, device='cuda') if weighted else None
+  dW = torch.full((n, H), float('nan'), device='cuda')
+  db = torch.full((n,), float('nan'), device='cuda')
+  call('rcd_decoder_wgrad', ptr(G), ldn, ptr(Zs), ldh, rows, n, H, ptr(dW), H, ptr(w), ptr(db), engine)
+  torch.cuda.synchronize()
+  ref_dW = G[:, :n].float().t() @ Zs[:, :H].float()
+  ref_db = (G[:, :n].float() * (w[:, None] if weighted else 1.0)).sum(0)
+  torch.testing.assert_close(dW, ref_dW, rtol=1e-4, atol=1e-3 * rows ** 0.5)
+  torch.testing.assert_close(db, ref_db, rtol=1e-4, atol=1e-4)
