@@ -203,7 +203,7 @@ def kernel_work(name, w, rows, n, n_in, nnz_rows, tables):
   Figures are the per-unit numbers of DESIGN.md §4."""
   H, I = w['width'], w['items']
   dense = 2.0 * rows * n * H
-  if name in ('rcd_decoder_fwd', 'rcd_decoder_dgrad', 'rcd_decoder_wgrad'):
+  if name in ('rcd_decoder_fwd', 'rcd_decoder_fwd_loss', 'rcd_decoder_dgrad', 'rcd_decoder_wgrad'):
     return 'tensor', dense
   if name == 'rcd_adam_step':
     params, grads = tables
