@@ -146,7 +146,7 @@ def workload_config(args, w, U, batch, world):
   return {'workload': w['desc'], 'users': U, 'items': w['items'], 'nnz_per_user': w['nnz'], 'model': w['model'],
           'width': w['width'], 'loss': w['loss'], 'optimizer': 'adam (dense, torch.optim.Adam semantics)',
           'batch_per_gpu': batch, 'global_batch': batch * world, 'negative_sampling': True,
-          'parallelism': 'dp%d' % world,
+          'parallelism': 'dp%d' % world, 'dp_exchange': args.dp_exchange,
           'l2': 'per-step working set (embedding tables + Adam state + logits) is larger than the 126 MB L2'}
 
 
@@ -206,8 +206,12 @@ def kernel_work(name, w, rows, n, n_in, nnz_rows, tables):
   if name in ('rcd_decoder_fwd', 'rcd_decoder_fwd_loss', 'rcd_decoder_dgrad', 'rcd_decoder_wgrad'):
     return 'tensor', dense
   if name == 'rcd_adam_step':
-    params, grads = tables
+    params, grads = tables[0], tables[1]
     return 'hbm', 24.0 * params + 4.0 * grads
+  if name == 'rcd_adam_step_p2p':
+    # per rank: NVLink ingress = the other ranks' gradient rows of the owned shard + the other ranks' pushed rows
+    params, grads, world = tables if len(tables) == 3 else (tables[0], tables[1], 1)
+    return 'nvlink', 4.0 * (grads + params) * (world - 1) / max(world, 1)
   if name == 'rcd_loss_grad':
     return 'hbm', 4.0 * rows * n            # read bf16 logits, write bf16 dlogits
   if name == 'rcd_gather_rows':
@@ -267,7 +271,7 @@ def b200_arm(args, w):
       model = DynamicAutoencoder(hidden_layers=[H], activation_type='tanh')
     else:
       model = MatrixFactorization(embedding_size=H, activation_type='none')
-    trainer = Recoder(model=model, use_cuda=True, optimizer_type='adam', loss=w['loss'])
+    trainer = Recoder(model=model, use_cuda=True, optimizer_type='adam', loss=w['loss'], dp_exchange=args.dp_exchange)
     ds = RecommendationDataset(matrix, device_resident=device_resident)
     st = {'n': [], 'launch0': 0, 'launch1': 0, 'bytes0': None, 'bytes1': None, 'clocks': None, 'warm': {},
           'dominant': None}
@@ -291,7 +295,7 @@ def b200_arm(args, w):
             tot = sum(a.elapsed_time(b) for a, b in use)
             warm[name] = tot / max(W - 1, 1)
           st['warm'] = warm
-          cand = {k: v for k, v in warm.items() if k != 'rcd_collate'}
+          cand = {k: v for k, v in warm.items() if k not in ('rcd_collate', 'rcd_adam_step_p2p', 'rcd_p2p_barrier')}
           st['dominant'] = max(cand, key=cand.get) if cand else None
           _native.PROFILE = {st['dominant']} if st['dominant'] else None
           _native.TIMINGS.clear()
@@ -353,10 +357,13 @@ def b200_arm(args, w):
     grads = n_avg * H + n_avg + users_per_step * H
   kinds = {}
   for name, ms in sorted(s_dev['warm'].items(), key=lambda kv: -kv[1]):
-    bound, work = kernel_work(name, w, B, n_avg, n_avg, nnz_rows, (s_dev['params'], grads))
+    bound, work = kernel_work(name, w, B, n_avg, n_avg, nnz_rows, (s_dev['params'], grads, world))
     entry = {'ms_per_step': round(ms, 4), 'bound': bound}
     if work:
-      if bound == 'tensor':
+      if bound == 'nvlink':
+        entry['achieved_gbs_ingress_per_gpu'] = round(work / (ms * 1e-3) / 1e9, 1)
+        entry['frac_of_770_gbs_peer_copy'] = round(entry['achieved_gbs_ingress_per_gpu'] / 770.0, 4)
+      elif bound == 'tensor':
         entry['achieved_tflops'] = round(work / (ms * 1e-3) / 1e12, 2)
         entry['frac_of_measured_sustained'] = round(entry['achieved_tflops'] / peaks['tensor_sustained'], 4)
       else:
@@ -365,7 +372,7 @@ def b200_arm(args, w):
     kinds[name] = entry
   roofline = None
   if dom and s_dev['dom_ms']:
-    bound, work = kernel_work(dom, w, B, n_avg, n_avg, nnz_rows, (s_dev['params'], grads))
+    bound, work = kernel_work(dom, w, B, n_avg, n_avg, nnz_rows, (s_dev['params'], grads, world))
     lps = s_dev.get('dom_launches_per_step', 1.0)
     if work:
       per_launch = work / lps
@@ -427,6 +434,8 @@ def main():
   ap.add_argument('--config', default='c3', choices=sorted(WORKLOADS))
   ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (default: the config\'s)')
   ap.add_argument('--users', type=int, default=0, help='use a user prefix of the matrix (0 = all)')
+  ap.add_argument('--dp-exchange', default='auto', choices=['auto', 'p2p', 'nccl'],
+                  help='N>1: fused peer-memory reduce-scatter/Adam/all-gather kernel (p2p) or NCCL all-reduce + full Adam')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--skip-e2e', action='store_true', help='profiling runs only: skip the host-staged leg')
   ap.add_argument('--no-profile', action='store_true', help='no CUDA-event kernel breakdown during warm-up')

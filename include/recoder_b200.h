@@ -224,6 +224,38 @@ int rcd_sparse_adam_step(float* p, float* m, float* v, int H, const float* grad_
 int rcd_scatter_pos(const int64_t* ids, int n, int32_t* pos, int reset, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * K9  data-parallel exchange over peer memory (NVLink 5 / NVSwitch) — no reference counterpart: the reference
+ *     is single-device.  One process per GPU; buffers peers must reach are cudaMalloc
+ *     allocations shared with CUDA IPC.  Pointer tables (`*_host`) are HOST arrays indexed by rank holding the
+ *     address of the same buffer as mapped in THIS process (own rank: the local allocation).
+ *     rcd_p2p_alloc/free   : zero-filled device allocation that can be exported (synchronous host calls)
+ *     rcd_p2p_export/open/close : 64-byte IPC handle of an allocation / mapping of a peer's handle
+ *     rcd_p2p_barrier      : stream-ordered barrier of all ranks; `flags` = per-rank uint32[RCD_MAX_PEERS] arrays,
+ *                            `seq` strictly increasing per call; bad_flag |= 4 if a peer does not arrive in timeout_s
+ *     rcd_p2p_reduce       : dst[i] = sum over ranks q (ascending) of src_q[offset + i], i < count (fp32)
+ *     rcd_adam_step_p2p    : fused reduce-scatter -> Adam -> all-gather.  This rank owns table rows
+ *                            [row_begin, row_end): g = sum_q grads_q[pos[row], :] (rank order; only rank
+ *                            pos[row]/grad_block_rows when grad_block_rows > 0), torch.optim.Adam update of the local
+ *                            p/m/v rows (same arithmetic as rcd_adam_step), new p row stored into EVERY rank's table.
+ *                            Callers bracket it with rcd_p2p_barrier (all slabs written / all pushes landed).
+ * ------------------------------------------------------------------------------------------------------- */
+#define RCD_MAX_PEERS 16
+#define RCD_P2P_HANDLE_BYTES 64
+int rcd_p2p_alloc(size_t bytes, void** out_host);
+int rcd_p2p_free(void* p);
+int rcd_p2p_export(const void* p, unsigned char* handle_host);
+int rcd_p2p_open(const unsigned char* handle_host, void** out_host);
+int rcd_p2p_close(void* p);
+int rcd_p2p_barrier(void* const* flags_host, int rank, int world, unsigned int seq, int32_t* bad_flag,
+                    double timeout_s, void* stream);
+int rcd_p2p_reduce(const float* const* src_host, int world, long long offset, long long count, float* dst,
+                   void* stream);
+int rcd_adam_step_p2p(float* const* tables_host, float* m, float* v, long long row_begin, long long row_end, int H,
+                      const float* const* grads_host, int ldg, const int32_t* pos, int grad_block_rows, int rank,
+                      int world, double lr, double beta1, double beta2, double eps, double weight_decay, long long t,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Telemetry / tests: L2 norm squared of a strided fp32 matrix (double accumulation), out_sq[0] += ...
  * ------------------------------------------------------------------------------------------------------- */
 int rcd_sumsq(const float* x, long long rows, int cols, int ld, double* out_sq, void* stream);

@@ -58,6 +58,15 @@ _SIGNATURES = {
   'rcd_sparse_adam_step': (c_int, [_P, _P, _P, c_int, _P, c_int, _P, c_int, c_double, c_double, c_double, c_double,
                                    c_longlong, _P]),
   'rcd_scatter_pos': (c_int, [_P, c_int, _P, c_int, _P]),
+  'rcd_p2p_alloc': (c_int, [c_size_t, _P]),
+  'rcd_p2p_free': (c_int, [_P]),
+  'rcd_p2p_export': (c_int, [_P, _P]),
+  'rcd_p2p_open': (c_int, [_P, _P]),
+  'rcd_p2p_close': (c_int, [_P]),
+  'rcd_p2p_barrier': (c_int, [_P, c_int, c_int, ctypes.c_uint, _P, c_double, _P]),
+  'rcd_p2p_reduce': (c_int, [_P, c_int, c_longlong, c_longlong, _P, _P]),
+  'rcd_adam_step_p2p': (c_int, [_P, _P, _P, c_longlong, c_longlong, c_int, _P, c_int, _P, c_int, c_int, c_int,
+                                c_double, c_double, c_double, c_double, c_double, c_longlong, _P]),
   'rcd_sumsq': (c_int, [_P, c_longlong, c_int, c_int, _P, _P]),
   'rcd_gemm_bf16': (c_int, [c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
 }

@@ -41,6 +41,12 @@ static inline int rcd_div_up(long long a, long long b) { return (int)((a + b - 1
 
 int rcd_num_sms();
 
+// per-rank base pointers of a buffer every rank has mapped (CUDA IPC): index = rank
+struct PeerPtrs {
+  void* p[RCD_MAX_PEERS];
+};
+int rcd_fill_peers(PeerPtrs* out, const void* const* ptrs_host, int world, const char* who);
+
 // ---- device helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -94,6 +94,77 @@ static __global__ void __launch_bounds__(256)
   }
 }
 
+// Fused reduce-scatter -> Adam -> all-gather over peer memory (data-parallel exchange).
+// This rank owns table rows [row_begin, row_begin + nrows): for each it sums the compact gradient rows of ALL ranks
+// (ld over NVLink from the peers' slabs, fixed rank order -> deterministic), applies the torch.optim.Adam update to its
+// shard of p / m / v, and stores the new parameter row into every rank's replica (st over NVLink).  Replaces
+// ncclAllReduce(slab) + a full-table Adam pass on every rank: the optimizer's HBM traffic drops by the world size and
+// no rank ever holds a reduced copy of the slab.  grad_block_rows > 0: gradient row g was produced by exactly one
+// rank, g / grad_block_rows (MF user rows), so only that peer is read.
+template <int VEC>
+static __global__ void __launch_bounds__(256)
+    k_adam_p2p(PeerPtrs tables, float* __restrict__ m, float* __restrict__ v, long long row_begin, long long nrows,
+               int H, PeerPtrs grads, int ldg, const int32_t* __restrict__ pos, int grad_block_rows, int rank, int world,
+               AdamScalars a) {
+  const int vpr = H / VEC;
+  const long long total = nrows * vpr;
+  float* __restrict__ p_local = reinterpret_cast<float*>(tables.p[rank]);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = row_begin + i / vpr;
+    const int h = (int)(i % vpr) * VEC;
+    const size_t off = (size_t)r * H + h;
+    const long long gr = pos ? (long long)__ldg(pos + r) : r;
+    if (VEC == 4) {
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gr >= 0) {
+        const size_t goff = (size_t)gr * ldg + h;
+        if (grad_block_rows > 0) {
+          g = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(grads.p[gr / grad_block_rows]) + goff));
+        } else {
+          for (int q0 = 0; q0 < world; q0 += 4) {  // up to four peer loads in flight, summed in rank order
+            float4 t[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              t[j] = (q0 + j < world)
+                         ? __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(grads.p[q0 + j]) + goff))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              g.x += t[j].x; g.y += t[j].y; g.z += t[j].z; g.w += t[j].w;
+            }
+          }
+        }
+      }
+      float4 pp = __ldcs(reinterpret_cast<const float4*>(p_local + off));
+      float4 mm = __ldcs(reinterpret_cast<const float4*>(m + off));
+      float4 vv = __ldcs(reinterpret_cast<const float4*>(v + off));
+      adam_update(pp.x, mm.x, vv.x, g.x, a);
+      adam_update(pp.y, mm.y, vv.y, g.y, a);
+      adam_update(pp.z, mm.z, vv.z, g.z, a);
+      adam_update(pp.w, mm.w, vv.w, g.w, a);
+      __stcs(reinterpret_cast<float4*>(m + off), mm);
+      __stcs(reinterpret_cast<float4*>(v + off), vv);
+      for (int q = 0; q < world; ++q) __stcg(reinterpret_cast<float4*>(reinterpret_cast<float*>(tables.p[q]) + off), pp);
+    } else {
+      float g = 0.f;
+      if (gr >= 0) {
+        const size_t goff = (size_t)gr * ldg + h;
+        if (grad_block_rows > 0) {
+          g = __ldcg(reinterpret_cast<const float*>(grads.p[gr / grad_block_rows]) + goff);
+        } else {
+          for (int q = 0; q < world; ++q) g += __ldcg(reinterpret_cast<const float*>(grads.p[q]) + goff);
+        }
+      }
+      float pp = p_local[off], mm = m[off], vv = v[off];
+      adam_update(pp, mm, vv, g, a);
+      m[off] = mm;
+      v[off] = vv;
+      for (int q = 0; q < world; ++q) __stcg(reinterpret_cast<float*>(tables.p[q]) + off, pp);
+    }
+  }
+}
+
 template <int VEC>
 static __global__ void __launch_bounds__(256)
     k_sgd(float* __restrict__ p, float* __restrict__ buf, long long rows, int H, const float* __restrict__ grad_rows,
@@ -175,6 +246,39 @@ RCD_EXPORT int rcd_adam_step(float* p, float* m, float* v, long long rows, int H
     k_adam<4><<<stream_grid(rows * (H / 4)), 256, 0, st>>>(p, m, v, rows, H, grad_rows, ldg, pos, a);
   else
     k_adam<1><<<stream_grid(rows * H), 256, 0, st>>>(p, m, v, rows, H, grad_rows, ldg, pos, a);
+  RCD_LAUNCH_CHECK();
+  return RCD_OK;
+}
+
+RCD_EXPORT int rcd_adam_step_p2p(float* const* tables_host, float* m, float* v, long long row_begin, long long row_end,
+                                 int H, const float* const* grads_host, int ldg, const int32_t* pos, int grad_block_rows,
+                                 int rank, int world, double lr, double beta1, double beta2, double eps,
+                                 double weight_decay, long long t, void* stream) {
+  RCD_CHECK_ARG(m && v && H > 0 && t >= 1 && row_begin >= 0 && row_end >= row_begin, "bad arguments");
+  RCD_CHECK_ARG(rank >= 0 && rank < world && ldg >= H && grad_block_rows >= 0, "bad arguments");
+  PeerPtrs tabs, grads;
+  int rc = rcd_fill_peers(&tabs, reinterpret_cast<const void* const*>(tables_host), world, "rcd_adam_step_p2p");
+  if (rc != RCD_OK) return rc;
+  rc = rcd_fill_peers(&grads, reinterpret_cast<const void* const*>(grads_host), world, "rcd_adam_step_p2p");
+  if (rc != RCD_OK) return rc;
+  const long long nrows = row_end - row_begin;
+  if (nrows == 0) return RCD_OK;
+  AdamScalars a;
+  a.beta2 = (float)beta2; a.eps = (float)eps; a.wd = (float)weight_decay;
+  a.omb1 = (float)(1.0 - beta1); a.omb2 = (float)(1.0 - beta2);
+  const double bc1 = 1.0 - pow(beta1, (double)t);
+  const double bc2 = 1.0 - pow(beta2, (double)t);
+  a.step_size = (float)(lr / bc1);
+  a.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  bool vec = (H % 4 == 0) && (ldg % 4 == 0) && aligned16(m) && aligned16(v);
+  for (int q = 0; q < world; ++q) vec = vec && aligned16(tabs.p[q]) && aligned16(grads.p[q]);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec)
+    k_adam_p2p<4><<<stream_grid(nrows * (H / 4)), 256, 0, st>>>(tabs, m, v, row_begin, nrows, H, grads, ldg, pos,
+                                                               grad_block_rows, rank, world, a);
+  else
+    k_adam_p2p<1><<<stream_grid(nrows * H), 256, 0, st>>>(tabs, m, v, row_begin, nrows, H, grads, ldg, pos,
+                                                         grad_block_rows, rank, world, a);
   RCD_LAUNCH_CHECK();
   return RCD_OK;
 }

@@ -82,6 +82,7 @@ class ParamState:
     self.step = 0
     self.m = None   # Adam exp_avg / SGD momentum buffer
     self.v = None   # Adam exp_avg_sq
+    self.shared = None  # p2p.SharedBuffer holding `p` when the table lives in peer-mapped memory
 
   def view2d(self):
     t = self.p
@@ -136,6 +137,34 @@ class Optimizer:
       call('rcd_sgd_step', ptr(st.p), ptr(st.m), rows, H, ptr(grad), ldg, ptr(pos), float(self.lr), SGD_MOMENTUM,
            float(st.weight_decay))
 
+  def step_param_p2p(self, name, ctx, grads_table, ldg, pos, grad_block_rows=0):
+    """Fused reduce-scatter -> Adam -> all-gather over peer memory (`rcd_adam_step_p2p`): this rank updates its row
+    shard of the table from the sum of all ranks' compact gradients and stores the new rows into every replica.
+    m / v are full-size tensors of which only the owned rows are live (`gather_shards` completes them)."""
+    st = self.states[name]
+    assert self.type == 'adam' and not st.sparse and st.shared is not None
+    self._ensure(st)
+    st.step += 1
+    rows, H = st.view2d()
+    lo, hi = ctx.owned_rows(rows)
+    call('rcd_adam_step_p2p', st.shared.ptr_table(), ptr(st.m), ptr(st.v), lo, hi, H, grads_table, ldg, ptr(pos),
+         int(grad_block_rows), ctx.rank, ctx.world, float(self.lr), ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS,
+         float(st.weight_decay), st.step)
+
+  def gather_shards(self, ctx):
+    """Completes the row-sharded Adam state (m, v) of peer-memory tables on every rank (before a checkpoint)."""
+    import torch.distributed as dist
+    for st in self.states.values():
+      if st.shared is None or st.m is None:
+        continue
+      rows, _ = st.view2d()
+      per = (rows + ctx.world - 1) // ctx.world
+      for q in range(ctx.world):
+        lo, hi = min(q * per, rows), min((q + 1) * per, rows)
+        if hi > lo:
+          dist.broadcast(st.m[lo:hi], src=dist.get_global_rank(ctx.pg, q), group=ctx.pg)
+          dist.broadcast(st.v[lo:hi], src=dist.get_global_rank(ctx.pg, q), group=ctx.pg)
+
   # --- torch.optim-compatible state_dict (param index = position in named_parameters(), model.py:208-215) ----
   def state_dict(self, dense=True):
     names = [n for n, s in self.states.items() if s.sparse != dense]
@@ -185,7 +214,7 @@ class TrainEngine:
   LOSS_RING = 4096
 
   def __init__(self, kind, params, loss, confidence, activation, optimizer: Optimizer, gemm_engine=None,
-               process_group=None, tied=False):
+               process_group=None, tied=False, p2p=None):
     _native.require_cuda()
     self.kind = kind
     self.params = params          # dict of role -> (name, tensor)
@@ -196,6 +225,8 @@ class TrainEngine:
     self.gemm = _native.GEMM_TCGEN05 if gemm_engine is None else gemm_engine
     self.pg = process_group
     self.tied = tied
+    self.p2p = p2p                # p2p.P2PContext: exchange through peer memory instead of an NCCL all-reduce
+    self._slab_shared = None
     dev = next(iter(params.values()))[1].device
     self.device = dev
     self.buf = _Buffers(dev)
@@ -226,6 +257,8 @@ class TrainEngine:
     flag = int(self.bad_flag.item())
     if flag:
       self.bad_flag.zero_()
+      if flag & 4:
+        raise RuntimeError('recoder_b200: a peer rank did not reach the data-parallel barrier in time (flag %d)' % flag)
       raise FloatingPointError('recoder_b200: non-finite loss in a training step (flag %d: 1 = softmax row sum, '
                                '2 = loss value)' % flag)
 
@@ -343,6 +376,31 @@ class TrainEngine:
     call('rcd_csc_rows_accumulate', ptr(Zf32), H, ptr(csc_ptr), ptr(csc_row), ptr(csc_src), ptr(corr), n, ptr(dW),
          ptr(db))
 
+  def _slab(self, numel, capacity):
+    """The step's gradient slab: a grow-only private buffer, or (peer-memory exchange) a view of ONE shared
+    allocation of `capacity` floats that every rank has mapped."""
+    if self.p2p is None:
+      return self.buf.get('slab', numel, torch.float32)
+    if self._slab_shared is None or self._slab_shared.nbytes < 4 * numel:
+      # collective: every rank sees the same shapes, so every rank (re)allocates at the same step
+      torch.cuda.synchronize()
+      self._slab_shared = self.p2p.shared(4 * max(numel, capacity))
+    return self._slab_shared.view(torch.float32, numel)
+
+  def _p2p_begin(self, slab, loss_slot):
+    """Publishes this rank's slab (loss as hi/lo floats in its last two slots) and waits for all ranks."""
+    tail = slab[-2:]
+    hi = loss_slot.to(torch.float32)
+    tail[0:1].copy_(hi)
+    tail[1:2].copy_((loss_slot - hi.to(torch.float64)).to(torch.float32))
+    self.p2p.barrier(self.bad_flag)
+
+  def _p2p_reduce(self, name, offset, count):
+    """Sum over ranks of slab[offset : offset+count] into a private buffer (small replicated tensors)."""
+    out = self.buf.get(name, count, torch.float32)
+    call('rcd_p2p_reduce', self._slab_shared.ptr_table(), self.p2p.world, int(offset), int(count), ptr(out))
+    return out
+
   def _reduce_slab(self, slab, loss_slot):
     """Data-parallel exchange: ONE all-reduce over the gradient slab; the loss rides in its last 2 floats
     (hi/lo split of the double, so nothing is lost to fp32)."""
@@ -370,7 +428,7 @@ class TrainEngine:
     o_wd = n_in * H
     o_bd = o_wd + n * H
     o_be = o_bd + n4
-    slab = b.get('slab', o_be + h4 + 4, torch.float32)
+    slab = self._slab(o_be + h4 + 4, 2 * We.shape[0] * H + _round_up(We.shape[0], 4) + h4 + 4)
     dWe, dWd = slab[0:o_wd], slab[o_wd:o_bd]
     dbd, dbe = slab[o_bd:o_bd + n], slab[o_be:o_be + H]
 
@@ -396,8 +454,21 @@ class TrainEngine:
     call('rcd_ae_encoder_wgrad', ptr(dA), H, ptr(csc_ptr), ptr(csc_row), ptr(csc_val), ptr(pool.row_inv_norm), row0,
          n_in, ptr(dWe))
 
-    self._reduce_slab(slab, loss_slot)
     self.last = {'n': n, 'n_in': n_in, 'dWe': dWe.view(n_in, H), 'dWd': dWd.view(n, H), 'dbd': dbd, 'dbe': dbe}
+    if self.p2p is not None:
+      # peer-memory exchange: tables are row-sharded for the update and pushed to every replica by the same kernel;
+      # the small tensors (biases, loss) are summed over ranks and updated redundantly (identical on every rank)
+      self._p2p_begin(slab, loss_slot)
+      tail = self._p2p_reduce('tail', o_bd, slab.numel() - o_bd)
+      loss_slot.copy_(tail[-2:-1].to(torch.float64) + tail[-1:].to(torch.float64))
+      sh = self._slab_shared
+      self.opt.step_param_p2p(en_name, self.p2p, sh.ptr_table(0), H, pool.pos)
+      self.opt.step_param_p2p(de_name, self.p2p, sh.ptr_table(4 * o_wd), H, tpool.pos)
+      self.opt.step_param(enb_name, tail[n4:n4 + H], 1)
+      self.opt.step_param(deb_name, tail[0:n], 1, pos=tpool.pos)
+      self.p2p.barrier(self.bad_flag)   # all pushes have landed; the slabs may be overwritten
+      return
+    self._reduce_slab(slab, loss_slot)
 
     if self.tied:  # is_constrained: one table receives both gradients (recoder/nn.py:200)
       dWe.add_(dWd)
@@ -425,10 +496,10 @@ class TrainEngine:
     all_rows = rows * world
     o_b = n * D
     o_u = o_b + n4
-    slab = b.get('slab', o_u + all_rows * D + 4, torch.float32)
+    slab = self._slab(o_u + all_rows * D + 4, V.shape[0] * D + _round_up(V.shape[0], 4) + all_rows * D + 4)
     dV, dbias = slab[0:o_b], slab[o_b:o_b + n]
     dU_all = slab[o_u:o_u + all_rows * D]
-    if world > 1:
+    if world > 1 and self.p2p is None:
       dU_all.zero_()
     dU = dU_all[rank * rows * D:(rank + 1) * rows * D]
 
@@ -447,8 +518,9 @@ class TrainEngine:
     self._dgrad(G, ldn, corr, alpha, Vg, ldd, V, tpool, row0, rows, n, D, Ue, self.act, dU, None)
     self._wgrad(G, ldn, Us, ldd, Ue, csc, corr, alpha, rows, n, D, dV, dbias)
 
-    self._reduce_slab(slab, loss_slot)
     self.last = {'n': n, 'dV': dV.view(n, D), 'dbias': dbias, 'dU': dU.view(rows, D)}
+    if self.p2p is None:
+      self._reduce_slab(slab, loss_slot)
 
     # In DP the pool holds the GLOBAL batch and rank r works on its r-th block of `rows` rows, so the users
     # of all ranks are the pool rows of the whole global slice.
@@ -459,6 +531,19 @@ class TrainEngine:
       upos.fill_(-1)
       self._upos_init = True
     call('rcd_scatter_pos', ptr(all_users), all_rows, ptr(upos), 0)
+    if self.p2p is not None:
+      # user-row gradients are produced by exactly one rank each: block q of dU_all lives in rank q's slab
+      self._p2p_begin(slab, loss_slot)
+      dbias_sum = self._p2p_reduce('tail', o_b, n4)
+      lsum = self._p2p_reduce('tail_loss', slab.numel() - 2, 2)
+      loss_slot.copy_(lsum[0:1].to(torch.float64) + lsum[1:2].to(torch.float64))
+      sh = self._slab_shared
+      self.opt.step_param_p2p(u_name, self.p2p, sh.ptr_table(4 * o_u), D, upos, grad_block_rows=rows)
+      call('rcd_scatter_pos', ptr(all_users), all_rows, ptr(upos), 1)
+      self.opt.step_param_p2p(v_name, self.p2p, sh.ptr_table(0), D, tpool.pos)
+      self.opt.step_param(bias_name, dbias_sum[0:n], 1, pos=tpool.pos)
+      self.p2p.barrier(self.bad_flag)
+      return
     self.opt.step_param(u_name, dU_all, D, pos=upos, ids=all_users, n_ids=all_rows)
     call('rcd_scatter_pos', ptr(all_users), all_rows, ptr(upos), 1)
     self.opt.step_param(v_name, dV, D, pos=tpool.pos, ids=tpool.items_buf, n_ids=n)

@@ -58,6 +58,10 @@ class Recoder(object):
     process_group (optional, extension): torch.distributed group for data-parallel training; defaults to the
       WORLD group when torch.distributed is initialised with more than one rank.
     gemm_engine (optional, extension): _native.GEMM_TCGEN05 (default) or _native.GEMM_SIMT (validation).
+    dp_exchange (optional, extension): how data-parallel ranks combine a step — 'p2p': embedding tables and the
+      gradient slab live in CUDA-IPC peer memory and one fused kernel per table does reduce-scatter -> Adam ->
+      all-gather over NVLink (dense Adam, untied weights); 'nccl': one all-reduce of the slab, then a full Adam
+      pass on every rank; 'auto' (default): 'p2p' when it applies, else 'nccl'.
   """
 
   def __init__(self, model: FactorizationModel,
@@ -65,7 +69,7 @@ class Recoder(object):
                optimizer_type='sgd', loss='mse',
                loss_params=None, use_cuda=False,
                user_based=True, item_based=True,
-               process_group=None, gemm_engine=None):
+               process_group=None, gemm_engine=None, dp_exchange='auto'):
 
     self.model = model
     self.num_items = num_items
@@ -78,6 +82,10 @@ class Recoder(object):
     self.item_based = item_based
     self.process_group = process_group
     self.gemm_engine = gemm_engine
+    if dp_exchange not in ('auto', 'p2p', 'nccl'):
+      raise ValueError("dp_exchange must be 'auto', 'p2p' or 'nccl'")
+    self.dp_exchange = dp_exchange
+    self._p2p = None
 
     if self.use_cuda:
       self.device = torch.device('cuda')
@@ -154,16 +162,55 @@ class Recoder(object):
       self.optimizer.load_state_dict(self.__sparse_optimizer_state_dict, dense=False)
       self.__sparse_optimizer_state_dict = None
 
-  def __init_engine(self):
-    kind, roles, activation, tied = self.model._engine_spec()
-    loss_kind, confidence = self.__loss_spec()
+  def __resolve_pg(self):
     pg = self.process_group
     if pg is None:
       import torch.distributed as dist
       if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         pg = dist.group.WORLD
+    return pg
+
+  def __init_dp(self):
+    """Data-parallel set-up (once): replicas start from rank 0's parameters; for the peer-memory exchange the
+    embedding tables move into CUDA-IPC allocations every rank maps (`p2p.SharedBuffer`)."""
+    pg = self.__resolve_pg()
+    if pg is None or getattr(self, '_dp_ready', False):
+      return
+    import torch.distributed as dist
+    if dist.get_world_size(pg) < 2:
+      return
+    for p in self.model.parameters():
+      dist.broadcast(p.data, src=dist.get_global_rank(pg, 0), group=pg)
+    self._dp_ready = True
+    self._p2p_buffers = {}
+    if self.dp_exchange == 'nccl':
+      return
+    from .p2p import P2PContext
+    _, roles, _, tied = self.model._engine_spec()
+    applies = (self.optimizer_type == 'adam' and not tied and not self.model._sparse_param_names()
+               and P2PContext.available(pg))
+    if not applies:
+      if self.dp_exchange == 'p2p':
+        raise RuntimeError("dp_exchange='p2p' needs dense Adam, untied weights and one NCCL rank per GPU with "
+                           'peer access between all GPUs')
+      return
+    self._p2p = P2PContext(pg)
+    named = dict(self.model.named_parameters())
+    for role in ('en_w', 'de_w', 'user_w', 'item_w'):
+      if role in roles:
+        name = roles[role][0]
+        buf, view = self._p2p.shared_like(named[name].data)
+        named[name].data = view
+        self._p2p_buffers[name] = buf
+
+  def __init_engine(self):
+    kind, roles, activation, tied = self.model._engine_spec()
+    loss_kind, confidence = self.__loss_spec()
+    pg = self.__resolve_pg()
+    for name, buf in getattr(self, '_p2p_buffers', {}).items():
+      self.optimizer.states[name].shared = buf
     self.engine = TrainEngine(kind, roles, loss_kind, confidence, activation, self.optimizer,
-                              gemm_engine=self.gemm_engine, process_group=pg, tied=tied)
+                              gemm_engine=self.gemm_engine, process_group=pg, tied=tied, p2p=self._p2p)
 
   def init_from_model_file(self, model_file):
     """
@@ -202,6 +249,8 @@ class Recoder(object):
     """
     checkpoint_file = "{}_epoch_{}.model".format(model_checkpoint_prefix, self.current_epoch)
     log.info("Saving model to {}".format(checkpoint_file))
+    if self._p2p is not None and self.optimizer is not None:
+      self.optimizer.gather_shards(self._p2p)   # collective: every rank must call save_state
     current_state = {
       'recoder_version': __version__,
       'model_params': self.model.model_params(),
@@ -222,7 +271,8 @@ class Recoder(object):
       current_state['loss'] = self.loss
       current_state['loss_params'] = self.loss_params
 
-    torch.save(current_state, checkpoint_file)
+    if self._world()[1] == 0:
+      torch.save(current_state, checkpoint_file)
     return checkpoint_file
 
   def __init_training(self, train_dataset, lr, weight_decay):
@@ -253,6 +303,7 @@ class Recoder(object):
     self.__loss_spec()  # raises ValueError for unknown / missing losses before touching the device
     self.__require_cuda()
     self.__init_model()
+    self.__init_dp()
     self.__init_optimizer(lr=lr, weight_decay=weight_decay)
     self.__init_engine()
 
@@ -447,9 +498,9 @@ class Recoder(object):
       progress_bar.set_postfix(postfix)
       progress_bar.close()
 
-      if model_checkpoint_prefix and rank == 0 and \
+      if model_checkpoint_prefix and \
           ((checkpoint_freq > 0 and epoch % checkpoint_freq == 0) or epoch == num_epochs):
-        self.save_state(model_checkpoint_prefix)
+        self.save_state(model_checkpoint_prefix)   # every rank calls it; rank 0 writes the file
 
   def _validate(self, val_dataloader):
     """Average loss over the validation batches (reference model.py:439-452); forward + loss kernels only."""

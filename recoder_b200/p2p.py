@@ -1,0 +1,134 @@
+"""Peer-memory plumbing of the data-parallel exchange: one process per GPU, buffers shared with
+CUDA IPC so that kernels address peer HBM directly over NVLink (`rcd_p2p_*`, `rcd_adam_step_p2p`).
+
+`torch.distributed` is used for exactly one thing here: exchanging the 64-byte IPC handles (and agreeing that every
+rank could map every peer).  The reference has no multi-GPU code; nothing here has a reference counterpart.
+"""
+import ctypes
+
+import torch
+
+from . import _native
+
+HANDLE_BYTES = 64
+MAX_PEERS = 16
+
+
+class _RawCudaMemory:
+  """Exposes a raw device allocation through __cuda_array_interface__ so torch can alias it as a tensor."""
+
+  def __init__(self, ptr, nbytes):
+    self.ptr = ptr
+    self.nbytes = nbytes
+    self.__cuda_array_interface__ = {'shape': (nbytes,), 'typestr': '|u1', 'data': (ptr, False), 'version': 2}
+
+
+class SharedBuffer:
+  """A device buffer of `nbytes` on every rank, each mapped into all the others.
+
+  `local` is a uint8 tensor aliasing this rank's allocation; `peer_ptrs[q]` is the address of rank q's
+  allocation in THIS process (own rank: the local address)."""
+
+  def __init__(self, ctx, nbytes):
+    import torch.distributed as dist
+    lib = _native.load()
+    self.ctx = ctx
+    self.nbytes = int(nbytes)
+    out = ctypes.c_void_p()
+    _native.check(lib.rcd_p2p_alloc(self.nbytes, ctypes.byref(out)), 'rcd_p2p_alloc')
+    self.local_ptr = int(out.value)
+    handle = (ctypes.c_ubyte * HANDLE_BYTES)()
+    _native.check(lib.rcd_p2p_export(ctypes.c_void_p(self.local_ptr), handle), 'rcd_p2p_export')
+    handles = [None] * ctx.world
+    dist.all_gather_object(handles, bytes(handle), group=ctx.pg)
+    self.peer_ptrs = []
+    self._opened = []
+    for q in range(ctx.world):
+      if q == ctx.rank:
+        self.peer_ptrs.append(self.local_ptr)
+        continue
+      h = (ctypes.c_ubyte * HANDLE_BYTES).from_buffer_copy(handles[q])
+      mapped = ctypes.c_void_p()
+      _native.check(lib.rcd_p2p_open(h, ctypes.byref(mapped)), 'rcd_p2p_open (rank %d)' % q)
+      self.peer_ptrs.append(int(mapped.value))
+      self._opened.append(int(mapped.value))
+    self._mem = _RawCudaMemory(self.local_ptr, self.nbytes)
+    self.local = torch.as_tensor(self._mem, device=torch.device('cuda', torch.cuda.current_device()))
+    assert self.local.data_ptr() == self.local_ptr
+
+  def view(self, dtype, numel, offset_bytes=0):
+    """Typed view on the local allocation."""
+    nbytes = numel * torch.empty((), dtype=dtype).element_size()
+    assert offset_bytes + nbytes <= self.nbytes
+    return self.local[offset_bytes:offset_bytes + nbytes].view(dtype)
+
+  def ptr_table(self, offset_bytes=0):
+    """HOST array of per-rank base addresses (+offset), the `*_host` argument of the rcd_p2p_* entry points."""
+    arr = (ctypes.c_void_p * self.ctx.world)()
+    for q, p in enumerate(self.peer_ptrs):
+      arr[q] = p + offset_bytes
+    return arr
+
+
+class P2PContext:
+  """Per-process state of the peer-memory exchange: rank/world, barrier flags, sequence counter."""
+
+  def __init__(self, pg):
+    import torch.distributed as dist
+    _native.require_cuda()
+    self.pg = pg
+    self.world = dist.get_world_size(pg)
+    self.rank = dist.get_rank(pg)
+    if self.world > MAX_PEERS:
+      raise RuntimeError('recoder_b200: peer-memory exchange supports up to %d ranks' % MAX_PEERS)
+    self.device = torch.device('cuda', torch.cuda.current_device())
+    self.flags = SharedBuffer(self, 4 * MAX_PEERS)
+    self._flag_table = self.flags.ptr_table()
+    self.seq = 0
+    self.barrier_timeout_s = 60.0
+
+  @staticmethod
+  def available(pg):
+    """True when every rank of `pg` sits on its own GPU of one node with peer access to all the others."""
+    import torch.distributed as dist
+    ok = 1
+    try:
+      if not torch.cuda.is_available() or dist.get_backend(pg) != 'nccl':
+        ok = 0
+      else:
+        me = torch.cuda.current_device()
+        devs = [None] * dist.get_world_size(pg)
+        dist.all_gather_object(devs, me, group=pg)
+        if len(set(devs)) != len(devs):
+          ok = 0
+        else:
+          for d in devs:
+            if d != me and not torch.cuda.can_device_access_peer(me, d):
+              ok = 0
+    except Exception:
+      ok = 0
+    flag = torch.tensor([ok], device='cuda' if torch.cuda.is_available() else 'cpu')
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=pg)
+    return bool(flag.item())
+
+  def shared(self, nbytes):
+    return SharedBuffer(self, nbytes)
+
+  def shared_like(self, tensor):
+    """Moves `tensor`'s contents into a new shared allocation; returns (buffer, tensor view of the same shape)."""
+    buf = SharedBuffer(self, max(tensor.numel() * tensor.element_size(), 16))
+    view = buf.view(tensor.dtype, tensor.numel()).view(tensor.shape)
+    view.copy_(tensor)
+    return buf, view
+
+  def barrier(self, bad_flag):
+    """Stream-ordered barrier of all ranks (`rcd_p2p_barrier`)."""
+    self.seq += 1
+    _native.call('rcd_p2p_barrier', self._flag_table, self.rank, self.world, self.seq, _native.ptr(bad_flag),
+                 float(self.barrier_timeout_s))
+
+  def owned_rows(self, rows):
+    """Contiguous row shard of this rank for a table of `rows` rows."""
+    per = (rows + self.world - 1) // self.world
+    lo = min(self.rank * per, rows)
+    return lo, min(lo + per, rows)
