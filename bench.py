@@ -303,8 +303,10 @@ def b200_arm(args, w):
         sampler.start()
         st['launch0'] = lib.rcd_launch_count()
         st['bytes0'] = dict(rdata.TRANSFER_BYTES)
+        trainer.engine.join()
         ev0.record()
       elif step == W + K:
+        trainer.engine.join()   # the optimizer / exchange kernels of the last step run on the update stream
         ev1.record()
         torch.cuda.synchronize()
         st['launch1'] = lib.rcd_launch_count()

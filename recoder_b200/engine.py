@@ -227,6 +227,11 @@ class TrainEngine:
     self.tied = tied
     self.p2p = p2p                # p2p.P2PContext: exchange through peer memory instead of an NCCL all-reduce
     self._slab_shared = None
+    import os
+    self.overlap = os.environ.get('RCD_OVERLAP', '1') != '0'
+    self.late_update = os.environ.get('RCD_LATE_UPDATE', '0') == '1'   # experiment: decoder-side update at the end
+    self._side = None
+    self._ready = {}
     dev = next(iter(params.values()))[1].device
     self.device = dev
     self.buf = _Buffers(dev)
@@ -248,12 +253,14 @@ class TrainEngine:
   def losses(self, last_k):
     """The last `last_k` step losses as a CPU float64 tensor (one sync)."""
     k = min(last_k, self.steps_done, self.LOSS_RING)
+    self.join()
     self.check_finite()
     idx = [(self.steps_done - k + j) % self.LOSS_RING for j in range(k)]
     return self.loss_ring[torch.tensor(idx, device=self.device, dtype=torch.long)].cpu() if k else torch.zeros(0)
 
   def check_finite(self):
     """Raises if a step produced a non-finite loss / softmax row sum (synchronises)."""
+    self.join()
     flag = int(self.bad_flag.item())
     if flag:
       self.bad_flag.zero_()
@@ -270,6 +277,8 @@ class TrainEngine:
       self._loss_host = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(4)]
       self._loss_pending = []
     i = (self.steps_done - 1) % self.LOSS_RING
+    if self.p2p is not None:
+      self.join()   # the global loss is produced on the update stream
     buf = self._loss_host[self.steps_done % len(self._loss_host)]
     buf.copy_(self.loss_ring[i:i + 1], non_blocking=True)
     ev = torch.cuda.Event()
@@ -313,6 +322,7 @@ class TrainEngine:
   def eval_loss(self, pool, row0, rows, target_pool=None):
     """Loss of one batch without touching the parameters (`Recoder._validate`, recoder/model.py:439-452)."""
     slot = self.buf.get('eval_loss', 1, torch.float64)
+    self.join()
     slot.zero_()
     if self.kind == 'ae':
       self._ae_step(pool, target_pool or pool, row0, rows, 1.0 / rows, slot, train=False)
@@ -357,15 +367,19 @@ class TrainEngine:
          ptr(Zf32), H, ptr(Zs), ldh, ptr(loss_slot), ptr(self.bad_flag))
     return G, ldn, corr, alpha, (Zs if Zs is not None else Zb)
 
-  def _dgrad(self, G, ldn, corr, alpha, Wg, ldh, W_master, tpool, row0, rows, n, H, Zf32, act, dA, db):
-    """dZ = alpha * (dense part: tcgen05 split-K GEMM over bf16 G) + sparse part (fp32, master table) -> dA, db."""
-    b = self.buf
+  def _sparse_dgrad(self, corr, W_master, tpool, row0, rows, n, H):
+    """fp32 sparse part of dZ (reads the MASTER table, so it is issued before that table's optimizer update).
+    Returns (partials buffer, splits): slot `splits` holds the sparse part, slots [0, splits) are for the GEMM."""
     splits = self.lib.rcd_decoder_dgrad_splits(rows, n, H)
-    partials = b.get('dz_partials', (splits + 1) * rows * H, torch.float32)
-    call('rcd_decoder_dgrad', ptr(G), ldn, ptr(Wg), ldh, rows, n, H, splits, ptr(partials), H, self.gemm)
+    partials = self.buf.get('dz_partials', (splits + 1) * rows * H, torch.float32)
     sparse_slot = partials[splits * rows * H:]
     call('rcd_sparse_dgrad', ptr(W_master), H, ptr(tpool.row_ptr), ptr(tpool.raw_items), ptr(corr), row0, rows,
          ptr(sparse_slot), H)
+    return partials, splits
+
+  def _dgrad(self, G, ldn, alpha, Wg, ldh, partials, splits, rows, n, H, Zf32, act, dA, db):
+    """dZ = alpha * (dense part: tcgen05 split-K GEMM over bf16 G) + sparse part (already in partials) -> dA, db."""
+    call('rcd_decoder_dgrad', ptr(G), ldn, ptr(Wg), ldh, rows, n, H, splits, ptr(partials), H, self.gemm)
     call('rcd_dz_act', ptr(partials), splits + 1, splits, ptr(alpha), H, ptr(Zf32), rows, H, act, ptr(dA), ptr(db))
 
   def _wgrad(self, G, ldn, Zs, ldh, Zf32, csc, corr, alpha, rows, n, H, dW, db):
@@ -375,6 +389,42 @@ class TrainEngine:
     csc_ptr, csc_row, _, csc_src = csc
     call('rcd_csc_rows_accumulate', ptr(Zf32), H, ptr(csc_ptr), ptr(csc_row), ptr(csc_src), ptr(corr), n, ptr(dW),
          ptr(db))
+
+  # --- update stream: optimizer / exchange kernels overlap the rest of the backward ------------------------------
+  def _update_stream(self):
+    """Context manager: kernels launched inside run on the side stream, ordered after everything enqueued so far on
+    the main stream (RCD_OVERLAP=0: they stay on the main stream)."""
+    import contextlib
+    if not self.overlap:
+      return contextlib.nullcontext()
+    if self._side is None:
+      self._side = torch.cuda.Stream(device=self.device)
+    ev = torch.cuda.Event()
+    ev.record()
+    self._side.wait_event(ev)
+    return torch.cuda.stream(self._side)
+
+  def _mark_ready(self, tag):
+    ev = torch.cuda.Event()
+    ev.record()          # on the current stream (the side stream inside `_update_stream`)
+    self._ready[tag] = ev
+
+  def _wait_ready(self, tag):
+    ev = self._ready.pop(tag, None)
+    if ev is not None:
+      torch.cuda.current_stream().wait_event(ev)
+
+  def join(self):
+    """Makes the current stream wait for every update still running on the side stream."""
+    for tag in list(self._ready):
+      self._wait_ready(tag)
+
+  def _stash_loss(self, slab, loss_slot):
+    """The step loss (float64) rides in the slab's last two floats as a hi/lo split."""
+    tail = slab[-2:]
+    hi = loss_slot.to(torch.float32)
+    tail[0:1].copy_(hi)
+    tail[1:2].copy_((loss_slot - hi.to(torch.float64)).to(torch.float32))
 
   def _slab(self, numel, capacity):
     """The step's gradient slab: a grow-only private buffer, or (peer-memory exchange) a view of ONE shared
@@ -386,14 +436,6 @@ class TrainEngine:
       torch.cuda.synchronize()
       self._slab_shared = self.p2p.shared(4 * max(numel, capacity))
     return self._slab_shared.view(torch.float32, numel)
-
-  def _p2p_begin(self, slab, loss_slot):
-    """Publishes this rank's slab (loss as hi/lo floats in its last two slots) and waits for all ranks."""
-    tail = slab[-2:]
-    hi = loss_slot.to(torch.float32)
-    tail[0:1].copy_(hi)
-    tail[1:2].copy_((loss_slot - hi.to(torch.float64)).to(torch.float32))
-    self.p2p.barrier(self.bad_flag)
 
   def _p2p_reduce(self, name, offset, count):
     """Sum over ranks of slab[offset : offset+count] into a private buffer (small replicated tensors)."""
@@ -434,11 +476,13 @@ class TrainEngine:
 
     Wg = b.get('Wg', n * ldh, torch.bfloat16)
     bg = b.get('bias_g', n, torch.float32)
+    self._wait_ready('de')   # the previous step's W_d / b_d update (side stream; peers' pushes) has landed
     call('rcd_gather_rows', ptr(Wd), H, ptr(t_items), n, 0, ptr(Wg), ldh, None)
     call('rcd_gather_vec', ptr(bd), ptr(t_items), n, ptr(bg))
 
     Z = b.get('Z', rows * H, torch.float32)
     Zb = b.get('Zb', rows * ldh, torch.bfloat16)
+    self._wait_ready('en')
     call('rcd_ae_encoder_fwd', ptr(We), H, ptr(be), ptr(pool.row_ptr), ptr(pool.raw_items), ptr(pool.vals),
          ptr(pool.row_inv_norm), row0, rows, self.act, ptr(Z), ptr(Zb), ldh)
 
@@ -447,37 +491,56 @@ class TrainEngine:
     if not train:
       return
 
-    dA = b.get('dA', rows * H, torch.float32)
-    self._dgrad(G, ldn, corr, alpha, Wg, ldh, Wd, tpool, row0, rows, n, H, Z, self.act, dA, dbe)
+    # Backward, ordered so that the decoder-side update (HBM- or NVLink-bound) runs on the side stream underneath the
+    # tensor-core dgrad GEMM and the encoder backward: sparse dgrad (reads master W_d) -> dW_d -> [W_d, b_d update]
+    # || dgrad GEMM -> dA -> dW_e -> [W_e, b_e update].
+    partials, splits = self._sparse_dgrad(corr, Wd, tpool, row0, rows, n, H)
     self._wgrad(G, ldn, Zs, ldh, Z, csc_t, corr, alpha, rows, n, H, dWd, dbd)
+    self.last = {'n': n, 'n_in': n_in, 'dWe': dWe.view(n_in, H), 'dWd': dWd.view(n, H), 'dbd': dbd, 'dbe': dbe}
+    sequential = self.tied or (self.pg is not None and self.p2p is None) or (self.late_update and self.pg is None)
+    if not sequential:
+      with self._update_stream():
+        if self.p2p is not None:
+          self.p2p.barrier(self.bad_flag)          # every rank's dW_d / db_d is complete
+          self.opt.step_param_p2p(de_name, self.p2p, self._slab_shared.ptr_table(4 * o_wd), H, tpool.pos)
+          dbd_sum = self._p2p_reduce('tail_de', o_bd, n4)
+          self.opt.step_param(deb_name, dbd_sum[0:n], 1, pos=tpool.pos)
+        else:
+          self.opt.step_param(de_name, dWd, H, pos=tpool.pos, ids=tpool.items_buf, n_ids=n)
+          self.opt.step_param(deb_name, dbd, 1, pos=tpool.pos)
+          self._mark_ready('de')
+
+    dA = b.get('dA', rows * H, torch.float32)
+    self._dgrad(G, ldn, alpha, Wg, ldh, partials, splits, rows, n, H, Z, self.act, dA, dbe)
     csc_ptr, csc_row, csc_val, _ = csc_in
     call('rcd_ae_encoder_wgrad', ptr(dA), H, ptr(csc_ptr), ptr(csc_row), ptr(csc_val), ptr(pool.row_inv_norm), row0,
          n_in, ptr(dWe))
 
-    self.last = {'n': n, 'n_in': n_in, 'dWe': dWe.view(n_in, H), 'dWd': dWd.view(n, H), 'dbd': dbd, 'dbe': dbe}
     if self.p2p is not None:
-      # peer-memory exchange: tables are row-sharded for the update and pushed to every replica by the same kernel;
-      # the small tensors (biases, loss) are summed over ranks and updated redundantly (identical on every rank)
-      self._p2p_begin(slab, loss_slot)
-      tail = self._p2p_reduce('tail', o_bd, slab.numel() - o_bd)
-      loss_slot.copy_(tail[-2:-1].to(torch.float64) + tail[-1:].to(torch.float64))
-      sh = self._slab_shared
-      self.opt.step_param_p2p(en_name, self.p2p, sh.ptr_table(0), H, pool.pos)
-      self.opt.step_param_p2p(de_name, self.p2p, sh.ptr_table(4 * o_wd), H, tpool.pos)
-      self.opt.step_param(enb_name, tail[n4:n4 + H], 1)
-      self.opt.step_param(deb_name, tail[0:n], 1, pos=tpool.pos)
-      self.p2p.barrier(self.bad_flag)   # all pushes have landed; the slabs may be overwritten
+      self._stash_loss(slab, loss_slot)
+      with self._update_stream():
+        self.p2p.barrier(self.bad_flag)            # dW_e / db_e / loss complete everywhere; W_d pushes have landed
+        self._mark_ready('de')
+        self.opt.step_param_p2p(en_name, self.p2p, self._slab_shared.ptr_table(0), H, pool.pos)
+        tail = self._p2p_reduce('tail_en', o_be, h4 + 4)
+        self.opt.step_param(enb_name, tail[0:H], 1)
+        loss_slot.copy_(tail[-2:-1].to(torch.float64) + tail[-1:].to(torch.float64))
+        self.p2p.barrier(self.bad_flag)            # W_e pushes have landed; the slabs may be overwritten
+        self._mark_ready('en')
       return
-    self._reduce_slab(slab, loss_slot)
-
-    if self.tied:  # is_constrained: one table receives both gradients (recoder/nn.py:200)
-      dWe.add_(dWd)
-      self.opt.step_param(en_name, dWe, H, pos=pool.pos, ids=pool.items_buf, n_ids=n_in)
-    else:
-      self.opt.step_param(en_name, dWe, H, pos=pool.pos, ids=pool.items_buf, n_ids=n_in)
-      self.opt.step_param(de_name, dWd, H, pos=tpool.pos, ids=tpool.items_buf, n_ids=n)
+    if sequential:
+      self._reduce_slab(slab, loss_slot)
+      if self.tied:  # is_constrained: one table receives both gradients (recoder/nn.py:200)
+        dWe.add_(dWd)
+        self.opt.step_param(en_name, dWe, H, pos=pool.pos, ids=pool.items_buf, n_ids=n_in)
+      else:
+        self.opt.step_param(en_name, dWe, H, pos=pool.pos, ids=pool.items_buf, n_ids=n_in)
+        self.opt.step_param(de_name, dWd, H, pos=tpool.pos, ids=tpool.items_buf, n_ids=n)
+      self.opt.step_param(enb_name, dbe, 1)
+      self.opt.step_param(deb_name, dbd, 1, pos=tpool.pos)
+      return
+    self.opt.step_param(en_name, dWe, H, pos=pool.pos, ids=pool.items_buf, n_ids=n_in)
     self.opt.step_param(enb_name, dbe, 1)
-    self.opt.step_param(deb_name, dbd, 1, pos=tpool.pos)
 
   # ------------------------------------------------------------------------------------------------------
   def _mf_step(self, pool, tpool, row0, rows, inv_b, loss_slot, train):
@@ -505,22 +568,37 @@ class TrainEngine:
 
     Vg = b.get('Wg', n * ldd, torch.bfloat16)
     bg = b.get('bias_g', n, torch.float32)
+    self._wait_ready('item')
     call('rcd_gather_rows', ptr(V), D, ptr(t_items), n, 0, ptr(Vg), ldd, None)
     call('rcd_gather_vec', ptr(bias), ptr(t_items), n, ptr(bg))
     Ue = b.get('Z', rows * D, torch.float32)
     Ub = b.get('Zb', rows * ldd, torch.bfloat16)
+    self._wait_ready('user')
     call('rcd_gather_rows', ptr(U), D, ptr(users), rows, self.act, ptr(Ub), ldd, ptr(Ue))
 
     G, ldn, corr, alpha, Us = self._decoder_and_loss(Ub, ldd, Ue, Vg, bg, rows, n, D, inv_b, tpool, row0, loss_slot,
                                                      train)
     if not train:
       return
-    self._dgrad(G, ldn, corr, alpha, Vg, ldd, V, tpool, row0, rows, n, D, Ue, self.act, dU, None)
+    # same schedule as the autoencoder: sparse dgrad (reads master V) -> dV -> [V, bias update on the side stream]
+    # || dgrad GEMM -> dU -> [user-table update]
+    partials, splits = self._sparse_dgrad(corr, V, tpool, row0, rows, n, D)
     self._wgrad(G, ldn, Us, ldd, Ue, csc, corr, alpha, rows, n, D, dV, dbias)
-
     self.last = {'n': n, 'dV': dV.view(n, D), 'dbias': dbias, 'dU': dU.view(rows, D)}
-    if self.p2p is None:
-      self._reduce_slab(slab, loss_slot)
+    sequential = self.pg is not None and self.p2p is None
+    if not sequential:
+      with self._update_stream():
+        if self.p2p is not None:
+          self.p2p.barrier(self.bad_flag)
+          self.opt.step_param_p2p(v_name, self.p2p, self._slab_shared.ptr_table(0), D, tpool.pos)
+          dbias_sum = self._p2p_reduce('tail_de', o_b, n4)
+          self.opt.step_param(bias_name, dbias_sum[0:n], 1, pos=tpool.pos)
+        else:
+          self.opt.step_param(v_name, dV, D, pos=tpool.pos, ids=tpool.items_buf, n_ids=n)
+          self.opt.step_param(bias_name, dbias, 1, pos=tpool.pos)
+          self._mark_ready('item')
+
+    self._dgrad(G, ldn, alpha, Vg, ldd, partials, splits, rows, n, D, Ue, self.act, dU, None)
 
     # In DP the pool holds the GLOBAL batch and rank r works on its r-th block of `rows` rows, so the users
     # of all ranks are the pool rows of the whole global slice.
@@ -530,21 +608,25 @@ class TrainEngine:
     if not getattr(self, '_upos_init', False):
       upos.fill_(-1)
       self._upos_init = True
-    call('rcd_scatter_pos', ptr(all_users), all_rows, ptr(upos), 0)
     if self.p2p is not None:
       # user-row gradients are produced by exactly one rank each: block q of dU_all lives in rank q's slab
-      self._p2p_begin(slab, loss_slot)
-      dbias_sum = self._p2p_reduce('tail', o_b, n4)
-      lsum = self._p2p_reduce('tail_loss', slab.numel() - 2, 2)
-      loss_slot.copy_(lsum[0:1].to(torch.float64) + lsum[1:2].to(torch.float64))
-      sh = self._slab_shared
-      self.opt.step_param_p2p(u_name, self.p2p, sh.ptr_table(4 * o_u), D, upos, grad_block_rows=rows)
-      call('rcd_scatter_pos', ptr(all_users), all_rows, ptr(upos), 1)
-      self.opt.step_param_p2p(v_name, self.p2p, sh.ptr_table(0), D, tpool.pos)
-      self.opt.step_param(bias_name, dbias_sum[0:n], 1, pos=tpool.pos)
-      self.p2p.barrier(self.bad_flag)
+      self._stash_loss(slab, loss_slot)
+      with self._update_stream():
+        self.p2p.barrier(self.bad_flag)            # dU / loss complete everywhere; V pushes have landed
+        self._mark_ready('item')
+        call('rcd_scatter_pos', ptr(all_users), all_rows, ptr(upos), 0)
+        self.opt.step_param_p2p(u_name, self.p2p, self._slab_shared.ptr_table(4 * o_u), D, upos, grad_block_rows=rows)
+        call('rcd_scatter_pos', ptr(all_users), all_rows, ptr(upos), 1)
+        lsum = self._p2p_reduce('tail_en', slab.numel() - 2, 2)
+        loss_slot.copy_(lsum[0:1].to(torch.float64) + lsum[1:2].to(torch.float64))
+        self.p2p.barrier(self.bad_flag)            # user-row pushes have landed; the slabs may be overwritten
+        self._mark_ready('user')
       return
+    if sequential:
+      self._reduce_slab(slab, loss_slot)
+    call('rcd_scatter_pos', ptr(all_users), all_rows, ptr(upos), 0)
     self.opt.step_param(u_name, dU_all, D, pos=upos, ids=all_users, n_ids=all_rows)
     call('rcd_scatter_pos', ptr(all_users), all_rows, ptr(upos), 1)
-    self.opt.step_param(v_name, dV, D, pos=tpool.pos, ids=tpool.items_buf, n_ids=n)
-    self.opt.step_param(bias_name, dbias, 1, pos=tpool.pos)
+    if sequential:
+      self.opt.step_param(v_name, dV, D, pos=tpool.pos, ids=tpool.items_buf, n_ids=n)
+      self.opt.step_param(bias_name, dbias, 1, pos=tpool.pos)
