@@ -238,6 +238,10 @@ int rcd_scatter_pos(const int64_t* ids, int n, int32_t* pos, int reset, void* st
  *                            pos[row]/grad_block_rows when grad_block_rows > 0), torch.optim.Adam update of the local
  *                            p/m/v rows (same arithmetic as rcd_adam_step), new p row stored into EVERY rank's table.
  *                            Callers bracket it with rcd_p2p_barrier (all slabs written / all pushes landed).
+ *                            grads_mc / table_mc (optional, NULL = off): NVSwitch MULTICAST addresses of the gradient
+ *                            block / the table (same memory as the per-rank pointers, bound to one multicast object):
+ *                            the sum becomes one `multimem.ld_reduce` (reduced inside the switch) and the replica
+ *                            update one `multimem.st` — link traffic per GPU drops from (world-1) x to 1 x.
  * ------------------------------------------------------------------------------------------------------- */
 #define RCD_MAX_PEERS 16
 #define RCD_P2P_HANDLE_BYTES 64
@@ -253,7 +257,7 @@ int rcd_p2p_reduce(const float* const* src_host, int world, long long offset, lo
 int rcd_adam_step_p2p(float* const* tables_host, float* m, float* v, long long row_begin, long long row_end, int H,
                       const float* const* grads_host, int ldg, const int32_t* pos, int grad_block_rows, int rank,
                       int world, double lr, double beta1, double beta2, double eps, double weight_decay, long long t,
-                      void* stream);
+                      const float* grads_mc, float* table_mc, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Telemetry / tests: L2 norm squared of a strided fp32 matrix (double accumulation), out_sq[0] += ...

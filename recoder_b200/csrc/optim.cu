@@ -101,11 +101,27 @@ static __global__ void __launch_bounds__(256)
 // ncclAllReduce(slab) + a full-table Adam pass on every rank: the optimizer's HBM traffic drops by the world size and
 // no rank ever holds a reduced copy of the slab.  grad_block_rows > 0: gradient row g was produced by exactly one
 // rank, g / grad_block_rows (MF user rows), so only that peer is read.
+// NVLS (NVSwitch multicast) forms: one instruction reduces the same address across every rank's copy inside the
+// switch / stores to every rank's copy — per-GPU link traffic drops from (world-1) x to 1 x per element.
+__device__ __forceinline__ float4 multimem_ld_reduce_add_v4(const float* mc_addr) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(mc_addr)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st_v4(float* mc_addr, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
 template <int VEC>
 static __global__ void __launch_bounds__(256)
     k_adam_p2p(PeerPtrs tables, float* __restrict__ m, float* __restrict__ v, long long row_begin, long long nrows,
                int H, PeerPtrs grads, int ldg, const int32_t* __restrict__ pos, int grad_block_rows, int rank, int world,
-               AdamScalars a) {
+               AdamScalars a, const float* __restrict__ grads_mc, float* __restrict__ table_mc) {
   const int vpr = H / VEC;
   const long long total = nrows * vpr;
   float* __restrict__ p_local = reinterpret_cast<float*>(tables.p[rank]);
@@ -121,6 +137,8 @@ static __global__ void __launch_bounds__(256)
         const size_t goff = (size_t)gr * ldg + h;
         if (grad_block_rows > 0) {
           g = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(grads.p[gr / grad_block_rows]) + goff));
+        } else if (grads_mc) {
+          g = multimem_ld_reduce_add_v4(grads_mc + goff);   // summed across all ranks' slabs inside the switch
         } else {
           for (int q0 = 0; q0 < world; q0 += 4) {  // up to four peer loads in flight, summed in rank order
             float4 t[4];
@@ -145,7 +163,12 @@ static __global__ void __launch_bounds__(256)
       adam_update(pp.w, mm.w, vv.w, g.w, a);
       __stcs(reinterpret_cast<float4*>(m + off), mm);
       __stcs(reinterpret_cast<float4*>(v + off), vv);
-      for (int q = 0; q < world; ++q) __stcg(reinterpret_cast<float4*>(reinterpret_cast<float*>(tables.p[q]) + off), pp);
+      if (table_mc) {
+        multimem_st_v4(table_mc + off, pp);   // one store, replicated to every rank's table by the switch
+      } else {
+        for (int q = 0; q < world; ++q)
+          __stcg(reinterpret_cast<float4*>(reinterpret_cast<float*>(tables.p[q]) + off), pp);
+      }
     } else {
       float g = 0.f;
       if (gr >= 0) {
@@ -253,7 +276,8 @@ RCD_EXPORT int rcd_adam_step(float* p, float* m, float* v, long long rows, int H
 RCD_EXPORT int rcd_adam_step_p2p(float* const* tables_host, float* m, float* v, long long row_begin, long long row_end,
                                  int H, const float* const* grads_host, int ldg, const int32_t* pos, int grad_block_rows,
                                  int rank, int world, double lr, double beta1, double beta2, double eps,
-                                 double weight_decay, long long t, void* stream) {
+                                 double weight_decay, long long t, const float* grads_mc, float* table_mc,
+                                 void* stream) {
   RCD_CHECK_ARG(m && v && H > 0 && t >= 1 && row_begin >= 0 && row_end >= row_begin, "bad arguments");
   RCD_CHECK_ARG(rank >= 0 && rank < world && ldg >= H && grad_block_rows >= 0, "bad arguments");
   PeerPtrs tabs, grads;
@@ -272,13 +296,14 @@ RCD_EXPORT int rcd_adam_step_p2p(float* const* tables_host, float* m, float* v, 
   a.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
   bool vec = (H % 4 == 0) && (ldg % 4 == 0) && aligned16(m) && aligned16(v);
   for (int q = 0; q < world; ++q) vec = vec && aligned16(tabs.p[q]) && aligned16(grads.p[q]);
+  vec = vec && aligned16(grads_mc) && aligned16(table_mc);
   cudaStream_t st = (cudaStream_t)stream;
   if (vec)
     k_adam_p2p<4><<<stream_grid(nrows * (H / 4)), 256, 0, st>>>(tabs, m, v, row_begin, nrows, H, grads, ldg, pos,
-                                                               grad_block_rows, rank, world, a);
-  else
+                                                               grad_block_rows, rank, world, a, grads_mc, table_mc);
+  else  // scalar fallback: unicast only
     k_adam_p2p<1><<<stream_grid(nrows * H), 256, 0, st>>>(tabs, m, v, row_begin, nrows, H, grads, ldg, pos,
-                                                         grad_block_rows, rank, world, a);
+                                                         grad_block_rows, rank, world, a, nullptr, nullptr);
   RCD_LAUNCH_CHECK();
   return RCD_OK;
 }

@@ -137,7 +137,7 @@ class Optimizer:
       call('rcd_sgd_step', ptr(st.p), ptr(st.m), rows, H, ptr(grad), ldg, ptr(pos), float(self.lr), SGD_MOMENTUM,
            float(st.weight_decay))
 
-  def step_param_p2p(self, name, ctx, grads_table, ldg, pos, grad_block_rows=0):
+  def step_param_p2p(self, name, ctx, grads_table, ldg, pos, grad_block_rows=0, grads_mc=None):
     """Fused reduce-scatter -> Adam -> all-gather over peer memory (`rcd_adam_step_p2p`): this rank updates its row
     shard of the table from the sum of all ranks' compact gradients and stores the new rows into every replica.
     m / v are full-size tensors of which only the owned rows are live (`gather_shards` completes them)."""
@@ -149,7 +149,7 @@ class Optimizer:
     lo, hi = ctx.owned_rows(rows)
     call('rcd_adam_step_p2p', st.shared.ptr_table(), ptr(st.m), ptr(st.v), lo, hi, H, grads_table, ldg, ptr(pos),
          int(grad_block_rows), ctx.rank, ctx.world, float(self.lr), ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS,
-         float(st.weight_decay), st.step)
+         float(st.weight_decay), st.step, grads_mc, st.shared.mc())
 
   def gather_shards(self, ctx):
     """Completes the row-sharded Adam state (m, v) of peer-memory tables on every rank (before a checkpoint)."""
@@ -502,7 +502,8 @@ class TrainEngine:
       with self._update_stream():
         if self.p2p is not None:
           self.p2p.barrier(self.bad_flag)          # every rank's dW_d / db_d is complete
-          self.opt.step_param_p2p(de_name, self.p2p, self._slab_shared.ptr_table(4 * o_wd), H, tpool.pos)
+          self.opt.step_param_p2p(de_name, self.p2p, self._slab_shared.ptr_table(4 * o_wd), H, tpool.pos,
+                                  grads_mc=self._slab_shared.mc(4 * o_wd))
           dbd_sum = self._p2p_reduce('tail_de', o_bd, n4)
           self.opt.step_param(deb_name, dbd_sum[0:n], 1, pos=tpool.pos)
         else:
@@ -521,7 +522,8 @@ class TrainEngine:
       with self._update_stream():
         self.p2p.barrier(self.bad_flag)            # dW_e / db_e / loss complete everywhere; W_d pushes have landed
         self._mark_ready('de')
-        self.opt.step_param_p2p(en_name, self.p2p, self._slab_shared.ptr_table(0), H, pool.pos)
+        self.opt.step_param_p2p(en_name, self.p2p, self._slab_shared.ptr_table(0), H, pool.pos,
+                                grads_mc=self._slab_shared.mc(0))
         tail = self._p2p_reduce('tail_en', o_be, h4 + 4)
         self.opt.step_param(enb_name, tail[0:H], 1)
         loss_slot.copy_(tail[-2:-1].to(torch.float64) + tail[-1:].to(torch.float64))
@@ -590,7 +592,8 @@ class TrainEngine:
       with self._update_stream():
         if self.p2p is not None:
           self.p2p.barrier(self.bad_flag)
-          self.opt.step_param_p2p(v_name, self.p2p, self._slab_shared.ptr_table(0), D, tpool.pos)
+          self.opt.step_param_p2p(v_name, self.p2p, self._slab_shared.ptr_table(0), D, tpool.pos,
+                                  grads_mc=self._slab_shared.mc(0))
           dbias_sum = self._p2p_reduce('tail_de', o_b, n4)
           self.opt.step_param(bias_name, dbias_sum[0:n], 1, pos=tpool.pos)
         else:

@@ -26,6 +26,9 @@ def run(kind, loss, mode, pg, batch, steps, matrix, U, I, H, seed_params):
   else:
     model = MatrixFactorization(embedding_size=H, activation_type='none')
   torch.manual_seed(seed_params)
+  if ':' in mode:   # 'p2p:ipc' = CUDA-IPC unicast ld/st, 'p2p:symm' = symmetric memory + NVLS multicast when available
+    mode, backend = mode.split(':')
+    os.environ['RCD_P2P_BACKEND'] = backend
   tr = Recoder(model=model, use_cuda=True, optimizer_type='adam', loss=loss, process_group=pg,
                dp_exchange=mode if mode != 'single' else 'nccl')
   ds = RecommendationDataset(matrix)
@@ -39,6 +42,8 @@ def run(kind, loss, mode, pg, batch, steps, matrix, U, I, H, seed_params):
   state = {n: (s.m.cpu().clone(), s.v.cpu().clone()) for n, s in tr.optimizer.states.items()}
   losses = tr.last_epoch_losses.copy()
   used_p2p = tr._p2p is not None
+  if used_p2p and dist.get_rank() == 0:
+    print('p2p backend %s, multicast %s' % (tr._p2p.backend, bool(tr._p2p.flags.mc_ptr and tr._p2p.multicast)), flush=True)
   return params, state, losses, used_p2p
 
 
@@ -59,10 +64,11 @@ def main():
       ref = run(kind, loss, 'single', solo, B * world, steps, matrix, U, I, H, 3)
     dist.barrier()
     nccl = run(kind, loss, 'nccl', None, B, steps, matrix, U, I, H, 3)
-    p2p = run(kind, loss, 'p2p', None, B, steps, matrix, U, I, H, 3)
-    assert p2p[3], 'peer-memory exchange was not used'
+    p2p = run(kind, loss, 'p2p:ipc', None, B, steps, matrix, U, I, H, 3)
+    p2p_mc = run(kind, loss, 'p2p:auto', None, B, steps, matrix, U, I, H, 3)
+    assert p2p[3] and p2p_mc[3], 'peer-memory exchange was not used'
     assert not nccl[3]
-    for tag, got in (('nccl', nccl), ('p2p', p2p)):
+    for tag, got in (('nccl', nccl), ('p2p-ipc', p2p), ('p2p-auto', p2p_mc)):
       # every rank holds the same replica
       for n, t in got[0].items():
         g = [torch.zeros_like(t, device='cuda') for _ in range(world)]
