@@ -197,12 +197,14 @@ int rcd_decoder_wgrad(const uint16_t* G, int ldg, const uint16_t* Zs, int ldzs, 
  *     rcd_dz_act        : dA = (row_scale[r] * sum_{s<n_scaled} partials[s] + sum_{s>=n_scaled} partials[s]) * act'(Z)
  *                         -> fp32 [rows, H] (row_scale NULL = 1); db_e[h] = sum_r dA[r,h]
  *     rcd_ae_encoder_wgrad : dWe_rows[c,:] = sum_{(r,x) in column c} x * row_inv_norm[row0+r] * dA[r,:]
+ *                         (csc_src + csr_vals, optional: take x from csr_vals[csc_src[e]] — the input values after
+ *                         the input-noise dropout, in the slice's CSR order — instead of csc_val[e])
  * ------------------------------------------------------------------------------------------------------- */
 int rcd_dz_act(const float* partials, int splits, int n_scaled, const float* row_scale, int ldp, const float* Z,
                int rows, int H, int act, float* dA, float* db, void* stream);
 int rcd_ae_encoder_wgrad(const float* dA, int H, const int32_t* csc_ptr, const int32_t* csc_row,
                          const float* csc_val, const float* row_inv_norm, int row0, int n, float* dWe_rows,
-                         void* stream);
+                         const int32_t* csc_src, const float* csr_vals, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K8  optimizers — replace torch.optim.{Adam,SGD,SparseAdam}.step as configured by
@@ -217,6 +219,13 @@ int rcd_adam_step(float* p, float* m, float* v, long long rows, int H, const flo
                   long long t, void* stream);
 int rcd_sgd_step(float* p, float* buf, long long rows, int H, const float* grad_rows, int ldg, const int32_t* pos,
                  double lr, double momentum, double weight_decay, void* stream);
+/* torch.optim.Adagrad(lr) and torch.optim.RMSprop(lr, momentum=0.9) with their defaults (lr_decay 0, eps 1e-10 /
+ * alpha 0.99, eps 1e-8, not centered) — recoder/model.py:140-144, 150-154; dense semantics as above. */
+int rcd_adagrad_step(float* p, float* sum, long long rows, int H, const float* grad_rows, int ldg, const int32_t* pos,
+                     double lr, double eps, double weight_decay, void* stream);
+int rcd_rmsprop_step(float* p, float* square_avg, float* buf, long long rows, int H, const float* grad_rows, int ldg,
+                     const int32_t* pos, double lr, double alpha, double eps, double momentum, double weight_decay,
+                     void* stream);
 /* torch.optim.SparseAdam on the n rows `ids` (no weight decay; recoder/model.py:137-138) */
 int rcd_sparse_adam_step(float* p, float* m, float* v, int H, const float* grad_rows, int ldg, const int64_t* ids,
                          int n, double lr, double beta1, double beta2, double eps, long long t, void* stream);
@@ -258,6 +267,27 @@ int rcd_adam_step_p2p(float* const* tables_host, float* m, float* v, long long r
                       const float* const* grads_host, int ldg, const int32_t* pos, int grad_block_rows, int rank,
                       int world, double lr, double beta1, double beta2, double eps, double weight_decay, long long t,
                       const float* grads_mc, float* table_mc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K10 generalised model pieces: inner dense layers of a multi-layer DynamicAutoencoder
+ *     (recoder/nn.py:189-226, 242-249), input noise / bottleneck / user-embedding dropout (nn.py:236-237, 245-246,
+ *     351-352) and the elementwise nodes of their backward.
+ *     rcd_sgemm   : fp32 C[M,N] = op(A)[M,K] * op(B)[K,N] (+ bias[N]) -> act; trans_a: A stored [K, lda>=M];
+ *                   trans_b: B stored [N, ldb>=K] (an nn.Linear weight [out, in] is B with trans_b = 1);
+ *                   accumulate != 0: C += result (tied weights receive two gradient contributions)
+ *     rcd_dropout : y[i] = keep_i ? x[i]/(1-p) : 0; keep_i from Philox4x32-10(seed, rng_stream) at element index
+ *                   index_base + i, or from keep_mask[i] (uint8, tests).  Apply it to the gradient for the backward.
+ *     rcd_act_grad: dpre = dy * act'(y) with y the activation OUTPUT (in place allowed)
+ *     rcd_colsum  : out[h] = sum_r x[r, h]
+ *     rcd_f32_to_bf16_rows : bf16 copy [rows, ld] (zero padded) of an fp32 [rows, H] matrix
+ * ------------------------------------------------------------------------------------------------------- */
+int rcd_sgemm(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+              int ldc, const float* bias, int act, int accumulate, void* stream);
+int rcd_dropout(const float* x, long long count, float p, unsigned long long seed, unsigned int rng_stream,
+                long long index_base, const uint8_t* keep_mask, float* y, void* stream);
+int rcd_act_grad(const float* dy, const float* y, long long count, int act, float* dpre, void* stream);
+int rcd_colsum(const float* x, int rows, int H, int ld, float* out, void* stream);
+int rcd_f32_to_bf16_rows(const float* x, int rows, int H, uint16_t* out, int ld, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Telemetry / tests: L2 norm squared of a strided fp32 matrix (double accumulation), out_sq[0] += ...

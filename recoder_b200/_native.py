@@ -51,7 +51,7 @@ _SIGNATURES = {
   'rcd_decoder_dgrad': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
   'rcd_decoder_wgrad': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int, _P]),
   'rcd_dz_act': (c_int, [_P, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P]),
-  'rcd_ae_encoder_wgrad': (c_int, [_P, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P]),
+  'rcd_ae_encoder_wgrad': (c_int, [_P, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P]),
   'rcd_adam_step': (c_int, [_P, _P, _P, c_longlong, c_int, _P, c_int, _P, c_double, c_double, c_double, c_double,
                             c_double, c_longlong, _P]),
   'rcd_sgd_step': (c_int, [_P, _P, c_longlong, c_int, _P, c_int, _P, c_double, c_double, c_double, _P]),
@@ -67,6 +67,14 @@ _SIGNATURES = {
   'rcd_p2p_reduce': (c_int, [_P, c_int, c_longlong, c_longlong, _P, _P]),
   'rcd_adam_step_p2p': (c_int, [_P, _P, _P, c_longlong, c_longlong, c_int, _P, c_int, _P, c_int, c_int, c_int,
                                 c_double, c_double, c_double, c_double, c_double, c_longlong, _P, _P, _P]),
+  'rcd_adagrad_step': (c_int, [_P, _P, c_longlong, c_int, _P, c_int, _P, c_double, c_double, c_double, _P]),
+  'rcd_rmsprop_step': (c_int, [_P, _P, _P, c_longlong, c_int, _P, c_int, _P, c_double, c_double, c_double, c_double,
+                               c_double, _P]),
+  'rcd_sgemm': (c_int, [c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, _P]),
+  'rcd_dropout': (c_int, [_P, c_longlong, c_float, ctypes.c_ulonglong, ctypes.c_uint, c_longlong, _P, _P, _P]),
+  'rcd_act_grad': (c_int, [_P, _P, c_longlong, c_int, _P, _P]),
+  'rcd_colsum': (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+  'rcd_f32_to_bf16_rows': (c_int, [_P, c_int, c_int, _P, c_int, _P]),
   'rcd_sumsq': (c_int, [_P, c_longlong, c_int, c_int, _P, _P]),
   'rcd_gemm_bf16': (c_int, [c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
 }

@@ -135,8 +135,8 @@ static __global__ void __launch_bounds__(kEmbThreads)
   for (int k = 0; k < NV; ++k) acc[k].zero();
   seg_accumulate<VEC, NV>(acc, dA, H, t, tpr, s, e, [&](int p, int& idx, float& cf) {
     idx = csc_row[p];
-    if (src) cf = csc_val[src[p]];
-    else cf = row_inv_norm ? csc_val[p] * row_inv_norm[row0 + idx] : csc_val[p];
+    cf = src ? csc_val[src[p]] : csc_val[p];
+    if (row_inv_norm) cf *= row_inv_norm[row0 + idx];
   });
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -327,8 +327,10 @@ RCD_EXPORT int rcd_ae_encoder_fwd(const float* We, int H, const float* be, const
 
 RCD_EXPORT int rcd_ae_encoder_wgrad(const float* dA, int H, const int32_t* csc_ptr, const int32_t* csc_row,
                                     const float* csc_val, const float* row_inv_norm, int row0, int n,
-                                    float* dWe_rows, void* stream) {
+                                    float* dWe_rows, const int32_t* csc_src, const float* csr_vals, void* stream) {
   RCD_CHECK_ARG(dA && csc_ptr && csc_row && csc_val && row_inv_norm && dWe_rows, "null pointer");
+  RCD_CHECK_ARG((csc_src == nullptr) == (csr_vals == nullptr), "csc_src and csr_vals come together");
+  if (csr_vals) csc_val = csr_vals;  // input values in CSR order of the slice (noised), reached through csc_src
   RCD_CHECK_ARG(n > 0 && H > 0 && row0 >= 0, "bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(dA) & 15) == 0);
@@ -337,10 +339,10 @@ RCD_EXPORT int rcd_ae_encoder_wgrad(const float* dA, int H, const int32_t* csc_p
   const int blocks = rcd_div_up(n, kEmbThreads / tpr);
   if (vec)
     RCD_DISPATCH_NV(k_encoder_wgrad, 4, units, tpr, <<<blocks, kEmbThreads, 0, st>>>(
-        dA, H, csc_ptr, csc_row, csc_val, nullptr, row_inv_norm, row0, n, tpr, dWe_rows, 0, nullptr));
+        dA, H, csc_ptr, csc_row, csc_val, csc_src, row_inv_norm, row0, n, tpr, dWe_rows, 0, nullptr));
   else
     RCD_DISPATCH_NV(k_encoder_wgrad, 1, units, tpr, <<<blocks, kEmbThreads, 0, st>>>(
-        dA, H, csc_ptr, csc_row, csc_val, nullptr, row_inv_norm, row0, n, tpr, dWe_rows, 0, nullptr));
+        dA, H, csc_ptr, csc_row, csc_val, csc_src, row_inv_norm, row0, n, tpr, dWe_rows, 0, nullptr));
   RCD_LAUNCH_CHECK();
   return RCD_OK;
 }

@@ -212,6 +212,38 @@ static __global__ void __launch_bounds__(256)
   }
 }
 
+// torch.optim.Adagrad (lr_decay 0, initial accumulator 0, eps 1e-10) and torch.optim.RMSprop (alpha .99, eps 1e-8,
+// momentum .9, not centered) as built at recoder/model.py:140-144, 150-154; dense semantics like k_adam / k_sgd.
+//   KIND 0 Adagrad : sum += g*g; p -= lr * g / (sqrt(sum) + eps)
+//   KIND 1 RMSprop : sq = alpha*sq + (1-alpha)*g*g; buf = momentum*buf + g / (sqrt(sq) + eps); p -= lr * buf
+template <int KIND>
+static __global__ void __launch_bounds__(256)
+    k_opt_accum(float* __restrict__ p, float* __restrict__ s1, float* __restrict__ s2, long long rows, int H,
+                const float* __restrict__ grad_rows, int ldg, const int32_t* __restrict__ pos, float lr, float alpha,
+                float eps, float momentum, float wd) {
+  const long long total = rows * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / H;
+    const int h = (int)(i - r * H);
+    const long long gr = pos ? (long long)pos[r] : r;
+    float pp = p[i];
+    float g = (gr >= 0 && grad_rows) ? grad_rows[(size_t)gr * ldg + h] : 0.f;
+    g = fmaf(wd, pp, g);
+    if (KIND == 0) {
+      const float sum = fmaf(g, g, s1[i]);
+      s1[i] = sum;
+      p[i] = pp - lr * (g / (sqrtf(sum) + eps));
+    } else {
+      const float sq = fmaf(1.0f - alpha, g * g, alpha * s1[i]);
+      s1[i] = sq;
+      const float buf = fmaf(momentum, s2[i], g / (sqrtf(sq) + eps));
+      s2[i] = buf;
+      p[i] = pp - lr * buf;
+    }
+  }
+}
+
 // torch.optim.SparseAdam on the n rows `ids` (sparse_adam functional): no weight decay, eps outside the
 // bias correction: p -= lr*sqrt(bc2)/bc1 * m / (sqrt(v) + eps)
 static __global__ void __launch_bounds__(256)
@@ -320,6 +352,29 @@ RCD_EXPORT int rcd_sgd_step(float* p, float* buf, long long rows, int H, const f
   else
     k_sgd<1><<<stream_grid(rows * H), 256, 0, st>>>(p, buf, rows, H, grad_rows, ldg, pos, (float)lr, (float)momentum,
                                                    (float)weight_decay);
+  RCD_LAUNCH_CHECK();
+  return RCD_OK;
+}
+
+RCD_EXPORT int rcd_adagrad_step(float* p, float* sum, long long rows, int H, const float* grad_rows, int ldg,
+                                const int32_t* pos, double lr, double eps, double weight_decay, void* stream) {
+  RCD_CHECK_ARG(p && sum && rows > 0 && H > 0, "bad arguments");
+  RCD_CHECK_ARG(!grad_rows || ldg >= H, "ldg < H");
+  k_opt_accum<0><<<stream_grid(rows * H), 256, 0, (cudaStream_t)stream>>>(p, sum, nullptr, rows, H, grad_rows, ldg, pos,
+                                                                         (float)lr, 0.f, (float)eps, 0.f,
+                                                                         (float)weight_decay);
+  RCD_LAUNCH_CHECK();
+  return RCD_OK;
+}
+
+RCD_EXPORT int rcd_rmsprop_step(float* p, float* square_avg, float* buf, long long rows, int H, const float* grad_rows,
+                                int ldg, const int32_t* pos, double lr, double alpha, double eps, double momentum,
+                                double weight_decay, void* stream) {
+  RCD_CHECK_ARG(p && square_avg && buf && rows > 0 && H > 0, "bad arguments");
+  RCD_CHECK_ARG(!grad_rows || ldg >= H, "ldg < H");
+  k_opt_accum<1><<<stream_grid(rows * H), 256, 0, (cudaStream_t)stream>>>(p, square_avg, buf, rows, H, grad_rows, ldg,
+                                                                         pos, (float)lr, (float)alpha, (float)eps,
+                                                                         (float)momentum, (float)weight_decay);
   RCD_LAUNCH_CHECK();
   return RCD_OK;
 }

@@ -97,10 +97,7 @@ class Optimizer:
   separate row-sparse Adam for `sparse=True` embedding tables (model.py:110-115,137-138)."""
 
   def __init__(self, named_params, optimizer_type, lr, weight_decay, sparse_names=()):
-    if optimizer_type not in ('adam', 'sgd'):
-      if optimizer_type in ('adagrad', 'rmsprop'):
-        raise NotImplementedError("optimizer '%s' is outside the B200 hot path (adam and sgd are implemented)"
-                                  % optimizer_type)
+    if optimizer_type not in ('adam', 'sgd', 'adagrad', 'rmsprop'):
       raise Exception('Unknown optimizer kind')                       # model.py:156
     self.type = optimizer_type
     self.lr = lr            # dense optimizer lr (MultiStepLR acts on it, model.py:327-332)
@@ -109,15 +106,15 @@ class Optimizer:
     for name, p in named_params:
       wd = 0 if 'bias' in name else weight_decay
       sp = name in sparse_names
-      if sp and optimizer_type != 'adam':
+      if sp and optimizer_type != 'adam':  # sgd / adagrad / rmsprop
         raise ValueError('Sparse gradients optimization not supported with %s' % optimizer_type)  # model.py:142-152
       self.states[name] = ParamState(name, p, wd, sp)
 
   def _ensure(self, st):
     if st.m is None:
-      st.m = torch.zeros_like(st.p)
-      if self.type == 'adam':
-        st.v = torch.zeros_like(st.p)
+      st.m = torch.zeros_like(st.p)     # adam exp_avg | sgd momentum buffer | adagrad sum | rmsprop square_avg
+      if self.type in ('adam', 'rmsprop'):
+        st.v = torch.zeros_like(st.p)   # adam exp_avg_sq | rmsprop momentum buffer
 
   def step_param(self, name, grad, ldg, pos=None, ids=None, n_ids=0):
     """grad: compact rows [*, ldg] (see rcd_adam_step); pos: int32 map row->grad row or None for dense grads;
@@ -133,9 +130,15 @@ class Optimizer:
       else:
         call('rcd_adam_step', ptr(st.p), ptr(st.m), ptr(st.v), rows, H, ptr(grad), ldg, ptr(pos), float(self.lr),
              ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS, float(st.weight_decay), st.step)
-    else:
+    elif self.type == 'sgd':
       call('rcd_sgd_step', ptr(st.p), ptr(st.m), rows, H, ptr(grad), ldg, ptr(pos), float(self.lr), SGD_MOMENTUM,
            float(st.weight_decay))
+    elif self.type == 'adagrad':   # torch.optim.Adagrad defaults (model.py:144): lr_decay 0, eps 1e-10
+      call('rcd_adagrad_step', ptr(st.p), ptr(st.m), rows, H, ptr(grad), ldg, ptr(pos), float(self.lr), 1e-10,
+           float(st.weight_decay))
+    else:                          # torch.optim.RMSprop(momentum=0.9) (model.py:154): alpha 0.99, eps 1e-8
+      call('rcd_rmsprop_step', ptr(st.p), ptr(st.m), ptr(st.v), rows, H, ptr(grad), ldg, ptr(pos), float(self.lr),
+           0.99, 1e-8, SGD_MOMENTUM, float(st.weight_decay))
 
   def step_param_p2p(self, name, ctx, grads_table, ldg, pos, grad_block_rows=0, grads_mc=None):
     """Fused reduce-scatter -> Adam -> all-gather over peer memory (`rcd_adam_step_p2p`): this rank updates its row
@@ -175,11 +178,20 @@ class Optimizer:
         if self.type == 'adam':
           state[i] = {'step': torch.tensor(float(s.step)), 'exp_avg': s.m.detach().cpu().clone(),
                       'exp_avg_sq': s.v.detach().cpu().clone()}
+        elif self.type == 'adagrad':
+          state[i] = {'step': torch.tensor(float(s.step)), 'sum': s.m.detach().cpu().clone()}
+        elif self.type == 'rmsprop':
+          state[i] = {'step': s.step, 'square_avg': s.m.detach().cpu().clone(),
+                      'momentum_buffer': s.v.detach().cpu().clone()}
         else:
           state[i] = {'momentum_buffer': s.m.detach().cpu().clone()}
       g = {'params': [i], 'lr': self.lr if dense else self.sparse_lr, 'weight_decay': s.weight_decay}
       if self.type == 'adam':
         g.update({'betas': ADAM_BETAS, 'eps': ADAM_EPS})
+      elif self.type == 'adagrad':
+        g.update({'lr_decay': 0, 'eps': 1e-10, 'initial_accumulator_value': 0})
+      elif self.type == 'rmsprop':
+        g.update({'momentum': SGD_MOMENTUM, 'alpha': 0.99, 'eps': 1e-8, 'centered': False})
       else:
         g.update({'momentum': SGD_MOMENTUM, 'dampening': 0, 'nesterov': False})
       groups.append(g)
@@ -196,6 +208,13 @@ class Optimizer:
       if self.type == 'adam':
         s.m = entry['exp_avg'].to(dev, torch.float32).clone()
         s.v = entry['exp_avg_sq'].to(dev, torch.float32).clone()
+        s.step = int(float(entry['step']))
+      elif self.type == 'adagrad':
+        s.m = entry['sum'].to(dev, torch.float32).clone()
+        s.step = int(float(entry['step']))
+      elif self.type == 'rmsprop':
+        s.m = entry['square_avg'].to(dev, torch.float32).clone()
+        s.v = entry['momentum_buffer'].to(dev, torch.float32).clone()
         s.step = int(float(entry['step']))
       else:
         s.m = entry['momentum_buffer'].to(dev, torch.float32).clone()
@@ -232,8 +251,16 @@ class TrainEngine:
     self.late_update = os.environ.get('RCD_LATE_UPDATE', '0') == '1'   # experiment: decoder-side update at the end
     self._side = None
     self._ready = {}
-    dev = next(iter(params.values()))[1].device
+    dev = (params['en_w'] if kind == 'ae' else params['item_w'])[1].device
     self.device = dev
+    # generalised model: inner dense layers, input noise, bottleneck / user-embedding dropout
+    self.enc_layers = params.get('enc_layers', [])   # [{'w': (name, [out,in]), 'b': (name, [out])}, ...]
+    self.dec_layers = params.get('dec_layers', [])   # 'w' is None for tied layers (weight = enc layer^T)
+    self.noise_prob = float(params.get('noise_prob', 0.0))
+    self.dropout_prob = float(params.get('dropout_prob', 0.0))
+    self.rng_seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+    self.debug_noise_keep = None     # tests: explicit uint8 keep masks instead of Philox
+    self.debug_dropout_keep = None
     self.buf = _Buffers(dev)
     self.loss_ring = torch.zeros(self.LOSS_RING, dtype=torch.float64, device=dev)
     self.steps_done = 0
@@ -426,6 +453,141 @@ class TrainEngine:
     tail[0:1].copy_(hi)
     tail[1:2].copy_((loss_slot - hi.to(torch.float64)).to(torch.float32))
 
+  # --- generalised model: inner dense layers, dropout --------------------------------------
+  def _inner_layout(self):
+    """Offsets of the inner-layer gradients inside the slab: {'size', 'enc': [(o_w, o_b, out, in)], 'dec': [...]}
+    (a tied decoding layer has no weight gradient of its own: o_w is the encoder layer's)."""
+    lay = getattr(self, '_inner_layout_cache', None)
+    if lay is not None:
+      return lay
+    off = 0
+    enc, dec = [], []
+    for L in self.enc_layers:
+      out_f, in_f = L['w'][1].shape
+      enc.append((off, off + out_f * in_f, out_f, in_f))
+      off += out_f * in_f + _round_up(out_f, 4)
+      off = _round_up(off, 4)
+    k = len(self.enc_layers)
+    for j, L in enumerate(self.dec_layers):
+      if L['w'] is None:
+        e_out, e_in = self.enc_layers[k - 1 - j]['w'][1].shape
+        out_f, in_f = e_in, e_out
+        dec.append((enc[k - 1 - j][0], off, out_f, in_f))
+        off += _round_up(out_f, 4)
+      else:
+        out_f, in_f = L['w'][1].shape
+        dec.append((off, off + out_f * in_f, out_f, in_f))
+        off += out_f * in_f + _round_up(out_f, 4)
+        off = _round_up(off, 4)
+    self._inner_layout_cache = {'size': _round_up(off, 4), 'enc': enc, 'dec': dec}
+    return self._inner_layout_cache
+
+  def _dropout(self, x, y, p, rng_stream, index_base, keep_mask):
+    """y = dropout(x) with the step's Philox key (or an explicit keep mask, tests)."""
+    seed = (self.rng_seed + 0x9E3779B97F4A7C15 * (self.steps_done + 1)) & 0xFFFFFFFFFFFFFFFF
+    call('rcd_dropout', ptr(x), int(x.numel()), float(p), seed, int(rng_stream), int(index_base), ptr(keep_mask),
+         ptr(y))
+
+  def _mid_forward(self, Z0, rows, row0, H, train):
+    """Everything between the embedding encoder and the embedding decoder (nn.py:242-249): inner encoding layers,
+    bottleneck dropout, inner decoding layers (activation after EVERY layer).  Returns (Y [rows, H], saved)."""
+    b = self.buf
+    acts = [Z0.view(rows, H)]
+    for i, L in enumerate(self.enc_layers):
+      W, bias = L['w'][1], L['b'][1]
+      out_f, in_f = W.shape
+      y = b.get('enc_act%d' % i, rows * out_f, torch.float32).view(rows, out_f)
+      call('rcd_sgemm', 0, 1, rows, out_f, in_f, ptr(acts[-1]), in_f, ptr(W), in_f, ptr(y), out_f, ptr(bias), self.act, 0)
+      acts.append(y)
+    top = acts[-1]
+    drop = train and self.dropout_prob > 0.0
+    y0 = top
+    if drop:
+      y0 = b.get('drop_out', top.numel(), torch.float32).view(top.shape)
+      self._dropout(top, y0, self.dropout_prob, 2, row0 * top.shape[1], self.debug_dropout_keep)
+    dec_acts = [y0]
+    k = len(self.enc_layers)
+    for j, L in enumerate(self.dec_layers):
+      bias = L['b'][1]
+      if L['w'] is None:     # tied: weight = enc layer^T, y = x @ W_enc (no transpose of the stored [out,in] needed)
+        We_l = self.enc_layers[k - 1 - j]['w'][1]
+        in_f, out_f = We_l.shape
+        y = b.get('dec_act%d' % j, rows * out_f, torch.float32).view(rows, out_f)
+        call('rcd_sgemm', 0, 0, rows, out_f, in_f, ptr(dec_acts[-1]), in_f, ptr(We_l), out_f, ptr(y), out_f, ptr(bias),
+             self.act, 0)
+      else:
+        W = L['w'][1]
+        out_f, in_f = W.shape
+        y = b.get('dec_act%d' % j, rows * out_f, torch.float32).view(rows, out_f)
+        call('rcd_sgemm', 0, 1, rows, out_f, in_f, ptr(dec_acts[-1]), in_f, ptr(W), in_f, ptr(y), out_f, ptr(bias),
+             self.act, 0)
+      dec_acts.append(y)
+    Y = dec_acts[-1]
+    assert Y.shape[1] == H
+    return Y.reshape(-1), {'acts': acts, 'dec_acts': dec_acts, 'drop': drop}
+
+  def _mid_backward(self, dY, mid, rows, row0, H, dA, inner_grads, lay):
+    """Backward of `_mid_forward`.  dY: gradient w.r.t. the PRE-activation of the last decoding layer when inner
+    decoding layers exist, else w.r.t. the decoder input itself.  Writes dA = gradient w.r.t. the pre-activation of
+    the embedding encoder and the inner-layer weight / bias gradients into `inner_grads`."""
+    b = self.buf
+    acts, dec_acts, drop = mid['acts'], mid['dec_acts'], mid['drop']
+    k = len(self.enc_layers)
+    none = _native.ACT_IDS['none']
+    g = dY.view(rows, -1)[:, :dec_acts[-1].shape[1]]
+    tied_done = set()
+    for j in range(len(self.dec_layers) - 1, -1, -1):      # g = dPre of decoding layer j
+      L = self.dec_layers[j]
+      o_w, o_b, out_f, in_f = lay['dec'][j]
+      x = dec_acts[j]
+      call('rcd_colsum', ptr(g), rows, out_f, out_f, ptr(inner_grads[o_b:]))
+      gx = b.get('dec_gx%d' % j, rows * in_f, torch.float32).view(rows, in_f)
+      if L['w'] is None:
+        We_l = self.enc_layers[k - 1 - j]['w'][1]          # [in_f, out_f] stored; dec weight = We_l^T
+        # d(We_l) (+)= x^T @ g   ([in_f, out_f]); accumulated with the encoder-side contribution below
+        call('rcd_sgemm', 1, 0, in_f, out_f, rows, ptr(x), in_f, ptr(g), out_f, ptr(inner_grads[o_w:]), out_f, None,
+             none, 0)
+        tied_done.add(k - 1 - j)
+        call('rcd_sgemm', 0, 1, rows, in_f, out_f, ptr(g), out_f, ptr(We_l), out_f, ptr(gx), in_f, None, none, 0)
+      else:
+        W = L['w'][1]
+        call('rcd_sgemm', 1, 0, out_f, in_f, rows, ptr(g), out_f, ptr(x), in_f, ptr(inner_grads[o_w:]), in_f, None,
+             none, 0)
+        call('rcd_sgemm', 0, 0, rows, in_f, out_f, ptr(g), out_f, ptr(W), in_f, ptr(gx), in_f, None, none, 0)
+      if j > 0:
+        call('rcd_act_grad', ptr(gx), ptr(dec_acts[j]), int(gx.numel()), self.act, ptr(gx))
+      g = gx
+    # g = gradient w.r.t. dec_acts[0] (the dropped bottleneck)
+    top = acts[-1]
+    if drop:
+      gt = b.get('drop_grad', top.numel(), torch.float32).view(top.shape)
+      self._dropout(g, gt, self.dropout_prob, 2, row0 * top.shape[1], self.debug_dropout_keep)
+      g = gt
+    out = dA.view(rows, H) if k == 0 else b.get('enc_gpre%d' % k, top.numel(), torch.float32).view(top.shape)
+    call('rcd_act_grad', ptr(g), ptr(top), int(top.numel()), self.act, ptr(out))
+    g = out
+    for i in range(k - 1, -1, -1):                         # g = dPre of encoding layer i
+      W = self.enc_layers[i]['w'][1]
+      o_w, o_b, out_f, in_f = lay['enc'][i]
+      x = acts[i]
+      call('rcd_colsum', ptr(g), rows, out_f, out_f, ptr(inner_grads[o_b:]))
+      call('rcd_sgemm', 1, 0, out_f, in_f, rows, ptr(g), out_f, ptr(x), in_f, ptr(inner_grads[o_w:]), in_f, None, none,
+           1 if i in tied_done else 0)
+      gx = dA.view(rows, H) if i == 0 else b.get('enc_gpre%d' % i, rows * in_f, torch.float32).view(rows, in_f)
+      call('rcd_sgemm', 0, 0, rows, in_f, out_f, ptr(g), out_f, ptr(W), in_f, ptr(gx), in_f, None, none, 0)
+      call('rcd_act_grad', ptr(gx), ptr(x), int(gx.numel()), self.act, ptr(gx))
+      g = gx
+
+  def _step_inner(self, inner_grads, lay):
+    """Optimizer steps of the inner dense layers (dense gradients)."""
+    for L, (o_w, o_b, out_f, in_f) in zip(self.enc_layers, lay['enc']):
+      self.opt.step_param(L['w'][0], inner_grads[o_w:o_w + out_f * in_f], in_f)
+      self.opt.step_param(L['b'][0], inner_grads[o_b:o_b + out_f], 1)
+    for L, (o_w, o_b, out_f, in_f) in zip(self.dec_layers, lay['dec']):
+      if L['w'] is not None:
+        self.opt.step_param(L['w'][0], inner_grads[o_w:o_w + out_f * in_f], in_f)
+      self.opt.step_param(L['b'][0], inner_grads[o_b:o_b + out_f], 1)
+
   def _slab(self, numel, capacity):
     """The step's gradient slab: a grow-only private buffer, or (peer-memory exchange) a view of ONE shared
     allocation of `capacity` floats that every rank has mapped."""
@@ -465,14 +627,17 @@ class TrainEngine:
     csc_t = self._slice_csc(tpool, row0, rows, n, 't_') if train else None
     csc_in = csc_t if same else (self._slice_csc(pool, row0, rows, n_in, 'i_') if train else None)
 
-    # gradient slab: [dWe_rows n_in*H | dWd_rows n*H | dbd n (pad 4) | dbe H (pad 4) | pad 2 | loss hi, lo]
+    # gradient slab: [dWe_rows n_in*H | dWd_rows n*H | dbd n (pad 4) | dbe H (pad 4) | inner layers | pad 2 | loss hi, lo]
     n4, h4 = _round_up(n, 4), _round_up(H, 4)
+    inner = self._inner_layout()
     o_wd = n_in * H
     o_bd = o_wd + n * H
     o_be = o_bd + n4
-    slab = self._slab(o_be + h4 + 4, 2 * We.shape[0] * H + _round_up(We.shape[0], 4) + h4 + 4)
+    o_in = o_be + h4
+    slab = self._slab(o_in + inner['size'] + 4, 2 * We.shape[0] * H + _round_up(We.shape[0], 4) + h4 + inner['size'] + 4)
     dWe, dWd = slab[0:o_wd], slab[o_wd:o_bd]
     dbd, dbe = slab[o_bd:o_bd + n], slab[o_be:o_be + H]
+    inner_grads = slab[o_in:o_in + inner['size']]
 
     Wg = b.get('Wg', n * ldh, torch.bfloat16)
     bg = b.get('bias_g', n, torch.float32)
@@ -480,13 +645,28 @@ class TrainEngine:
     call('rcd_gather_rows', ptr(Wd), H, ptr(t_items), n, 0, ptr(Wg), ldh, None)
     call('rcd_gather_vec', ptr(bd), ptr(t_items), n, ptr(bg))
 
+    general = bool(self.enc_layers) or (train and self.dropout_prob > 0.0)
+    base = int(pool.row_ptr_host[row0])
+    nnz_in = int(pool.row_ptr_host[row0 + rows]) - base
+    in_vals = pool.vals
+    if train and self.noise_prob > 0.0 and nnz_in > 0:
+      # input noise (nn.py:236-237): dropout on the normalised input == dropout on the stored non-zeros
+      in_vals = b.get('noised_vals', pool.vals.numel(), torch.float32)
+      self._dropout(pool.vals[base:base + nnz_in], in_vals[base:base + nnz_in], self.noise_prob, 1,
+                    base, self.debug_noise_keep)
+
     Z = b.get('Z', rows * H, torch.float32)
     Zb = b.get('Zb', rows * ldh, torch.bfloat16)
     self._wait_ready('en')
-    call('rcd_ae_encoder_fwd', ptr(We), H, ptr(be), ptr(pool.row_ptr), ptr(pool.raw_items), ptr(pool.vals),
-         ptr(pool.row_inv_norm), row0, rows, self.act, ptr(Z), ptr(Zb), ldh)
+    call('rcd_ae_encoder_fwd', ptr(We), H, ptr(be), ptr(pool.row_ptr), ptr(pool.raw_items), ptr(in_vals),
+         ptr(pool.row_inv_norm), row0, rows, self.act, ptr(Z), None if general else ptr(Zb), ldh)
+    mid = None
+    Y = Z
+    if general:
+      Y, mid = self._mid_forward(Z, rows, row0, H, train)
+      call('rcd_f32_to_bf16_rows', ptr(Y), rows, H, ptr(Zb), ldh)
 
-    G, ldn, corr, alpha, Zs = self._decoder_and_loss(Zb, ldh, Z, Wg, bg, rows, n, H, inv_b, tpool, row0, loss_slot,
+    G, ldn, corr, alpha, Zs = self._decoder_and_loss(Zb, ldh, Y, Wg, bg, rows, n, H, inv_b, tpool, row0, loss_slot,
                                                      train)
     if not train:
       return
@@ -495,8 +675,9 @@ class TrainEngine:
     # tensor-core dgrad GEMM and the encoder backward: sparse dgrad (reads master W_d) -> dW_d -> [W_d, b_d update]
     # || dgrad GEMM -> dA -> dW_e -> [W_e, b_e update].
     partials, splits = self._sparse_dgrad(corr, Wd, tpool, row0, rows, n, H)
-    self._wgrad(G, ldn, Zs, ldh, Z, csc_t, corr, alpha, rows, n, H, dWd, dbd)
-    self.last = {'n': n, 'n_in': n_in, 'dWe': dWe.view(n_in, H), 'dWd': dWd.view(n, H), 'dbd': dbd, 'dbe': dbe}
+    self._wgrad(G, ldn, Zs, ldh, Y, csc_t, corr, alpha, rows, n, H, dWd, dbd)
+    self.last = {'n': n, 'n_in': n_in, 'dWe': dWe.view(n_in, H), 'dWd': dWd.view(n, H), 'dbd': dbd, 'dbe': dbe,
+                 'inner': inner_grads, 'inner_layout': inner}
     sequential = self.tied or (self.pg is not None and self.p2p is None) or (self.late_update and self.pg is None)
     if not sequential:
       with self._update_stream():
@@ -512,10 +693,22 @@ class TrainEngine:
           self._mark_ready('de')
 
     dA = b.get('dA', rows * H, torch.float32)
-    self._dgrad(G, ldn, alpha, Wg, ldh, partials, splits, rows, n, H, Z, self.act, dA, dbe)
-    csc_ptr, csc_row, csc_val, _ = csc_in
-    call('rcd_ae_encoder_wgrad', ptr(dA), H, ptr(csc_ptr), ptr(csc_row), ptr(csc_val), ptr(pool.row_inv_norm), row0,
-         n_in, ptr(dWe))
+    if not general:
+      self._dgrad(G, ldn, alpha, Wg, ldh, partials, splits, rows, n, H, Z, self.act, dA, dbe)
+    else:
+      # gradient w.r.t. the decoder input Y: through its activation when Y is an inner decoding layer's output
+      dY = b.get('dY', rows * H, torch.float32)
+      self._dgrad(G, ldn, alpha, Wg, ldh, partials, splits, rows, n, H, Y,
+                  self.act if self.dec_layers else _native.ACT_IDS['none'], dY, None)
+      self._mid_backward(dY, mid, rows, row0, H, dA, inner_grads, inner)
+      call('rcd_colsum', ptr(dA), rows, H, H, ptr(dbe))
+    csc_ptr, csc_row, csc_val, csc_src = csc_in
+    if in_vals is pool.vals:
+      call('rcd_ae_encoder_wgrad', ptr(dA), H, ptr(csc_ptr), ptr(csc_row), ptr(csc_val), ptr(pool.row_inv_norm), row0,
+           n_in, ptr(dWe), None, None)
+    else:
+      call('rcd_ae_encoder_wgrad', ptr(dA), H, ptr(csc_ptr), ptr(csc_row), ptr(csc_val), ptr(pool.row_inv_norm), row0,
+           n_in, ptr(dWe), ptr(csc_src), ptr(in_vals[base:]))
 
     if self.p2p is not None:
       self._stash_loss(slab, loss_slot)
@@ -524,8 +717,9 @@ class TrainEngine:
         self._mark_ready('de')
         self.opt.step_param_p2p(en_name, self.p2p, self._slab_shared.ptr_table(0), H, pool.pos,
                                 grads_mc=self._slab_shared.mc(0))
-        tail = self._p2p_reduce('tail_en', o_be, h4 + 4)
+        tail = self._p2p_reduce('tail_en', o_be, h4 + inner['size'] + 4)
         self.opt.step_param(enb_name, tail[0:H], 1)
+        self._step_inner(tail[h4:h4 + inner['size']], inner)
         loss_slot.copy_(tail[-2:-1].to(torch.float64) + tail[-1:].to(torch.float64))
         self.p2p.barrier(self.bad_flag)            # W_e pushes have landed; the slabs may be overwritten
         self._mark_ready('en')
@@ -540,9 +734,11 @@ class TrainEngine:
         self.opt.step_param(de_name, dWd, H, pos=tpool.pos, ids=tpool.items_buf, n_ids=n)
       self.opt.step_param(enb_name, dbe, 1)
       self.opt.step_param(deb_name, dbd, 1, pos=tpool.pos)
+      self._step_inner(inner_grads, inner)
       return
     self.opt.step_param(en_name, dWe, H, pos=pool.pos, ids=pool.items_buf, n_ids=n_in)
     self.opt.step_param(enb_name, dbe, 1)
+    self._step_inner(inner_grads, inner)
 
   # ------------------------------------------------------------------------------------------------------
   def _mf_step(self, pool, tpool, row0, rows, inv_b, loss_slot, train):
@@ -577,15 +773,21 @@ class TrainEngine:
     Ub = b.get('Zb', rows * ldd, torch.bfloat16)
     self._wait_ready('user')
     call('rcd_gather_rows', ptr(U), D, ptr(users), rows, self.act, ptr(Ub), ldd, ptr(Ue))
+    drop = train and self.dropout_prob > 0.0
+    Y = Ue
+    if drop:   # dropout on the (activated) user embedding, nn.py:351-352
+      Y = b.get('drop_out', rows * D, torch.float32)
+      self._dropout(Ue, Y, self.dropout_prob, 2, row0 * D, self.debug_dropout_keep)
+      call('rcd_f32_to_bf16_rows', ptr(Y), rows, D, ptr(Ub), ldd)
 
-    G, ldn, corr, alpha, Us = self._decoder_and_loss(Ub, ldd, Ue, Vg, bg, rows, n, D, inv_b, tpool, row0, loss_slot,
+    G, ldn, corr, alpha, Us = self._decoder_and_loss(Ub, ldd, Y, Vg, bg, rows, n, D, inv_b, tpool, row0, loss_slot,
                                                      train)
     if not train:
       return
     # same schedule as the autoencoder: sparse dgrad (reads master V) -> dV -> [V, bias update on the side stream]
     # || dgrad GEMM -> dU -> [user-table update]
     partials, splits = self._sparse_dgrad(corr, V, tpool, row0, rows, n, D)
-    self._wgrad(G, ldn, Us, ldd, Ue, csc, corr, alpha, rows, n, D, dV, dbias)
+    self._wgrad(G, ldn, Us, ldd, Y, csc, corr, alpha, rows, n, D, dV, dbias)
     self.last = {'n': n, 'dV': dV.view(n, D), 'dbias': dbias, 'dU': dU.view(rows, D)}
     sequential = self.pg is not None and self.p2p is None
     if not sequential:
@@ -601,7 +803,13 @@ class TrainEngine:
           self.opt.step_param(bias_name, dbias, 1, pos=tpool.pos)
           self._mark_ready('item')
 
-    self._dgrad(G, ldn, alpha, Vg, ldd, partials, splits, rows, n, D, Ue, self.act, dU, None)
+    if not drop:
+      self._dgrad(G, ldn, alpha, Vg, ldd, partials, splits, rows, n, D, Ue, self.act, dU, None)
+    else:
+      dY = b.get('dY', rows * D, torch.float32)
+      self._dgrad(G, ldn, alpha, Vg, ldd, partials, splits, rows, n, D, Y, _native.ACT_IDS['none'], dY, None)
+      self._dropout(dY, dY, self.dropout_prob, 2, row0 * D, self.debug_dropout_keep)
+      call('rcd_act_grad', ptr(dY), ptr(Ue), rows * D, self.act, ptr(dU))
 
     # In DP the pool holds the GLOBAL batch and rank r works on its r-th block of `rows` rows, so the users
     # of all ranks are the pool rows of the whole global slice.

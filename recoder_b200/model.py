@@ -47,8 +47,7 @@ class Recoder(object):
       be computed from the first training dataset passed to ``train()``.
     num_users (int, optional): the number of users to represent. If not provided, it will
       be computed from the first training dataset passed to ``train()``.
-    optimizer_type (str, optional): optimizer type (one of 'sgd', 'adam'; 'adagrad' and 'rmsprop' raise
-      NotImplementedError — they are outside the accelerated path).
+    optimizer_type (str, optional): optimizer type (one of 'sgd', 'adam', 'adagrad', 'rmsprop').
     loss (str or torch.nn.Module, optional): `mse` for ``MSELoss``, `logistic` for ``BCEWithLogitsLoss``,
       `logloss` for ``MultinomialNLLLoss``, or an instance of one of those modules.
     loss_params (dict, optional): loss function extra params based on loss module if ``loss`` is a ``str``.

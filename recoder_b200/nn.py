@@ -214,18 +214,19 @@ class DynamicAutoencoder(FactorizationModel):
     return self.__de_linear_embedding_layer.bias
 
   def _engine_spec(self):
-    if len(self.hidden_layers) != 1:
-      raise NotImplementedError('multi-layer autoencoders (hidden_layers=%s) are not on the B200 hot path yet; '
-                                'use a single hidden layer' % (self.hidden_layers,))
-    if self.noise_prob > 0.0 or self.dropout_prob > 0.0:
-      raise NotImplementedError('input noise / bottleneck dropout are not on the B200 hot path yet '
-                                '(noise_prob=%s, dropout_prob=%s)' % (self.noise_prob, self.dropout_prob))
     sd_names = {id(p): n for n, p in self.named_parameters()}
+    named = lambda p: (sd_names[id(p)], p.data)  # noqa: E731
     roles = {
-      'en_w': (sd_names[id(self.en_embedding_layer.weight)], self.en_embedding_layer.weight.data),
-      'en_b': (sd_names[id(self.en_bias)], self.en_bias.data),
-      'de_w': (sd_names[id(self.de_embedding_layer.weight)], self.de_embedding_layer.weight.data),
-      'de_b': (sd_names[id(self.de_bias)], self.de_bias.data),
+      'en_w': named(self.en_embedding_layer.weight),
+      'en_b': named(self.en_bias),
+      'de_w': named(self.de_embedding_layer.weight),
+      'de_b': named(self.de_bias),
+      # inner dense layers (nn.py:189-226): a tied decoding layer has no weight of its own ('w': None)
+      'enc_layers': [{'w': named(l.weight), 'b': named(l.bias)} for l in self.encoding_layers],
+      'dec_layers': [{'w': None if self.is_constrained else named(l.weight), 'b': named(l.bias)}
+                     for l in self.decoding_layers],
+      'noise_prob': float(self.noise_prob),
+      'dropout_prob': float(self.dropout_prob),
     }
     return 'ae', roles, self.activation_type, self.is_constrained
 
@@ -238,8 +239,6 @@ class DynamicAutoencoder(FactorizationModel):
   def forward(self, input, input_users=None, input_items=None, target_users=None, target_items=None):
     """Inference forward on a dense ``[B, n]`` CUDA input (reference nn.py:228-253), fp32 logits out.
     Noise / dropout layers are identities outside training, as in the reference's eval mode."""
-    if len(self.hidden_layers) != 1:
-      raise NotImplementedError('multi-layer autoencoders are not on the B200 hot path yet')
     dev = input.device
     B, n_in = input.shape
     We, Wd = self.en_embedding_layer.weight.data, self.de_embedding_layer.weight.data
@@ -255,6 +254,29 @@ class DynamicAutoencoder(FactorizationModel):
     act = _native.ACT_IDS[self.activation_type]
     call('rcd_ae_encoder_fwd', ptr(We), H, ptr(self.en_bias.data), ptr(row_ptr), ptr(raw), ptr(vals), ptr(rin), 0, B,
          act, ptr(Z), ptr(Zb), ldh)
+    if len(self.encoding_layers):
+      # inner encoding / decoding layers, activation after every one (nn.py:242-249); dropout is off in eval mode
+      z = Z
+      enc = list(self.encoding_layers)
+      for layer in enc:
+        W = layer.weight.data
+        y = torch.empty(B, W.shape[0], dtype=torch.float32, device=dev)
+        call('rcd_sgemm', 0, 1, B, W.shape[0], W.shape[1], ptr(z), W.shape[1], ptr(W), W.shape[1], ptr(y), W.shape[0],
+             ptr(layer.bias.data), act, 0)
+        z = y
+      for j, layer in enumerate(self.decoding_layers):
+        if self.is_constrained:   # weight = encoding layer^T (nn.py:224-226): y = z @ W_enc
+          W = enc[len(enc) - 1 - j].weight.data
+          y = torch.empty(B, W.shape[1], dtype=torch.float32, device=dev)
+          call('rcd_sgemm', 0, 0, B, W.shape[1], W.shape[0], ptr(z), W.shape[0], ptr(W), W.shape[1], ptr(y), W.shape[1],
+               ptr(layer.bias.data), act, 0)
+        else:
+          W = layer.weight.data
+          y = torch.empty(B, W.shape[0], dtype=torch.float32, device=dev)
+          call('rcd_sgemm', 0, 1, B, W.shape[0], W.shape[1], ptr(z), W.shape[1], ptr(W), W.shape[1], ptr(y), W.shape[0],
+               ptr(layer.bias.data), act, 0)
+        z = y
+      call('rcd_f32_to_bf16_rows', ptr(z), B, H, ptr(Zb), ldh)
     return _decode_all(Zb, ldh, Wd, self.de_bias.data, target_items, B, H)
 
 
@@ -324,12 +346,11 @@ class MatrixFactorization(FactorizationModel):
     self.dropout_prob = model_params['dropout_prob']
 
   def _engine_spec(self):
-    if self.dropout_prob > 0:
-      raise NotImplementedError('user-embedding dropout is not on the B200 hot path yet')
     roles = {
       'bias': ('bias', self.bias.data),
       'user_w': ('user_embedding_layer.weight', self.user_embedding_layer.weight.data),
       'item_w': ('item_embedding_layer.weight', self.item_embedding_layer.weight.data),
+      'dropout_prob': float(self.dropout_prob),
     }
     return 'mf', roles, self.activation_type, False
 

@@ -8,7 +8,11 @@ For every case it drives the reference's own objects — `RecommendationDataset.
 (recoder/data.py:50-61), `BatchCollator.collate` (data.py:203-251), `Recoder.__init_training`
 (model.py:226-254), `Recoder.__compute_loss` (model.py:454-485), `loss.backward()` and the optimizer steps
 (model.py:397-402) — on an explicit user order, and records the collate outputs, loss, dense gradients and
-post-step parameters of each step.  Dropout/noise are off (RNG streams cannot be matched).
+post-step parameters of each step.  Dropout/noise RNG streams cannot be matched across implementations
+(SURVEY.md §7.1): for the cases that use them the keep masks the reference drew are recorded per step
+(`noise_keep` at the stored non-zeros, `dropout_keep` [B, width]) and injected into the implementation under test.
+
+    python tests/golden/make_golden.py [case names...]     (no names: regenerate everything)
 """
 import json
 import os
@@ -48,6 +52,21 @@ CASES = [
        act='none', wd=1e-2, neg=True, batch=24, pool=24, ratings=False),
   dict(name='mf_nll_sgd', model='mf', loss='logloss', loss_params={}, opt='sgd', sparse=False, hidden=16,
        act='tanh', wd=0.0, neg=True, batch=24, pool=24, ratings=False),
+  # remaining optimizers, tied / deeper autoencoders, input noise and dropout (keep masks recorded)
+  dict(name='ae_mse_adagrad', model='ae', loss='mse', loss_params={}, opt='adagrad', sparse=False, hidden=[16],
+       act='tanh', wd=1e-3, neg=True, batch=24, pool=24, ratings=False),
+  dict(name='ae_nll_rmsprop', model='ae', loss='logloss', loss_params={}, opt='rmsprop', sparse=False, hidden=[16],
+       act='tanh', wd=1e-4, neg=True, batch=24, pool=24, ratings=False),
+  dict(name='ae_nll_deep_tied', model='ae', loss='logloss', loss_params={}, opt='adam', sparse=False, hidden=[16, 8],
+       act='tanh', wd=1e-4, neg=True, batch=24, pool=24, ratings=False, constrained=True),
+  dict(name='ae_bce_deep3', model='ae', loss='logistic', loss_params={}, opt='adam', sparse=False, hidden=[16, 12, 8],
+       act='sigmoid', wd=0.0, neg=True, batch=24, pool=24, ratings=False),
+  dict(name='ae_nll_noise_dropout', model='ae', loss='logloss', loss_params={}, opt='adam', sparse=False, hidden=[16],
+       act='tanh', wd=2e-5, neg=True, batch=24, pool=24, ratings=False, noise=0.5, dropout=0.25),
+  dict(name='ae_mse_deep_dropout', model='ae', loss='mse', loss_params={}, opt='adam', sparse=False, hidden=[16, 8],
+       act='tanh', wd=0.0, neg=True, batch=24, pool=24, ratings=True, noise=0.3, dropout=0.5),
+  dict(name='mf_mse_dropout', model='mf', loss='mse', loss_params={}, opt='adam', sparse=False, hidden=16,
+       act='tanh', wd=0.0, neg=True, batch=24, pool=24, ratings=False, dropout=0.4),
 ]
 
 NUM_USERS, NUM_ITEMS, NNZ = 80, 101, 9
@@ -72,10 +91,15 @@ def run_case(case, rdata, rnn, rmodel):
   torch.manual_seed(1234)
   csr = make_matrix(7, case['ratings'])
   dataset = rdata.RecommendationDataset(csr)
+  noise, dropout = float(case.get('noise', 0.0)), float(case.get('dropout', 0.0))
   if case['model'] == 'ae':
-    model = rnn.DynamicAutoencoder(hidden_layers=case['hidden'], activation_type=case['act'], sparse=case['sparse'])
+    model = rnn.DynamicAutoencoder(hidden_layers=case['hidden'], activation_type=case['act'], sparse=case['sparse'],
+                                   is_constrained=bool(case.get('constrained', False)), noise_prob=noise,
+                                   dropout_prob=dropout)
   else:
-    model = rnn.MatrixFactorization(embedding_size=case['hidden'], activation_type=case['act'], sparse=case['sparse'])
+    model = rnn.MatrixFactorization(embedding_size=case['hidden'], activation_type=case['act'], sparse=case['sparse'],
+                                    dropout_prob=dropout)
+  model.train()
   trainer = rmodel.Recoder(model=model, use_cuda=False, optimizer_type=case['opt'], loss=case['loss'],
                            loss_params=case['loss_params'])
   trainer._Recoder__init_training(train_dataset=dataset, lr=LR, weight_decay=case['wd'])
@@ -104,9 +128,24 @@ def run_case(case, rdata, rnn, rmodel):
         trainer.optimizer.zero_grad()
       if trainer.sparse_optimizer is not None:
         trainer.sparse_optimizer.zero_grad()
+      pre = 'step%d/' % step
+      if noise > 0 or dropout > 0:
+        # nn.Dropout draws from the global CPU generator: replay the draws the forward is about to make (same shapes,
+        # same order: input noise on the dense [B, n] input, then the bottleneck / user-embedding dropout) to record
+        # the keep masks, then rewind the generator so the reference's forward sees exactly those draws.
+        torch.manual_seed(1000 + step)
+        B_, n_ = int(b.size[0]), int(b.size[1])
+        if noise > 0:
+          keep = torch.nn.functional.dropout(torch.ones(B_, n_), noise, True) != 0
+          idx = b.indices.numpy()
+          out[pre + 'noise_keep'] = keep.numpy()[idx[0], idx[1]].astype(np.uint8)
+        if dropout > 0:
+          width = case['hidden'][-1] if case['model'] == 'ae' else case['hidden']
+          keep = torch.nn.functional.dropout(torch.ones(B_, width), dropout, True) != 0
+          out[pre + 'dropout_keep'] = keep.numpy().astype(np.uint8)
+        torch.manual_seed(1000 + step)
       loss = trainer._Recoder__compute_loss(b, None)
       loss.backward()
-      pre = 'step%d/' % step
       out[pre + 'users'] = b.users.numpy().astype(np.int64)
       out[pre + 'items'] = (b.items.numpy().astype(np.int64) if b.items is not None else np.zeros(0, dtype=np.int64))
       out[pre + 'has_items'] = np.array(b.items is not None)
@@ -133,7 +172,10 @@ def main():
   rdata, rnn, rlosses, rmodel = ref_shims.import_reference()
   import warnings
   warnings.simplefilter('ignore')
+  only = set(sys.argv[1:])
   for case in CASES:
+    if only and case['name'] not in only:
+      continue
     out = run_case(case, rdata, rnn, rmodel)
     path = os.path.join(HERE, case['name'] + '.npz')
     np.savez_compressed(path, **out)

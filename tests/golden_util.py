@@ -32,6 +32,8 @@ class Golden:
     return dict(users=z[pre + 'users'], items=(z[pre + 'items'] if bool(z[pre + 'has_items']) else None),
                 indices=z[pre + 'indices'], values=z[pre + 'values'], size=tuple(int(v) for v in z[pre + 'size']),
                 loss=float(z[pre + 'loss']),
+                noise_keep=(z[pre + 'noise_keep'] if (pre + 'noise_keep') in z.files else None),
+                dropout_keep=(z[pre + 'dropout_keep'] if (pre + 'dropout_keep') in z.files else None),
                 grads={n: z[pre + 'grad/' + n] for n in self.param_names},
                 params={n: z[pre + 'param/' + n] for n in self.param_names})
 

@@ -10,13 +10,15 @@ from recoder_b200.nn import DynamicAutoencoder, MatrixFactorization
 from recoder_b200.synth import to_scipy
 
 
-def make_model(kind, num_items, num_users, hidden, act, params, sparse=False):
+def make_model(kind, num_items, num_users, hidden, act, params, sparse=False, constrained=False, noise=0.0,
+               dropout=0.0):
   """Builds a recoder_b200 model on cuda:0 and loads `params` (reference state_dict names -> numpy/tensor)."""
   if kind == 'ae':
     model = DynamicAutoencoder(hidden_layers=hidden if isinstance(hidden, list) else [hidden],
-                               activation_type=act, sparse=sparse)
+                               activation_type=act, sparse=sparse, is_constrained=constrained, noise_prob=noise,
+                               dropout_prob=dropout)
   else:
-    model = MatrixFactorization(embedding_size=hidden, activation_type=act, sparse=sparse)
+    model = MatrixFactorization(embedding_size=hidden, activation_type=act, sparse=sparse, dropout_prob=dropout)
   model.init_model(num_items=num_items, num_users=num_users)
   model = model.to('cuda')
   named = dict(model.named_parameters())
@@ -31,6 +33,23 @@ def make_engine(model, loss, confidence, opt_type, lr, wd, gemm_engine):
   named = [(n, p.data) for n, p in model.named_parameters()]
   opt = Optimizer(named, opt_type, lr, wd, sparse_names=model._sparse_param_names())
   return TrainEngine(kind, roles, loss, confidence, act, opt, gemm_engine=gemm_engine, tied=tied)
+
+
+def inner_grads(eng, model):
+  """{parameter name: gradient} of the inner dense layers of the last step (views into the gradient slab)."""
+  lay = eng.last.get('inner_layout')
+  if not lay or not lay['size']:
+    return {}
+  flat = eng.last['inner']
+  out = {}
+  for L, (o_w, o_b, out_f, in_f) in zip(eng.enc_layers, lay['enc']):
+    out[L['w'][0]] = flat[o_w:o_w + out_f * in_f].view(out_f, in_f)
+    out[L['b'][0]] = flat[o_b:o_b + out_f]
+  for L, (o_w, o_b, out_f, in_f) in zip(eng.dec_layers, lay['dec']):
+    if L['w'] is not None:
+      out[L['w'][0]] = flat[o_w:o_w + out_f * in_f].view(out_f, in_f)
+    out[L['b'][0]] = flat[o_b:o_b + out_f]
+  return out
 
 
 def device_dataset(indptr, indices, data, num_items):

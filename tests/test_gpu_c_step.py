@@ -11,13 +11,17 @@ from recoder_b200 import _native
 from recoder_b200.data import collate_pool
 from recoder_b200.synth import synthetic_csr
 from tests.golden_util import Golden
-from tests.gpu_util import compact_oracle_grads, device_dataset, make_engine, make_model, rel_err
+from tests.gpu_util import compact_oracle_grads, device_dataset, inner_grads, make_engine, make_model, rel_err
 
 pytestmark = pytest.mark.gpu
 
 ENGINES = [pytest.param(_native.GEMM_SIMT, id='simt'), pytest.param(_native.GEMM_TCGEN05, id='tcgen05')]
 GOLDEN_CASES = ['ae_mse_adam', 'ae_mse_conf_ratings', 'ae_nll_adam', 'ae_bce_adam', 'ae_mse_sgd',
-                'ae_nll_sparseadam', 'ae_mse_noneg', 'ae_nll_pool', 'mf_mse_adam', 'mf_nll_sgd']
+                'ae_nll_sparseadam', 'ae_mse_noneg', 'ae_nll_pool', 'mf_mse_adam', 'mf_nll_sgd',
+                # Adagrad / RMSprop, multi-layer and tied autoencoders, input noise and dropout
+                # (the keep masks the reference drew are injected)
+                'ae_mse_deep', 'ae_mse_adagrad', 'ae_nll_rmsprop', 'ae_nll_deep_tied', 'ae_bce_deep3',
+                'ae_nll_noise_dropout', 'ae_mse_deep_dropout', 'mf_mse_dropout']
 
 # bf16 operands (2^-9 relative rounding, zero mean) against an fp32 reference
 TOL_LOSS = 1e-3
@@ -36,7 +40,9 @@ def test_step_matches_reference_golden(name, engine):
   g = Golden(name)
   m = g.meta
   kind = m['model']
-  model = make_model(kind, m['num_items'], m['num_users'], m['hidden'], m['act'], g.init_params(), sparse=m['sparse'])
+  tied = bool(m.get('constrained', False))
+  model = make_model(kind, m['num_items'], m['num_users'], m['hidden'], m['act'], g.init_params(), sparse=m['sparse'],
+                     constrained=tied, noise=float(m.get('noise', 0.0)), dropout=float(m.get('dropout', 0.0)))
   eng = make_engine(model, m['loss'], m['loss_params'].get('confidence', 0.0), m['opt'], m['lr'], m['wd'], engine)
   ds = device_dataset(g.indptr, g.indices, g.data, m['num_items'])
   csr = ds.device_csr()
@@ -54,14 +60,22 @@ def test_step_matches_reference_golden(name, engine):
             named[n2].copy_(torch.from_numpy(v2).to('cuda'))
       row0 = k * m['batch']
       rows = ref['size'][0]
+      eng.debug_noise_keep = None if ref['noise_keep'] is None else torch.from_numpy(ref['noise_keep']).cuda()
+      eng.debug_dropout_keep = None if ref['dropout_keep'] is None else \
+        torch.from_numpy(np.ascontiguousarray(ref['dropout_keep'])).cuda()
       eng.train_step(pool, row0, rows)
       loss = float(eng.losses(1)[0])
       assert loss == pytest.approx(ref['loss'], rel=TOL_LOSS), 'loss step %d' % s
       items = ref['items'] if ref['items'] is not None else np.arange(m['num_items'])
       last = {k2: (v.detach().cpu().numpy() if torch.is_tensor(v) else v) for k2, v in eng.last.items()}
       if kind == 'ae':
-        pairs = [('dWe', ref['grads'][O.AE_EN_W][items]), ('dWd', ref['grads'][O.AE_DE_W][items]),
-                 ('dbe', ref['grads'][O.AE_EN_B]), ('dbd', ref['grads'][O.AE_DE_B][items])]
+        pairs = [('dWe', ref['grads'][O.AE_EN_W][items]), ('dbe', ref['grads'][O.AE_EN_B]),
+                 ('dbd', ref['grads'][O.AE_DE_B][items])]
+        if not tied:   # tied: the single table's gradient (both contributions) is reported as dWe
+          pairs.append(('dWd', ref['grads'][O.AE_DE_W][items]))
+        for n2, gt in inner_grads(eng, model).items():
+          last[n2] = gt.detach().cpu().numpy()
+          pairs.append((n2, ref['grads'][n2]))
       else:
         pairs = [('dV', ref['grads'][O.MF_ITEM_W][items]), ('dbias', ref['grads'][O.MF_BIAS][items]),
                  ('dU', ref['grads'][O.MF_USER_W][ref['users']])]

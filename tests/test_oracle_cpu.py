@@ -15,7 +15,8 @@ def _trainer_from(g):
   params = {k: torch.from_numpy(v.copy()) for k, v in g.init_params().items()}
   return O.OracleTrainer(model=m['model'], params=params, loss=m['loss'],
                          confidence=m['loss_params'].get('confidence', 0.0), optimizer=m['opt'], lr=m['lr'],
-                         weight_decay=m['wd'], activation=m['act'], sparse=m['sparse'])
+                         weight_decay=m['wd'], activation=m['act'], sparse=m['sparse'],
+                         is_constrained=bool(m.get('constrained', False)))
 
 
 @pytest.mark.parametrize('name', case_names())
@@ -37,7 +38,8 @@ def test_oracle_matches_reference_golden(name):
       assert np.array_equal(b.indices, ref['indices'])
       assert np.array_equal(b.values, ref['values'])
       assert tuple(b.size) == ref['size']
-      loss, grads = tr.step(b)
+      loss, grads = tr.step(b, noise_keep=ref['noise_keep'], noise_prob=float(m.get('noise', 0.0)),
+                            dropout_keep=ref['dropout_keep'], dropout_prob=float(m.get('dropout', 0.0)))
       assert loss == pytest.approx(ref['loss'], rel=1e-6, abs=1e-7)
       for n in g.param_names:
         np.testing.assert_allclose(grads[n].numpy(), ref['grads'][n], rtol=1e-5, atol=1e-7, err_msg=n)
