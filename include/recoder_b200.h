@@ -290,6 +290,19 @@ int rcd_colsum(const float* x, int rows, int H, int ld, float* out, void* stream
 int rcd_f32_to_bf16_rows(const float* x, int rows, int H, uint16_t* out, int ld, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * K11 recommendation — replaces the tail of Recoder.recommend (recoder/model.py:525-544):
+ *     `output[input > 0] = -inf` and `torch.topk(output, k, dim=1, sorted=True)`.
+ *     rcd_mask_seen : logits[r, items[p]] = -inf for the stored interactions p of pool rows [row0, row0+rows)
+ *                     (row_ptr / items = the collate outputs row_ptr / raw_items); logits fp32 [rows, ld]
+ *     rcd_topk_rows : per row the k largest of n logits, descending (ties: lower index first);
+ *                     out_val fp32 [rows, k], out_idx int64 [rows, k]; 1 <= k <= min(n, 1024)
+ * ------------------------------------------------------------------------------------------------------- */
+int rcd_mask_seen(const int32_t* row_ptr, const int32_t* items, int row0, int rows, float* logits, long long ld,
+                  void* stream);
+int rcd_topk_rows(const float* logits, long long ld, int rows, int n, int k, float* out_val, int64_t* out_idx,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Telemetry / tests: L2 norm squared of a strided fp32 matrix (double accumulation), out_sq[0] += ...
  * ------------------------------------------------------------------------------------------------------- */
 int rcd_sumsq(const float* x, long long rows, int cols, int ld, double* out_sq, void* stream);

@@ -75,6 +75,8 @@ _SIGNATURES = {
   'rcd_act_grad': (c_int, [_P, _P, c_longlong, c_int, _P, _P]),
   'rcd_colsum': (c_int, [_P, c_int, c_int, c_int, _P, _P]),
   'rcd_f32_to_bf16_rows': (c_int, [_P, c_int, c_int, _P, c_int, _P]),
+  'rcd_mask_seen': (c_int, [_P, _P, c_int, c_int, _P, c_longlong, _P]),
+  'rcd_topk_rows': (c_int, [_P, c_longlong, c_int, c_int, c_int, _P, _P, _P]),
   'rcd_sumsq': (c_int, [_P, c_longlong, c_int, c_int, _P, _P]),
   'rcd_gemm_bf16': (c_int, [c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
 }

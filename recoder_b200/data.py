@@ -333,6 +333,17 @@ def collate_pool(csr, users, negative_sampling: bool) -> PoolBatch:
   return collate_pool_finish(collate_pool_launch(csr, users, negative_sampling))
 
 
+def pool_of(users_interactions, negative_sampling):
+  """Collates a whole :class:`UsersInteractions` on the GPU; returns (PoolBatch, the CSR it came from)."""
+  if users_interactions._source is not None:
+    _, get_csr, index = users_interactions._source
+    csr, rows = get_csr(), index
+  else:
+    m = users_interactions.interactions_matrix.tocsr()
+    csr, rows = DeviceCSR(m), np.arange(m.shape[0])
+  return collate_pool(csr, rows, negative_sampling), csr
+
+
 class BatchCollator:
   """
   Collator of :class:`UsersInteractions` into multiple :class:`Batch` based on ``batch_size``
@@ -354,13 +365,7 @@ class BatchCollator:
     Returns:
       list[Batch]: list of batches (``items`` shared by all slices, data.py:246).
     """
-    if users_interactions._source is not None:
-      _, get_csr, index = users_interactions._source
-      csr, rows = get_csr(), index
-    else:
-      m = users_interactions.interactions_matrix.tocsr()
-      csr, rows = DeviceCSR(m), np.arange(m.shape[0])
-    pb = collate_pool(csr, rows, self.negative_sampling)
+    pb, csr = pool_of(users_interactions, self.negative_sampling)
     batch_users = torch.as_tensor(np.asarray(users_interactions.users), dtype=torch.int64, device=csr.device)
     vector_dim = pb.n if self.negative_sampling else csr.shape[1]
     items = pb.items if self.negative_sampling else None

@@ -17,7 +17,8 @@ from torch.nn import BCEWithLogitsLoss
 
 from . import __version__
 from . import _native
-from .data import RecommendationDataLoader, BatchCollator, collate_pool, collate_pool_launch, collate_pool_finish
+from .data import (RecommendationDataLoader, BatchCollator, collate_pool, collate_pool_launch, collate_pool_finish,
+                   pool_of)
 from .engine import Optimizer, TrainEngine, shard_rows
 from .losses import MSELoss, MultinomialNLLLoss
 from .nn import FactorizationModel
@@ -543,7 +544,8 @@ class Recoder(object):
   def _evaluate(self, eval_dataset, num_recommendations, metrics, batch_size=1, num_users=None):
     if self.model is None:
       raise Exception('Model not initialized')
-    from .metrics import RecommenderEvaluator, InferenceRecommender
+    from .metrics import RecommenderEvaluator
+    from .recommender import InferenceRecommender
     self.model.eval()
     recommender = InferenceRecommender(self, num_recommendations)
     evaluator = RecommenderEvaluator(recommender, metrics)
@@ -556,11 +558,25 @@ class Recoder(object):
     Returns:
       list: list of recommended items for each user in users_interactions.
     """
-    output, input = self.predict(users_interactions, return_input=True)
-    # Set input items output to -inf so that they don't get recommended
-    output = output.clone()
-    output[input > 0] = - float('inf')
-    top_output, top_ind = torch.topk(output, num_recommendations, dim=1, sorted=True)
+    if self.model is None:
+      raise Exception('Model not initialized.')
+    self.__require_cuda()
+    if self.engine is not None:
+      self.engine.join()
+    self.model.eval()
+    # the pool is collated on the GPU (no negative sampling: columns are raw item ids) and goes through the encoder as
+    # CSR; the dense [B, I] input and the boolean mask pass of the reference (model.py:502-510, 541) never exist
+    pool, _ = pool_of(users_interactions, False)
+    logits = self.model.forward_pool(pool)
+    rows, n = logits.shape
+    ld = logits.stride(0)
+    if pool.nnz:
+      _native.call('rcd_mask_seen', _native.ptr(pool.row_ptr), _native.ptr(pool.raw_items), 0, rows,
+                   _native.ptr(logits), ld)
+    k = int(num_recommendations)
+    top_val = torch.empty(rows, k, dtype=torch.float32, device=logits.device)
+    top_ind = torch.empty(rows, k, dtype=torch.int64, device=logits.device)
+    _native.call('rcd_topk_rows', _native.ptr(logits), ld, rows, n, k, _native.ptr(top_val), _native.ptr(top_ind))
     return top_ind.tolist()
 
   def evaluate(self, eval_dataset, num_recommendations, metrics, batch_size=1, num_users=None):

@@ -239,20 +239,27 @@ class DynamicAutoencoder(FactorizationModel):
   def forward(self, input, input_users=None, input_items=None, target_users=None, target_items=None):
     """Inference forward on a dense ``[B, n]`` CUDA input (reference nn.py:228-253), fp32 logits out.
     Noise / dropout layers are identities outside training, as in the reference's eval mode."""
-    dev = input.device
-    B, n_in = input.shape
-    We, Wd = self.en_embedding_layer.weight.data, self.de_embedding_layer.weight.data
-    H = We.shape[1]
-    ldh = (H + 7) // 8 * 8
     row_ptr, cols, vals, rin, _ = _dense_input_to_csr(input)
     if input_items is not None:
-      raw = input_items.to(dev)[cols.long()].to(torch.int32)
+      raw = input_items.to(input.device)[cols.long()].to(torch.int32)
     else:
       raw = cols
+    return self._forward_csr(row_ptr, raw, vals, rin, 0, input.shape[0], target_items)
+
+  def forward_pool(self, pool, target_items=None):
+    """Inference forward straight from a collated pool (data.PoolBatch, negative_sampling=False): logits fp32
+    [rows, num_items] — the dense [B, I] input of the reference's `predict` (model.py:502-510) never exists."""
+    return self._forward_csr(pool.row_ptr, pool.raw_items, pool.vals, pool.row_inv_norm, 0, pool.num_rows, target_items)
+
+  def _forward_csr(self, row_ptr, raw, vals, rin, row0, B, target_items):
+    We, Wd = self.en_embedding_layer.weight.data, self.de_embedding_layer.weight.data
+    dev = We.device
+    H = We.shape[1]
+    ldh = (H + 7) // 8 * 8
     Z = torch.empty(B, H, dtype=torch.float32, device=dev)
     Zb = torch.empty(B, ldh, dtype=torch.bfloat16, device=dev)
     act = _native.ACT_IDS[self.activation_type]
-    call('rcd_ae_encoder_fwd', ptr(We), H, ptr(self.en_bias.data), ptr(row_ptr), ptr(raw), ptr(vals), ptr(rin), 0, B,
+    call('rcd_ae_encoder_fwd', ptr(We), H, ptr(self.en_bias.data), ptr(row_ptr), ptr(raw), ptr(vals), ptr(rin), row0, B,
          act, ptr(Z), ptr(Zb), ldh)
     if len(self.encoding_layers):
       # inner encoding / decoding layers, activation after every one (nn.py:242-249); dropout is off in eval mode
@@ -364,8 +371,12 @@ class MatrixFactorization(FactorizationModel):
     dev = U.device
     D = V.shape[1]
     ldd = (D + 7) // 8 * 8
-    users = input_users.to(dev).to(torch.int64).contiguous()
+    users = torch.as_tensor(input_users).to(dev).to(torch.int64).contiguous()
     B = users.numel()
     Ub = torch.empty(B, ldd, dtype=torch.bfloat16, device=dev)
     call('rcd_gather_rows', ptr(U), D, ptr(users), B, _native.ACT_IDS[self.activation_type], ptr(Ub), ldd, None)
     return _decode_all(Ub, ldd, V, self.bias.data, target_items, B, D)
+
+  def forward_pool(self, pool, target_items=None):
+    """Inference forward for the users of a collated pool (data.PoolBatch)."""
+    return self.forward(None, input_users=pool.users, target_items=target_items)

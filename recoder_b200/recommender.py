@@ -1,0 +1,27 @@
+"""Recommender adapters with the reference's interface (recoder/recommender.py:8-24, 104-118).  The Annoy-based
+`SimilarityRecommender` (recommender.py:27-101) is a serving-side component outside the training path
+ and is not rebuilt."""
+
+
+class Recommender(object):
+  """Base class for recommenders: ``recommend(users_hist) -> list of item-id lists``."""
+
+  def recommend(self, users_hist):
+    raise NotImplementedError
+
+
+class InferenceRecommender(Recommender):
+  """
+  Recommends items based on the predictions by a :class:`recoder_b200.model.Recoder` model.
+
+  Args:
+    model (Recoder): model used to predict recommendations
+    num_recommendations (int): number of recommendations to generate for each user.
+  """
+
+  def __init__(self, model, num_recommendations):
+    self.model = model
+    self.num_recommendations = num_recommendations
+
+  def recommend(self, users_hist):
+    return self.model.recommend(users_hist, self.num_recommendations)
