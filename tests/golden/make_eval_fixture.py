@@ -1,10 +1,10 @@
 """Generates the evaluation fixtures from the UNMODIFIED reference (build container only):
 
-  tests/golden/ml_fixture.npz   the train / validation interaction matrices of the reference's golden-metric test
+  tests/golden/eval/ml_fixture.npz   the train / validation interaction matrices of the reference's golden-metric test
                                 (tests/test_model.py:18-36: tests/data/{train,val}.csv through
                                 recoder.utils.dataframe_to_csr_matrix, validation items restricted to training items),
                                 stored as CSR with uint16 item ids (all values are 1)
-  tests/golden/eval_golden.npz  `Recoder.recommend` (model.py:525-544) + Recall/NDCG/AP (metrics.py) of the reference on
+  tests/golden/eval/eval_golden.npz  `Recoder.recommend` (model.py:525-544) + Recall/NDCG/AP (metrics.py) of the reference on
                                 a seeded random DynamicAutoencoder and MatrixFactorization: the inputs, the parameters,
                                 the top-k lists and the per-user metric values
 
@@ -44,7 +44,7 @@ def ml_fixture():
     out[name + '_indptr'] = m.indptr.astype(np.int32)
     out[name + '_indices'] = m.indices.astype(np.uint16)
     out[name + '_shape'] = np.array(m.shape, dtype=np.int64)
-  path = os.path.join(HERE, 'ml_fixture.npz')
+  path = os.path.join(HERE, 'eval', 'ml_fixture.npz')
   np.savez_compressed(path, **out)
   print('ml_fixture: train %s nnz %d, val %s nnz %d, %.0f KB' % (train.shape, train.nnz, val.shape, val.nnz,
                                                                  os.path.getsize(path) / 1024))
@@ -96,7 +96,7 @@ def eval_golden():
         per_user[str(m)].append(m.evaluate(recs[u], y))
     for k2, v in per_user.items():
       out[kind + '/metric/' + k2] = np.array(v, dtype=np.float64)
-  path = os.path.join(HERE, 'eval_golden.npz')
+  path = os.path.join(HERE, 'eval', 'eval_golden.npz')
   np.savez_compressed(path, **out)
   print('eval_golden: %.0f KB' % (os.path.getsize(path) / 1024))
 

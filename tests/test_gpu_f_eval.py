@@ -1,7 +1,7 @@
 """Evaluation path: the mask + top-k kernels against torch, `Recoder.recommend` against the
-recommendations / scores / metrics the unmodified reference produced (tests/golden/eval_golden.npz), and the
+recommendations / scores / metrics the unmodified reference produced (tests/golden/eval/eval_golden.npz), and the
 reference's own end-to-end golden-metric test (tests/test_model.py:14-84: Recall@20 0.40, Recall@50 0.43, NDCG@100
-0.45, atol 0.01, then the same after a checkpoint round trip) on its own data (tests/golden/ml_fixture.npz)."""
+0.45, atol 0.01, then the same after a checkpoint round trip) on its own data (tests/golden/eval/ml_fixture.npz)."""
 import os
 
 import numpy as np
@@ -17,7 +17,7 @@ from recoder_b200.model import Recoder
 from recoder_b200.nn import DynamicAutoencoder, MatrixFactorization
 
 pytestmark = pytest.mark.gpu
-GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'eval')
 
 
 @pytest.mark.parametrize('rows,n,k', [(7, 100, 10), (64, 11466, 100), (33, 200000, 1024), (5, 50, 50), (3, 1000, 1)])

@@ -1,6 +1,6 @@
 """Ranking metrics (recoder_b200/metrics.py) against the reference's own known-answer tests
 (tests/test_metrics.py:12-54 there, restated with the same inputs and expected values, rtol 1e-9) and against the
-per-user values the unmodified reference computed for tests/golden/eval_golden.npz."""
+per-user values the unmodified reference computed for tests/golden/eval/eval_golden.npz."""
 import os
 
 import numpy as np
@@ -9,7 +9,7 @@ import pytest
 from recoder_b200.metrics import NDCG, AveragePrecision, Recall
 
 RTOL, ATOL = 1e-9, 0.0
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'eval_golden.npz')
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'eval', 'eval_golden.npz')
 
 
 @pytest.mark.parametrize('x, y, k, normalize, expected', [
