@@ -252,11 +252,16 @@ class PoolBatch:
     return self.items_buf[:self.n]
 
 
-def collate_pool_launch(csr, users, negative_sampling: bool) -> PoolBatch:
+def collate_pool_launch(csr, users, negative_sampling: bool, stream=None, after=()) -> PoolBatch:
   """Enqueues K1 on the rows `users` of `csr` (DeviceCSR, or HostStagedCSR: staged over PCIe first) and an
   asynchronous read-back of the two counts (n, nnz) every downstream shape depends on.  The returned PoolBatch is
   usable after `collate_pool_finish`.  Launching the collate of pool i+1 before the training step of pool i is
-  enqueued hides the read-back behind that step (Recoder._pool_steps)."""
+  enqueued hides the read-back behind that step (Recoder._pool_steps).
+
+  `stream`: run the collate kernels on this (auxiliary) CUDA stream so that they overlap the training step the
+  caller enqueues next on the current stream; the outputs are allocated on the CURRENT stream's pool and the auxiliary
+  stream first waits for the current stream and for every stream in `after`, so recycled memory is never written
+  while an earlier kernel still reads it.  `collate_pool_finish` makes the current stream wait for the collate."""
   users = np.ascontiguousarray(np.asarray(users).reshape(-1), dtype=np.int64)
   assert users.size > 0
   assert users.min() >= 0 and users.max() < csr.shape[0], 'user index out of range'
@@ -289,15 +294,24 @@ def collate_pool_launch(csr, users, negative_sampling: bool) -> PoolBatch:
   lib = _native.load()
   sbytes = lib.rcd_collate_scratch_bytes(P, I)
   scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
-  _native.call('rcd_collate', _native.ptr(csr.indptr), _native.ptr(csr.indices), _native.ptr(csr.data),
-               _native.ptr(rows_dev), P, I, int(bool(negative_sampling)), cap, _native.ptr(pb.row_ptr),
-               _native.ptr(pb.raw_items), _native.ptr(pb.cols), _native.ptr(pb.vals), _native.ptr(pb.row_inv_norm),
-               _native.ptr(pb.row_sum), _native.ptr(pb.pos), _native.ptr(pb.items_buf), _native.ptr(pb.counts),
-               _native.ptr(scratch), sbytes)
   counts_host = _pinned_counts()
-  counts_host.copy_(pb.counts, non_blocking=True)
-  ev = torch.cuda.Event()
-  ev.record()
+  import contextlib
+  ctx = contextlib.nullcontext()
+  if stream is not None:
+    stream.wait_stream(torch.cuda.current_stream())
+    for other in after:
+      if other is not None:
+        stream.wait_stream(other)
+    ctx = torch.cuda.stream(stream)
+  with ctx:
+    _native.call('rcd_collate', _native.ptr(csr.indptr), _native.ptr(csr.indices), _native.ptr(csr.data),
+                 _native.ptr(rows_dev), P, I, int(bool(negative_sampling)), cap, _native.ptr(pb.row_ptr),
+                 _native.ptr(pb.raw_items), _native.ptr(pb.cols), _native.ptr(pb.vals), _native.ptr(pb.row_inv_norm),
+                 _native.ptr(pb.row_sum), _native.ptr(pb.pos), _native.ptr(pb.items_buf), _native.ptr(pb.counts),
+                 _native.ptr(scratch), sbytes)
+    counts_host.copy_(pb.counts, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
   TRANSFER_BYTES['d2h'] += 8
   pb._pending = (counts_host, ev, nnz, (csr, rows_dev, scratch))  # keeps the kernel inputs alive until finish
   return pb
@@ -320,6 +334,7 @@ def collate_pool_finish(pb: PoolBatch) -> PoolBatch:
   if pb._pending is None:
     return pb
   counts_host, ev, nnz, _ = pb._pending
+  torch.cuda.current_stream().wait_event(ev)   # no-op when the collate ran on the current stream
   ev.synchronize()
   pb.n = int(counts_host[0])
   pb.nnz = int(counts_host[1])

@@ -250,6 +250,7 @@ class TrainEngine:
     self.overlap = os.environ.get('RCD_OVERLAP', '1') != '0'
     self.late_update = os.environ.get('RCD_LATE_UPDATE', '0') == '1'   # experiment: decoder-side update at the end
     self._side = None
+    self._aux = None
     self._ready = {}
     dev = (params['en_w'] if kind == 'ae' else params['item_w'])[1].device
     self.device = dev
@@ -357,6 +358,23 @@ class TrainEngine:
       self._mf_step(pool, target_pool or pool, row0, rows, 1.0 / rows, slot, train=False)
     return float(slot.item())
 
+  def _aux_stream(self):
+    """Context manager: the column-major views of the slice (needed only by the weight gradients, late in the step)
+    are built on an auxiliary stream underneath the forward kernels."""
+    import contextlib
+    if not self.overlap:
+      return contextlib.nullcontext()
+    if self._aux is None:
+      self._aux = torch.cuda.Stream(device=self.device)
+    self._aux.wait_stream(torch.cuda.current_stream())
+    return torch.cuda.stream(self._aux)
+
+  def _aux_done(self):
+    if self._aux is not None:
+      ev = torch.cuda.Event()
+      ev.record(self._aux)
+      self._ready['csc'] = ev
+
   def _slice_csc(self, pool, row0, rows, n, tag):
     nnz = int(pool.row_ptr_host[row0 + rows] - pool.row_ptr_host[row0])
     b = self.buf
@@ -430,6 +448,17 @@ class TrainEngine:
     ev.record()
     self._side.wait_event(ev)
     return torch.cuda.stream(self._side)
+
+  def _keep_for_side(self, *pools):
+    """Pool tensors the update stream reads (pos / items) must not be recycled before its kernels have run."""
+    if self._side is None:
+      return
+    for pb in pools:
+      if pb is None:
+        continue
+      for t in (pb.pos, pb.items_buf, pb.users):
+        if t is not None and t.is_cuda:
+          t.record_stream(self._side)
 
   def _mark_ready(self, tag):
     ev = torch.cuda.Event()
@@ -624,8 +653,12 @@ class TrainEngine:
     if self.tied and not same:
       raise NotImplementedError('tied weights with a separate target matrix are not supported')
     t_items = tpool.items if tpool.negative_sampling else None
-    csc_t = self._slice_csc(tpool, row0, rows, n, 't_') if train else None
-    csc_in = csc_t if same else (self._slice_csc(pool, row0, rows, n_in, 'i_') if train else None)
+    csc_t = csc_in = None
+    if train:
+      with self._aux_stream():
+        csc_t = self._slice_csc(tpool, row0, rows, n, 't_')
+        csc_in = csc_t if same else self._slice_csc(pool, row0, rows, n_in, 'i_')
+      self._aux_done()
 
     # gradient slab: [dWe_rows n_in*H | dWd_rows n*H | dbd n (pad 4) | dbe H (pad 4) | inner layers | pad 2 | loss hi, lo]
     n4, h4 = _round_up(n, 4), _round_up(H, 4)
@@ -675,12 +708,14 @@ class TrainEngine:
     # tensor-core dgrad GEMM and the encoder backward: sparse dgrad (reads master W_d) -> dW_d -> [W_d, b_d update]
     # || dgrad GEMM -> dA -> dW_e -> [W_e, b_e update].
     partials, splits = self._sparse_dgrad(corr, Wd, tpool, row0, rows, n, H)
+    self._wait_ready('csc')
     self._wgrad(G, ldn, Zs, ldh, Y, csc_t, corr, alpha, rows, n, H, dWd, dbd)
     self.last = {'n': n, 'n_in': n_in, 'dWe': dWe.view(n_in, H), 'dWd': dWd.view(n, H), 'dbd': dbd, 'dbe': dbe,
                  'inner': inner_grads, 'inner_layout': inner}
     sequential = self.tied or (self.pg is not None and self.p2p is None) or (self.late_update and self.pg is None)
     if not sequential:
       with self._update_stream():
+        self._keep_for_side(pool, tpool)
         if self.p2p is not None:
           self.p2p.barrier(self.bad_flag)          # every rank's dW_d / db_d is complete
           self.opt.step_param_p2p(de_name, self.p2p, self._slab_shared.ptr_table(4 * o_wd), H, tpool.pos,
@@ -749,7 +784,11 @@ class TrainEngine:
     n = tpool.n
     world, rank = self._world()
     t_items = tpool.items if tpool.negative_sampling else None
-    csc = self._slice_csc(tpool, row0, rows, n, 't_') if train else None
+    csc = None
+    if train:
+      with self._aux_stream():
+        csc = self._slice_csc(tpool, row0, rows, n, 't_')
+      self._aux_done()
     users = pool.users[row0:row0 + rows]
 
     # slab: [dV_rows n*D | dbias n (pad 4) | dU rows of ALL ranks (other ranks' blocks zero) | pad 2 | loss hi, lo]
@@ -787,11 +826,13 @@ class TrainEngine:
     # same schedule as the autoencoder: sparse dgrad (reads master V) -> dV -> [V, bias update on the side stream]
     # || dgrad GEMM -> dU -> [user-table update]
     partials, splits = self._sparse_dgrad(corr, V, tpool, row0, rows, n, D)
+    self._wait_ready('csc')
     self._wgrad(G, ldn, Us, ldd, Y, csc, corr, alpha, rows, n, D, dV, dbias)
     self.last = {'n': n, 'dV': dV.view(n, D), 'dbias': dbias, 'dU': dU.view(rows, D)}
     sequential = self.pg is not None and self.p2p is None
     if not sequential:
       with self._update_stream():
+        self._keep_for_side(pool, tpool)
         if self.p2p is not None:
           self.p2p.barrier(self.bad_flag)
           self.opt.step_param_p2p(v_name, self.p2p, self._slab_shared.ptr_table(0), D, tpool.pos,

@@ -404,9 +404,13 @@ class Recoder(object):
     gstep = batch_size * world
     ns = dataloader.negative_sampling
 
+    # the collate of the NEXT pool runs on its own stream, underneath the current pool's training steps
+    aux = torch.cuda.Stream() if os.environ.get('RCD_OVERLAP', '1') != '0' else None
+
     def launch(index):
-      pool = collate_pool_launch(csr, index, ns)
-      tpool = collate_pool_launch(tcsr, index, ns) if tcsr is not None else None
+      after = (self.engine._side,) if self.engine is not None else ()
+      pool = collate_pool_launch(csr, index, ns, stream=aux, after=after)
+      tpool = collate_pool_launch(tcsr, index, ns, stream=aux, after=after) if tcsr is not None else None
       return pool, tpool
 
     # One-pool-ahead software pipeline: the collate of pool i+1 is enqueued BEFORE the training steps of pool i, so
