@@ -117,7 +117,13 @@ def ptr(t):
   return c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def stream_ptr():
+  """Raw cudaStream_t of torch's current stream on the current device."""
+  if _raw_stream is not None:
+    return c_void_p(_raw_stream(torch.cuda.current_device()))
   return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -131,17 +137,21 @@ def check(status, what):
 # TIMINGS maps entry-point name -> list of (start_event, end_event) recorded on the current stream.
 PROFILE = None
 TIMINGS = {}
+_FN = {}
 
 
 def call(name, *args):
   """Calls an `int`-status entry point on the current stream (stream appended automatically)."""
-  lib = load()
+  fn = _FN.get(name)
+  if fn is None:
+    fn = _FN[name] = getattr(load(), name)
   if PROFILE is not None and (PROFILE == 'all' or name in PROFILE):
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
-    status = getattr(lib, name)(*args, stream_ptr())
+    status = fn(*args, stream_ptr())
     end.record()
     TIMINGS.setdefault(name, []).append((start, end))
   else:
-    status = getattr(lib, name)(*args, stream_ptr())
-  check(status, name)
+    status = fn(*args, stream_ptr())
+  if status != 0:
+    check(status, name)

@@ -55,7 +55,7 @@ class HostStagedCSR:
   staging buffers (K0, `rcd_host_stage_rows`) and sends them H2D; the result is a pool-local DeviceCSR whose
   row r is user `users[r]`."""
 
-  RING = 2
+  RING = 3   # pool i trains while pool i+1 is staged/collated; one spare so a slot is never rewritten in flight
 
   def __init__(self, matrix: sparse.csr_matrix, device=None):
     _native.require_cuda()
@@ -76,6 +76,10 @@ class HostStagedCSR:
       slot = {'ptr': torch.empty(cap_p, dtype=torch.int64).pin_memory(),
               'idx': torch.empty(cap_n, dtype=torch.int32).pin_memory(),
               'val': torch.empty(cap_n, dtype=torch.float32).pin_memory(),
+              # device side of the staging slot: grow-only, so a step allocates nothing
+              'd_ptr': torch.empty(cap_p, dtype=torch.int64, device=self.device),
+              'd_idx': torch.empty(cap_n, dtype=torch.int32, device=self.device),
+              'd_val': torch.empty(cap_n, dtype=torch.float32, device=self.device),
               'event': None}
       self._ring[i] = slot
     elif slot['event'] is not None:
@@ -96,10 +100,14 @@ class HostStagedCSR:
     mini = DeviceCSR.__new__(DeviceCSR)
     mini.device = self.device
     mini.shape = (P, self.shape[1])
+    m = max(nnz, 1)
     mini.indptr_host = slot['ptr'][:P + 1].numpy()
-    mini.indptr = slot['ptr'][:P + 1].to(self.device, non_blocking=True)
-    mini.indices = slot['idx'][:max(nnz, 1)].to(self.device, non_blocking=True)
-    mini.data = slot['val'][:max(nnz, 1)].to(self.device, non_blocking=True)
+    mini.indptr = slot['d_ptr'][:P + 1]
+    mini.indices = slot['d_idx'][:m]
+    mini.data = slot['d_val'][:m]
+    mini.indptr.copy_(slot['ptr'][:P + 1], non_blocking=True)
+    mini.indices.copy_(slot['idx'][:m], non_blocking=True)
+    mini.data.copy_(slot['val'][:m], non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
     slot['event'] = ev
@@ -252,7 +260,31 @@ class PoolBatch:
     return self.items_buf[:self.n]
 
 
-def collate_pool_launch(csr, users, negative_sampling: bool, stream=None, after=()) -> PoolBatch:
+class PoolRing:
+  """Grow-only device buffers for the collate outputs of successive pools (3 slots: the pool being trained on, the
+  one being collated, one spare).  The training loop collates thousands of pools of nearly equal size: without the
+  ring every pool costs a dozen allocator round trips on the host, which is what bounds small configurations."""
+
+  SLOTS = 3
+
+  def __init__(self):
+    self._slots = [dict() for _ in range(self.SLOTS)]
+    self._turn = 0
+
+  def next_slot(self):
+    self._turn += 1
+    return self._slots[self._turn % self.SLOTS]
+
+  @staticmethod
+  def take(slot, name, numel, dtype, device):
+    t = slot.get(name)
+    if t is None or t.numel() < numel or t.dtype != dtype:
+      t = torch.empty(max(int(numel * 1.25) + 16, 1), dtype=dtype, device=device)
+      slot[name] = t
+    return t[:numel]
+
+
+def collate_pool_launch(csr, users, negative_sampling: bool, stream=None, after=(), ring=None) -> PoolBatch:
   """Enqueues K1 on the rows `users` of `csr` (DeviceCSR, or HostStagedCSR: staged over PCIe first) and an
   asynchronous read-back of the two counts (n, nnz) every downstream shape depends on.  The returned PoolBatch is
   usable after `collate_pool_finish`.  Launching the collate of pool i+1 before the training step of pool i is
@@ -267,13 +299,40 @@ def collate_pool_launch(csr, users, negative_sampling: bool, stream=None, after=
   assert users.min() >= 0 and users.max() < csr.shape[0], 'user index out of range'
   dev = csr.device
   P, I = int(users.size), int(csr.shape[1])
-  users_dev = torch.from_numpy(users).to(dev, non_blocking=True)
-  TRANSFER_BYTES['h2d'] += P * 8
-  rows_dev = users_dev
-  if isinstance(csr, HostStagedCSR):
-    csr = csr.stage(users)
-    users = np.arange(P, dtype=np.int64)
-    rows_dev = torch.arange(P, dtype=torch.int64, device=dev)
+  slot = ring.next_slot() if ring is not None else None
+
+  def buf(name, numel, dtype):
+    if slot is None:
+      return torch.empty(max(numel, 1), dtype=dtype, device=dev)[:numel]
+    return PoolRing.take(slot, name, numel, dtype, dev)
+
+  import contextlib
+  ctx = contextlib.nullcontext
+  if stream is not None:
+    stream.wait_stream(torch.cuda.current_stream())
+    for other in after:
+      if other is not None:
+        stream.wait_stream(other)
+    ctx = lambda: torch.cuda.stream(stream)  # noqa: E731
+  # with ring buffers nothing below allocates, so the H2D copies can ride on the auxiliary stream as well
+  copy_ctx = ctx if slot is not None else contextlib.nullcontext
+  with copy_ctx():
+    if slot is None:
+      users_dev = torch.from_numpy(users).to(dev, non_blocking=True)
+    else:
+      pin = slot.get('users_pin')
+      if pin is None or pin.numel() < P:
+        pin = torch.empty(int(P * 1.25) + 16, dtype=torch.int64).pin_memory()
+        slot['users_pin'] = pin
+      pin[:P].copy_(torch.from_numpy(users))
+      users_dev = buf('users', P, torch.int64)
+      users_dev.copy_(pin[:P], non_blocking=True)
+    TRANSFER_BYTES['h2d'] += P * 8
+    rows_dev = users_dev
+    if isinstance(csr, HostStagedCSR):
+      csr = csr.stage(users)
+      users = np.arange(P, dtype=np.int64)
+      rows_dev = _arange_cached(P, dev)
   lens = csr.indptr_host[users + 1] - csr.indptr_host[users]
   nnz = int(lens.sum())
   assert nnz < 2 ** 31, 'pool too large'
@@ -282,28 +341,23 @@ def collate_pool_launch(csr, users, negative_sampling: bool, stream=None, after=
   np.cumsum(lens, out=row_ptr_host[1:])
   pb.row_ptr_host = row_ptr_host
   cap = max(nnz, 1)
-  pb.row_ptr = torch.empty(P + 1, dtype=torch.int32, device=dev)
-  pb.raw_items = torch.empty(cap, dtype=torch.int32, device=dev)
-  pb.cols = torch.empty(cap, dtype=torch.int32, device=dev)
-  pb.vals = torch.empty(cap, dtype=torch.float32, device=dev)
-  pb.row_inv_norm = torch.empty(P, dtype=torch.float32, device=dev)
-  pb.row_sum = torch.empty(P, dtype=torch.float32, device=dev)
-  pb.pos = torch.empty(I, dtype=torch.int32, device=dev)
-  pb.items_buf = torch.empty(min(I, cap) if negative_sampling else I, dtype=torch.int64, device=dev)
-  pb.counts = torch.zeros(2, dtype=torch.int32, device=dev)
+  pb.row_ptr = buf('row_ptr', P + 1, torch.int32)
+  pb.raw_items = buf('raw_items', cap, torch.int32)
+  pb.cols = buf('cols', cap, torch.int32)
+  pb.vals = buf('vals', cap, torch.float32)
+  pb.row_inv_norm = buf('row_inv_norm', P, torch.float32)
+  pb.row_sum = buf('row_sum', P, torch.float32)
+  pb.pos = buf('pos', I, torch.int32)
+  pb.items_buf = buf('items_buf', min(I, cap) if negative_sampling else I, torch.int64)
+  pb.counts = buf('counts', 2, torch.int32)
   lib = _native.load()
   sbytes = lib.rcd_collate_scratch_bytes(P, I)
-  scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+  scratch = buf('scratch', sbytes, torch.uint8)
   counts_host = _pinned_counts()
-  import contextlib
-  ctx = contextlib.nullcontext()
-  if stream is not None:
-    stream.wait_stream(torch.cuda.current_stream())
-    for other in after:
-      if other is not None:
-        stream.wait_stream(other)
-    ctx = torch.cuda.stream(stream)
-  with ctx:
+  if stream is not None and slot is None:
+    stream.wait_stream(torch.cuda.current_stream())   # the copies above went to the current stream
+  with ctx():
+    pb.counts.zero_()
     _native.call('rcd_collate', _native.ptr(csr.indptr), _native.ptr(csr.indices), _native.ptr(csr.data),
                  _native.ptr(rows_dev), P, I, int(bool(negative_sampling)), cap, _native.ptr(pb.row_ptr),
                  _native.ptr(pb.raw_items), _native.ptr(pb.cols), _native.ptr(pb.vals), _native.ptr(pb.row_inv_norm),
@@ -315,6 +369,17 @@ def collate_pool_launch(csr, users, negative_sampling: bool, stream=None, after=
   TRANSFER_BYTES['d2h'] += 8
   pb._pending = (counts_host, ev, nnz, (csr, rows_dev, scratch))  # keeps the kernel inputs alive until finish
   return pb
+
+
+_ARANGE_CACHE = {}
+
+
+def _arange_cached(n, dev):
+  t = _ARANGE_CACHE.get(dev)
+  if t is None or t.numel() < n:
+    t = torch.arange(int(n * 1.25) + 16, dtype=torch.int64, device=dev)
+    _ARANGE_CACHE[dev] = t
+  return t[:n]
 
 
 _COUNTS_RING = []

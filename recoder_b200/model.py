@@ -18,7 +18,7 @@ from torch.nn import BCEWithLogitsLoss
 from . import __version__
 from . import _native
 from .data import (RecommendationDataLoader, BatchCollator, collate_pool, collate_pool_launch, collate_pool_finish,
-                   pool_of)
+                   pool_of, PoolRing)
 from .engine import Optimizer, TrainEngine, shard_rows
 from .losses import MSELoss, MultinomialNLLLoss
 from .nn import FactorizationModel
@@ -407,10 +407,12 @@ class Recoder(object):
     # the collate of the NEXT pool runs on its own stream, underneath the current pool's training steps
     aux = torch.cuda.Stream() if os.environ.get('RCD_OVERLAP', '1') != '0' else None
 
+    ring, tring = PoolRing(), PoolRing()
+
     def launch(index):
       after = (self.engine._side,) if self.engine is not None else ()
-      pool = collate_pool_launch(csr, index, ns, stream=aux, after=after)
-      tpool = collate_pool_launch(tcsr, index, ns, stream=aux, after=after) if tcsr is not None else None
+      pool = collate_pool_launch(csr, index, ns, stream=aux, after=after, ring=ring)
+      tpool = collate_pool_launch(tcsr, index, ns, stream=aux, after=after, ring=tring) if tcsr is not None else None
       return pool, tpool
 
     # One-pool-ahead software pipeline: the collate of pool i+1 is enqueued BEFORE the training steps of pool i, so
