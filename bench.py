@@ -61,6 +61,32 @@ def load_peaks():
     return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source='fallback')
 
 
+NCU_KERNEL_OF = {'rcd_adam_step': 'k_adam<4>', 'rcd_decoder_fwd_loss': 'k_decoder_fused', 'rcd_adam_step_p2p': 'k_adam_p2p'}
+
+
+def ncu_traffic(entry_point):
+  """DRAM bytes (read + write) per launch of the kernel behind `entry_point`, from the newest committed
+  `ncu --set full` summary under profiles/ (same workload shape as the default bench); None when there is none."""
+  import csv
+  import glob
+  kernel = NCU_KERNEL_OF.get(entry_point)
+  if kernel is None:
+    return None, None
+  for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_ncu_full_top_kernels.csv')), reverse=True):
+    try:
+      rows = list(csv.reader(open(path)))
+      hdr = rows[0]
+      ni, ri, wi = hdr.index('Kernel Name'), hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+      unit = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}.get(rows[1][ri], 1e9)
+      vals = [(float(r[ri]) + float(r[wi])) * unit for r in rows[2:] if kernel in r[ni]]
+      vals = [v for v in vals if v > 0.5 * max(vals)] if vals else vals   # the big launches (tables, not biases)
+      if vals:
+        return sum(vals) / len(vals), os.path.basename(path)
+    except Exception:
+      continue
+  return None, None
+
+
 def make_matrix(w, users_override=None):
   from recoder_b200.synth import synthetic_csr
   U = users_override or w['users']
@@ -383,8 +409,14 @@ def b200_arm(args, w):
         ach, peak, unit = per_launch / sec / 1e12, peaks['tensor_sustained'], 'TFLOP/s'
       else:
         ach, peak, unit = per_launch / sec / 1e9, peaks['hbm'], 'GB/s'
+      traffic, traffic_src = ncu_traffic(dom)
+      if traffic is not None and dom == 'rcd_adam_step':
+        # the ncu figure is the mean over the table launches; a step also has the (KB-sized) bias launches, and
+        # `achieved` averages over all `lps` launches of a step — put both on the same per-launch footing
+        traffic = traffic * n_tab / lps
       roofline = {'kernel': dom, 'bound': 'tensor' if bound == 'tensor' else 'hbm', 'achieved': round(ach, 2),
-                  'peak': peak, 'unit': unit, 'frac': round(ach / peak, 4), 'traffic': None,
+                  'peak': peak, 'unit': unit, 'frac': round(ach / peak, 4), 'traffic': traffic,
+                  'traffic_source': traffic_src, 'algorithmic_per_launch': per_launch,
                   'peak_source': peaks['source'] + (' (sustained)' if bound == 'tensor' else ''),
                   'launches_per_step': lps, 'avg_launch_ms': round(s_dev['dom_ms'], 4)}
 
