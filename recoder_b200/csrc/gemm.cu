@@ -44,7 +44,7 @@ RCD_EXPORT int rcd_decoder_fwd(const uint16_t* Zb, int ldzb, const uint16_t* Wg,
 RCD_EXPORT int rcd_decoder_dgrad_splits(int rows, int n, int H) {
   if (rows <= 0 || n <= 0 || H <= 0) return 1;
   const int bn = pick_bn(H);
-  const int tiles = rcd_div_up(rows, kTileM) * rcd_div_up(H, bn);
+  const int tiles = rcd_div_up(rows, rows > kTileM ? 2 * kTileM : kTileM) * rcd_div_up(H, bn);  // 256-row CTA tiles
   const int kblocks = rcd_div_up(n, kTileK);
   int splits = rcd_div_up(2 * rcd_num_sms(), tiles);  // about two waves of work units
   if (splits > kblocks) splits = kblocks;
@@ -61,7 +61,7 @@ RCD_EXPORT int rcd_decoder_dgrad(const uint16_t* dO, int lddo, const uint16_t* W
   RCD_CHECK_ARG(lddo >= n && ldw >= H && ldp >= H, "bad leading dimension");
   GemmProblem g{};
   g.mode = 1; g.A = dO; g.lda = lddo; g.B = Wg; g.ldb = ldw; g.M = rows; g.N = H; g.K = n;
-  g.bn = pick_bn(H); g.splits = splits; g.n_fastest = 1; g.split_major = 1;
+  g.bn = pick_bn(H); g.splits = splits; g.n_fastest = 1; g.split_major = 1; g.m_sub = 2;
   EpiParams e{};
   e.kind = EPI_F32; e.M = rows; e.N = H; e.C = partials; e.ldc = ldp; e.split_stride = (long long)rows * ldp;
   return launch(g, e, engine, (cudaStream_t)stream);
@@ -86,6 +86,7 @@ RCD_EXPORT int rcd_decoder_wgrad(const uint16_t* G, int ldg, const uint16_t* Zs,
   GemmProblem g{};
   g.mode = 2; g.A = G; g.lda = ldg; g.B = Zs; g.ldb = ldzs; g.M = n; g.N = H; g.K = rows;
   g.bn = pick_bn(H); g.splits = 1; g.n_fastest = 1;  // the n-tiles of one G^T tile run back to back (L2 reuse)
+  g.m_sub = 2;
   EpiParams e{};
   e.kind = EPI_F32; e.M = n; e.N = H; e.C = dW; e.ldc = lddw; e.split_stride = 0;
   if (engine == RCD_GEMM_TCGEN05) {
@@ -104,6 +105,8 @@ RCD_EXPORT int rcd_gemm_bf16(int mode, const uint16_t* A, int lda, const uint16_
   GemmProblem g{};
   g.mode = mode; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = M; g.N = N; g.K = K;
   g.bn = (mode == 0) ? kTileNMax : pick_bn(N); g.splits = 1; g.n_fastest = 1;
+  g.m_sub = (engine >> 8) & 3;   // tests: engine | (2 << 8) selects the 256-row CTA tile of the tcgen05 engine
+  engine &= 0xff;
   EpiParams e{};
   e.kind = EPI_F32; e.M = M; e.N = N; e.C = C; e.ldc = ldc; e.split_stride = 0;
   return launch(g, e, engine, (cudaStream_t)stream);

@@ -28,6 +28,7 @@ struct GemmProblem {
   int bn;        // n-tile width (multiple of 16, <= 256)
   int splits;    // k-splits (each non-empty)
   int n_fastest; // tile order
+  int m_sub;     // tcgen05 engine: 128-row sub-tiles per CTA (2 = 256-row tiles sharing the B stage; 0/1 = one)
   int split_major; // 1: unit = split * tiles + tile — CTAs in flight work on the SAME k-range of different tiles, so
                    // the A/B k-slabs they stream are shared through L2 (split-K over a K that does not fit L2)
 };

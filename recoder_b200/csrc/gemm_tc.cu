@@ -25,23 +25,42 @@
 
 namespace rcd {
 
-constexpr int kStages = 4;
-constexpr int kAStageBytes = kTileM * kTileK * 2;     // 16 KB
+// MT = 128-row sub-tiles per CTA.  MT = 1: 128 x bn tile, accumulators double-buffered in TMEM (the epilogue of tile i
+// overlaps the MMAs of tile i+1), 4-stage ring.  MT = 2: 256 x bn tile as two M=128 MMAs that share the B stage — one
+// third less operand traffic per MMA (A 2x16 KB + B 32 KB per 2x512 MMA cycles instead of 16 + 32 KB per 512): the
+// GEMMs of this path run at the L2->SM return bandwidth (~48 B/clk/SM measured), not at the tensor pipe, so bytes per
+// MMA is what sets their speed.  The two accumulators fill all 512 TMEM columns (no double buffering: the epilogue is
+// exposed, which costs little for the long units of dgrad (split-K) and wgrad (K = batch rows)); 3-stage ring.
+constexpr int kASubBytes = kTileM * kTileK * 2;       // 16 KB per 128-row sub-tile
 constexpr int kBStageBytes = kTileNMax * kTileK * 2;  // 32 KB
-constexpr int kStageBytes = kAStageBytes + kBStageBytes;
 constexpr int kBarrierBytes = 256;
 constexpr int kSideWarps = 4;
 constexpr int kSideSmemBytes = 8 * kTileM * 4;  // [8 k-groups][128 columns] partial sums
-constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + kSideSmemBytes + 1024;  // + 1024 B alignment slack
 constexpr int kGemmThreads = 320;  // warps 0/1 TMA/MMA, 2-5 epilogue, 6-9 column-sum side product
+constexpr int kMaxStages = 4;
+
+template <int MT>
+struct TcCfg {
+  static constexpr int kStages = (MT == 1) ? 4 : 3;
+  static constexpr int kAStageBytes = MT * kASubBytes;
+  static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
+  static constexpr int kAccBufs = (MT == 1) ? 2 : 1;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + kSideSmemBytes + 1024;  // + alignment slack
+};
 
 constexpr int kTmemCols = 512;
 constexpr int kBoxBytes = 64 * 64 * 2;  // MN-major box
 
+template <int MT>
 static __global__ void __launch_bounds__(kGemmThreads, 1)
     k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmProblem g,
               EpiParams e, int m_tiles, int n_tiles, int kblocks, uint32_t idesc, int b_boxes,
               uint32_t stage_tx_bytes) {
+  constexpr int kStages = TcCfg<MT>::kStages;
+  constexpr int kAStageBytes = TcCfg<MT>::kAStageBytes;
+  constexpr int kStageBytes = TcCfg<MT>::kStageBytes;
+  constexpr int kAccBufs = TcCfg<MT>::kAccBufs;
+  constexpr int kRowsPerCta = MT * kTileM;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t tiles = (raw_addr + 1023u) & ~1023u;  // 128B-swizzle atoms need 1024 B alignment
@@ -65,7 +84,7 @@ static __global__ void __launch_bounds__(kGemmThreads, 1)
         mbar_init(full_bar(s), 1);
         mbar_init(empty_bar(s), do_colsum ? 1 + kSideWarps : 1);  // tcgen05.commit (+ one arrive per side warp)
       }
-      for (int a = 0; a < 2; ++a) {
+      for (int a = 0; a < kAccBufs; ++a) {
         mbar_init(tfull_bar(a), 1);
         mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
       }
@@ -91,17 +110,22 @@ static __global__ void __launch_bounds__(kGemmThreads, 1)
       uint32_t stage = 0, phase = 0;
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
         const UnitCoord u = decode_unit(unit, m_tiles, n_tiles, g.splits, kblocks, g.n_fastest, g.split_major);
-        const int m0 = u.mt * kTileM, n0 = u.nt * g.bn;
+        const int m0 = u.mt * kRowsPerCta, n0 = u.nt * g.bn;
         for (int kb = u.kb0; kb < u.kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, 0);
           mbar_arrive_expect_tx(full_bar(stage), stage_tx_bytes);
           const uint32_t a_dst = tiles + stage * kStageBytes, b_dst = a_dst + kAStageBytes;
           const int k = kb * kTileK;
-          if (a_mn) {
-            tma_load_2d(a_dst, &tmA, full_bar(stage), m0, k);
-            tma_load_2d(a_dst + kBoxBytes, &tmA, full_bar(stage), m0 + 64, k);
-          } else {
-            tma_load_2d(a_dst, &tmA, full_bar(stage), k, m0);
+#pragma unroll
+          for (int sub = 0; sub < MT; ++sub) {  // rows beyond M: TMA zero-fills the box
+            const uint32_t a_sub = a_dst + sub * kASubBytes;
+            const int ms = m0 + sub * kTileM;
+            if (a_mn) {
+              tma_load_2d(a_sub, &tmA, full_bar(stage), ms, k);
+              tma_load_2d(a_sub + kBoxBytes, &tmA, full_bar(stage), ms + 64, k);
+            } else {
+              tma_load_2d(a_sub, &tmA, full_bar(stage), k, ms);
+            }
           }
           if (b_mn) {
             for (int j = 0; j < b_boxes; ++j) tma_load_2d(b_dst + j * kBoxBytes, &tmB, full_bar(stage), n0 + 64 * j, k);
@@ -122,8 +146,8 @@ static __global__ void __launch_bounds__(kGemmThreads, 1)
       int it = 0;
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
         const UnitCoord u = decode_unit(unit, m_tiles, n_tiles, g.splits, kblocks, g.n_fastest, g.split_major);
-        const int acc = it & 1;
-        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        const int acc = it % kAccBufs;
+        const uint32_t acc_phase = (uint32_t)(it / kAccBufs) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kTileNMax);
@@ -133,11 +157,15 @@ static __global__ void __launch_bounds__(kGemmThreads, 1)
           const uint32_t a_addr = tiles + stage * kStageBytes, b_addr = a_addr + kAStageBytes;
 #pragma unroll
           for (int k = 0; k < kTileK / 16; ++k) {
-            const uint64_t adesc = a_mn ? make_smem_desc(a_addr + k * 2048, kBoxBytes, 1024)
-                                        : make_smem_desc(a_addr + k * 32, 16, 1024);
             const uint64_t bdesc = b_mn ? make_smem_desc(b_addr + k * 2048, kBoxBytes, 1024)
                                         : make_smem_desc(b_addr + k * 32, 16, 1024);
-            tc_mma_bf16(tmem_d, adesc, bdesc, idesc, (kb > u.kb0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int sub = 0; sub < MT; ++sub) {  // the sub-tiles share the B stage; accumulator `sub` at column sub*256
+              const uint32_t a_sub = a_addr + sub * kASubBytes;
+              const uint64_t adesc = a_mn ? make_smem_desc(a_sub + k * 2048, kBoxBytes, 1024)
+                                          : make_smem_desc(a_sub + k * 32, 16, 1024);
+              tc_mma_bf16(tmem_d + (uint32_t)(sub * kTileNMax), adesc, bdesc, idesc, (kb > u.kb0 || k > 0) ? 1u : 0u);
+            }
           }
           tc_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
           if (++stage == kStages) {
@@ -161,29 +189,34 @@ static __global__ void __launch_bounds__(kGemmThreads, 1)
       uint32_t stage = 0, phase = 0;
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
         const UnitCoord u = decode_unit(unit, m_tiles, n_tiles, g.splits, kblocks, g.n_fastest, g.split_major);
-        float acc[8];
+        float acc[MT][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int sub = 0; sub < MT; ++sub)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[sub][j] = 0.f;
         for (int kb = u.kb0; kb < u.kb1; ++kb) {
           mbar_wait(full_bar(stage), phase, 4);
           if (u.nt == 0) {
             const int kg0 = kb * kTileK + lane, kg1 = kg0 + 32;
             const float w_lo = (kg0 < g.K) ? (e.colw ? __ldg(e.colw + kg0) : 1.0f) : 0.f;
             const float w_hi = (kg1 < g.K) ? (e.colw ? __ldg(e.colw + kg1) : 1.0f) : 0.f;
-            const uint8_t* a_ptr = smem + stage * kStageBytes + box_off;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const uint32_t k = kgrp + 8u * (uint32_t)i;
-              const float w = __shfl_sync(0xffffffffu, (i < 4) ? w_lo : w_hi, (int)(k & 31u));
-              const uint4 v = *reinterpret_cast<const uint4*>(a_ptr + k * 128u + (((c & 7u) ^ (k & 7u)) << 4));
-              acc[0] = fmaf(w, bf16_lo(v.x), acc[0]);
-              acc[1] = fmaf(w, bf16_hi(v.x), acc[1]);
-              acc[2] = fmaf(w, bf16_lo(v.y), acc[2]);
-              acc[3] = fmaf(w, bf16_hi(v.y), acc[3]);
-              acc[4] = fmaf(w, bf16_lo(v.z), acc[4]);
-              acc[5] = fmaf(w, bf16_hi(v.z), acc[5]);
-              acc[6] = fmaf(w, bf16_lo(v.w), acc[6]);
-              acc[7] = fmaf(w, bf16_hi(v.w), acc[7]);
+            for (int sub = 0; sub < MT; ++sub) {
+              const uint8_t* a_ptr = smem + stage * kStageBytes + sub * kASubBytes + box_off;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint32_t k = kgrp + 8u * (uint32_t)i;
+                const float w = __shfl_sync(0xffffffffu, (i < 4) ? w_lo : w_hi, (int)(k & 31u));
+                const uint4 v = *reinterpret_cast<const uint4*>(a_ptr + k * 128u + (((c & 7u) ^ (k & 7u)) << 4));
+                acc[sub][0] = fmaf(w, bf16_lo(v.x), acc[sub][0]);
+                acc[sub][1] = fmaf(w, bf16_hi(v.x), acc[sub][1]);
+                acc[sub][2] = fmaf(w, bf16_lo(v.y), acc[sub][2]);
+                acc[sub][3] = fmaf(w, bf16_hi(v.y), acc[sub][3]);
+                acc[sub][4] = fmaf(w, bf16_lo(v.z), acc[sub][4]);
+                acc[sub][5] = fmaf(w, bf16_hi(v.z), acc[sub][5]);
+                acc[sub][6] = fmaf(w, bf16_lo(v.w), acc[sub][6]);
+                acc[sub][7] = fmaf(w, bf16_hi(v.w), acc[sub][7]);
+              }
             }
           }
           __syncwarp();
@@ -195,14 +228,17 @@ static __global__ void __launch_bounds__(kGemmThreads, 1)
         }
         if (u.nt == 0) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) side[kgrp * kTileM + c * 8 + j] = acc[j];
-          named_bar_sync(2, kSideWarps * 32);
-          float sum = 0.f;
+          for (int sub = 0; sub < MT; ++sub) {
 #pragma unroll
-          for (int q2 = 0; q2 < 8; ++q2) sum += side[q2 * kTileM + t];  // fixed order
-          const int m = u.mt * kTileM + t;
-          if (m < g.M) e.colsum[m] = sum;
-          named_bar_sync(2, kSideWarps * 32);
+            for (int j = 0; j < 8; ++j) side[kgrp * kTileM + c * 8 + j] = acc[sub][j];
+            named_bar_sync(2, kSideWarps * 32);
+            float sum = 0.f;
+#pragma unroll
+            for (int q2 = 0; q2 < 8; ++q2) sum += side[q2 * kTileM + t];  // fixed order
+            const int m = u.mt * kRowsPerCta + sub * kTileM + t;
+            if (m < g.M) e.colsum[m] = sum;
+            named_bar_sync(2, kSideWarps * 32);
+          }
         }
       }
     }
@@ -212,20 +248,23 @@ static __global__ void __launch_bounds__(kGemmThreads, 1)
     int it = 0;
     for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
       const UnitCoord u = decode_unit(unit, m_tiles, n_tiles, g.splits, kblocks, g.n_fastest, g.split_major);
-      const int acc = it & 1;
-      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int acc = it % kAccBufs;
+      const uint32_t acc_phase = (uint32_t)(it / kAccBufs) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase, 3);
       tc_fence_after();
-      const int row = u.mt * kTileM + q * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTileNMax);
-      RowEpilogue epi;
-      epi.begin();
-      for (int cb = 0; cb < g.bn; cb += 32) {
-        float v[32];
-        tc_ld_32x32(taddr + (uint32_t)cb, v);
-        epi.chunk32(e, row, u.nt * g.bn + cb, u.split, v);
+#pragma unroll 1
+      for (int sub = 0; sub < MT; ++sub) {
+        const int row = u.mt * kRowsPerCta + sub * kTileM + q * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc + sub) * kTileNMax);
+        RowEpilogue epi;
+        epi.begin();
+        for (int cb = 0; cb < g.bn; cb += 32) {
+          float v[32];
+          tc_ld_32x32(taddr + (uint32_t)cb, v);
+          epi.chunk32(e, row, u.nt * g.bn + cb, u.split, v);
+        }
+        epi.end(e, row, u.nt);
       }
-      epi.end(e, row, u.nt);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -290,7 +329,10 @@ int gemm_tc_launch(const GemmProblem& g, const EpiParams& e, cudaStream_t st) {
     rcd_set_error("gemm_tc: bad n-tile %d", g.bn);
     return RCD_ERR_INVALID;
   }
-  const int m_tiles = rcd_div_up(g.M, kTileM), n_tiles = rcd_div_up(g.N, g.bn);
+  // 256-row CTA tiles (two sub-tiles sharing the B stage) whenever the epilogue is the plain fp32 store and there
+  // are at least two sub-tiles of rows; the decoder-logits epilogue keeps its per-(n-tile,row) statistics layout.
+  const int mt_sub = (g.m_sub == 2 && e.kind == EPI_F32 && g.M > kTileM) ? 2 : 1;
+  const int m_tiles = rcd_div_up(g.M, kTileM * mt_sub), n_tiles = rcd_div_up(g.N, g.bn);
   const int kblocks = rcd_div_up(g.K, kTileK);
   if (n_tiles > 1 && g.bn % 32 != 0) {
     rcd_set_error("gemm_tc: n-tile %d must be a multiple of 32 when N spans several tiles", g.bn);
@@ -310,20 +352,26 @@ int gemm_tc_launch(const GemmProblem& g, const EpiParams& e, cudaStream_t st) {
   else rc = encode_map(&tmB, g.B, g.K, g.N, g.ldb, kTileK, kTileNMax);
   if (rc != RCD_OK) return rc;
   const int b_boxes = rcd_div_up(g.bn, 64);
-  const uint32_t tx = (uint32_t)kAStageBytes + (b_mn ? (uint32_t)(b_boxes * kBoxBytes) : (uint32_t)kBStageBytes);
+  const uint32_t tx = (uint32_t)(mt_sub * kASubBytes) + (b_mn ? (uint32_t)(b_boxes * kBoxBytes) : (uint32_t)kBStageBytes);
   // instruction descriptor: D=f32 [4,6)=1 | A=bf16 [7,10)=1 | B=bf16 [10,13)=1 | a_major [15] | b_major [16] |
   // N>>3 [17,23) | M>>4 [24,29)
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
                          ((uint32_t)(g.bn >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
   static bool attr_set = false;
   if (!attr_set) {
-    RCD_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    RCD_CUDA(cudaFuncSetAttribute(k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<1>::kSmemBytes));
+    RCD_CUDA(cudaFuncSetAttribute(k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<2>::kSmemBytes));
     attr_set = true;
   }
   const int units = m_tiles * n_tiles * g.splits;
   const int sms = rcd_num_sms();
   const int grid = units < sms ? units : sms;
-  k_gemm_tc<<<grid, kGemmThreads, kSmemBytes, st>>>(tmA, tmB, g, e, m_tiles, n_tiles, kblocks, idesc, b_boxes, tx);
+  if (mt_sub == 2)
+    k_gemm_tc<2><<<grid, kGemmThreads, TcCfg<2>::kSmemBytes, st>>>(tmA, tmB, g, e, m_tiles, n_tiles, kblocks, idesc,
+                                                                  b_boxes, tx);
+  else
+    k_gemm_tc<1><<<grid, kGemmThreads, TcCfg<1>::kSmemBytes, st>>>(tmA, tmB, g, e, m_tiles, n_tiles, kblocks, idesc,
+                                                                  b_boxes, tx);
   RCD_LAUNCH_CHECK();
   return RCD_OK;
 }

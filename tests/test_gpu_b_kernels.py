@@ -57,6 +57,16 @@ def test_gemm_tcgen05_matches_fp32(mode, M, N, K):
   torch.testing.assert_close(C, ref, rtol=1e-4, atol=1e-3 * (K ** 0.5))
 
 
+@pytest.mark.parametrize('mode', [0, 1, 2])
+@pytest.mark.parametrize('M,N,K', SHAPES + [(2048, 512, 4096), (3001, 200, 333)])
+def test_gemm_tcgen05_256row_tiles_match_fp32(mode, M, N, K):
+  """256-row CTA tiles (two M=128 sub-tiles sharing the B stage, accumulators filling all 512 TMEM columns)."""
+  A, B, ref = _operands(mode, M, N, K, seed=mode * 100 + M)
+  C = _gemm(mode, A, B, M, N, K, _native.GEMM_TCGEN05 | (2 << 8))
+  assert not torch.isnan(C).any()
+  torch.testing.assert_close(C, ref, rtol=1e-4, atol=1e-3 * (K ** 0.5))
+
+
 def test_adam_kernel_matches_torch():
   torch.manual_seed(0)
   I, H, n = 300, 32, 57
