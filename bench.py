@@ -409,7 +409,8 @@ def b200_arm(args, w):
         ach, peak, unit = per_launch / sec / 1e12, peaks['tensor_sustained'], 'TFLOP/s'
       else:
         ach, peak, unit = per_launch / sec / 1e9, peaks['hbm'], 'GB/s'
-      traffic, traffic_src = ncu_traffic(dom)
+      # the committed ncu summaries are captures of the default workload (C3, 2048 users per GPU)
+      traffic, traffic_src = ncu_traffic(dom) if (args.config == 'c3' and B == WORKLOADS['c3']['batch']) else (None, None)
       if traffic is not None and dom == 'rcd_adam_step':
         # the ncu figure is the mean over the table launches; a step also has the (KB-sized) bias launches, and
         # `achieved` averages over all `lps` launches of a step — put both on the same per-launch footing

@@ -53,7 +53,7 @@ def main():
   torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
   dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ['LOCAL_RANK'])))
   from recoder_b200.synth import synthetic_csr, to_scipy
-  U, I, nnz, H, B, steps = 4096, 3000, 40, 64, 256, 4
+  U, I, nnz, H, B, steps = 8192, 3000, 40, 64, 128, 4
   indptr, indices, data = synthetic_csr(U, I, nnz, seed=11)
   matrix = to_scipy(indptr, indices, data, I)
   solo = dist.new_group([0])

@@ -24,7 +24,7 @@ def test_dp_exchange_matches_single_process():
   n = torch.cuda.device_count()
   if n < 2:
     pytest.skip('needs at least 2 GPUs')
-  world = 2
+  world = min(n, int(os.environ.get('RCD_TEST_WORLD', '2')))   # RCD_TEST_WORLD=4|8 on a bigger box (multicast path)
   cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
          '--master-addr', '127.0.0.1', '--master-port', str(_free_port()), os.path.join(ROOT, 'tests', 'dp_worker.py')]
   r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)

@@ -3,7 +3,7 @@
 # DP_MODES="p2p nccl", DP_ENVS="RCD_OVERLAP=1;RCD_OVERLAP=0" (semicolon-separated env settings), SKIP_TEST=1
 mkdir -p gpurun_out
 if [ "$SKIP_TEST" != "1" ]; then
-  echo "== dp test"; timeout 600 python -m pytest tests/test_gpu_d_multigpu.py -q -m gpu -x -s > gpurun_out/t_dp.log 2>&1; echo "rc=$?"; grep -E "losses|DP_|passed|failed|Error|differs" gpurun_out/t_dp.log | tail -30
+  echo "== dp test"; RCD_TEST_WORLD=${DP_N:-2} timeout 600 python -m pytest tests/test_gpu_d_multigpu.py -q -m gpu -x -s > gpurun_out/t_dp.log 2>&1; echo "rc=$?"; grep -E "losses|DP_|passed|failed|Error|differs" gpurun_out/t_dp.log | tail -30
 fi
 N=${DP_N:-2}
 IFS=';' read -ra ENVS <<< "${DP_ENVS:-RCD_OVERLAP=1}"
