@@ -160,7 +160,9 @@ int rcd_decoder_fwd_loss(const uint16_t* Zb, int ldzb, const uint16_t* Wg, int l
  *     rcd_loss_finish : reduces stat, adds the loss of the slice (divided by B) to loss_acc (double), writes
  *                       row_scale[r] = alpha[r] (1 for MSE/LOGISTIC) and, when Zs != NULL, Zs = bf16(alpha*Z)
  *                       [rows, ldzs] — the operand of the decoder weight gradient.  bad_flag |= 1 when a softmax
- *                       row sum is not positive/finite, |= 2 when the loss is not finite.
+ *                       row sum is not positive/finite, |= 2 when the loss is not finite.  local_targets != 0
+ *                       (item-parallel mode): stat is the row sum over ALL item shards, the stored targets are this
+ *                       rank's shard only, and the loss added is this rank's share.
  *     rcd_sparse_dgrad: out[r,0:H] = sum_p corr[p] * W[raw_items[p],:]  (fp32 master table; out fp32 [rows, ldp])
  *     rcd_csc_rows_accumulate: out[c,0:H] += sum_{e in column c} coef[csc_src[e]] * M[csc_row[e],:] and
  *                       db[c] += sum_e coef[csc_src[e]]  (csc_src == NULL: coef is already in CSC order)
@@ -171,7 +173,7 @@ int rcd_sddmm(const uint16_t* Zb, int ldzb, const uint16_t* Wg, int ldw, const f
 int rcd_loss_finish(const float* stat, int stat_ld, int stat_cols, int rows, int loss, float confidence, float inv_b,
                     const float* row_ref, const float* row_sum, const int32_t* row_ptr, const float* vals,
                     const float* o_nnz, int row0, float* row_scale, const float* Z, int H, uint16_t* Zs, int ldzs,
-                    double* loss_acc, int32_t* bad_flag, void* stream);
+                    double* loss_acc, int32_t* bad_flag, int local_targets, void* stream);
 int rcd_sparse_dgrad(const float* W, int H, const int32_t* row_ptr, const int32_t* raw_items, const float* corr,
                      int row0, int rows, float* out, int ldp, void* stream);
 int rcd_csc_rows_accumulate(const float* M, int H, const int32_t* csc_ptr, const int32_t* csc_row,
@@ -288,6 +290,11 @@ int rcd_dropout(const float* x, long long count, float p, unsigned long long see
 int rcd_act_grad(const float* dy, const float* y, long long count, int act, float* dpre, void* stream);
 int rcd_colsum(const float* x, int rows, int H, int ld, float* out, void* stream);
 int rcd_f32_to_bf16_rows(const float* x, int rows, int H, uint16_t* out, int ld, void* stream);
+/* item-parallel mode helpers: Z = act(x + bias) (fp32 [rows,H] + optional bf16 copy [rows, ld]) after the all-reduce
+ * of the encoder partial sums; out[r] = sum_c x[r, c] */
+int rcd_bias_act(const float* x, const float* bias, int rows, int H, int act, float* Z, uint16_t* Zb, int ld,
+                 void* stream);
+int rcd_rowsum(const float* x, int rows, int cols, int ld, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K11 recommendation — replaces the tail of Recoder.recommend (recoder/model.py:525-544):

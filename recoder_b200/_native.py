@@ -44,7 +44,7 @@ _SIGNATURES = {
   'rcd_sddmm': (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P,
                         _P]),
   'rcd_loss_finish': (c_int, [_P, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P, c_int, _P, _P,
-                              c_int, _P, c_int, _P, _P, _P]),
+                              c_int, _P, c_int, _P, _P, c_int, _P]),
   'rcd_sparse_dgrad': (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, _P, c_int, _P]),
   'rcd_csc_rows_accumulate': (c_int, [_P, c_int, _P, _P, _P, _P, c_int, _P, _P, _P]),
   'rcd_decoder_dgrad_splits': (c_int, [c_int, c_int, c_int]),
@@ -75,6 +75,8 @@ _SIGNATURES = {
   'rcd_act_grad': (c_int, [_P, _P, c_longlong, c_int, _P, _P]),
   'rcd_colsum': (c_int, [_P, c_int, c_int, c_int, _P, _P]),
   'rcd_f32_to_bf16_rows': (c_int, [_P, c_int, c_int, _P, c_int, _P]),
+  'rcd_bias_act': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, _P]),
+  'rcd_rowsum': (c_int, [_P, c_int, c_int, c_int, _P, _P]),
   'rcd_mask_seen': (c_int, [_P, _P, c_int, c_int, _P, c_longlong, _P]),
   'rcd_topk_rows': (c_int, [_P, c_longlong, c_int, c_int, c_int, _P, _P, _P]),
   'rcd_sumsq': (c_int, [_P, c_longlong, c_int, c_int, _P, _P]),

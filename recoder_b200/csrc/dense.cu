@@ -153,6 +153,33 @@ static __global__ void __launch_bounds__(256)
   }
 }
 
+// z = act(x + bias[h]) -> fp32 Z and (optional) bf16 copy [rows, ld] zero padded: finishes the encoder after the
+// partial sums of the item shards have been all-reduced (item-parallel mode)
+static __global__ void k_bias_act(const float* __restrict__ x, const float* __restrict__ bias, int rows, int H, int act,
+                                  float* __restrict__ Z, uint16_t* __restrict__ Zb, int ld) {
+  const long long total = (long long)rows * ld;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ld), h = (int)(i % ld);
+    float z = 0.f;
+    if (h < H) {
+      z = act_apply(x[(size_t)r * H + h] + bias[h], act);
+      Z[(size_t)r * H + h] = z;
+    }
+    if (Zb) reinterpret_cast<__nv_bfloat16*>(Zb)[i] = __float2bfloat16_rn(z);
+  }
+}
+
+// out[r] = sum_c x[r, c] (one warp per row, fixed order)
+static __global__ void k_rowsum(const float* __restrict__ x, int rows, int cols, int ld, float* __restrict__ out) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += x[(size_t)r * ld + c];
+  s = warp_sum(s);
+  if (lane == 0) out[r] = s;
+}
+
 static inline int ew_grid(long long count) {
   long long b = (count + 255) / 256;
   long long cap = (long long)rcd_num_sms() * 8;
@@ -202,6 +229,22 @@ RCD_EXPORT int rcd_colsum(const float* x, int rows, int H, int ld, float* out, v
 RCD_EXPORT int rcd_f32_to_bf16_rows(const float* x, int rows, int H, uint16_t* out, int ld, void* stream) {
   RCD_CHECK_ARG(x && out && rows > 0 && H > 0 && ld >= H, "bad arguments");
   k_f32_to_bf16_rows<<<ew_grid((long long)rows * ld), 256, 0, (cudaStream_t)stream>>>(x, rows, H, out, ld);
+  RCD_LAUNCH_CHECK();
+  return RCD_OK;
+}
+
+RCD_EXPORT int rcd_bias_act(const float* x, const float* bias, int rows, int H, int act, float* Z, uint16_t* Zb, int ld,
+                            void* stream) {
+  RCD_CHECK_ARG(x && bias && Z && rows > 0 && H > 0 && (!Zb || ld >= H), "bad arguments");
+  const int ldd = Zb ? ld : H;
+  k_bias_act<<<ew_grid((long long)rows * ldd), 256, 0, (cudaStream_t)stream>>>(x, bias, rows, H, act, Z, Zb, ldd);
+  RCD_LAUNCH_CHECK();
+  return RCD_OK;
+}
+
+RCD_EXPORT int rcd_rowsum(const float* x, int rows, int cols, int ld, float* out, void* stream) {
+  RCD_CHECK_ARG(x && out && rows > 0 && cols > 0 && ld >= cols, "bad arguments");
+  k_rowsum<<<rcd_div_up(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, out);
   RCD_LAUNCH_CHECK();
   return RCD_OK;
 }

@@ -101,7 +101,7 @@ static __global__ void __launch_bounds__(kSpWarps * 32)
                   const int32_t* __restrict__ row_ptr, const float* __restrict__ vals,
                   const float* __restrict__ o_nnz, int row0, float* __restrict__ row_scale,
                   const float* __restrict__ Z, int H, uint16_t* __restrict__ Zs, int ldzs,
-                  double* __restrict__ loss_acc, int32_t* __restrict__ bad) {
+                  double* __restrict__ loss_acc, int32_t* __restrict__ bad, int local_targets) {
   __shared__ double s_part[kSpWarps];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * kSpWarps + w;
@@ -112,9 +112,10 @@ static __global__ void __launch_bounds__(kSpWarps * 32)
     s = warp_sum(s);  // fixed order: deterministic
     const int base = row_ptr[row0];
     const int ps = row_ptr[row0 + r], pe = row_ptr[row0 + r + 1];
-    float sp = 0.f;
+    float sp = 0.f, st = 0.f;
     for (int p = ps + lane; p < pe; p += 32) {
       const float o = o_nnz[p - base], t = vals[p];
+      st += t;
       if (loss == RCD_LOSS_MSE) {
         const float wgt = 1.0f + (t > 0.f ? conf : 0.f);  // losses.py:44
         sp += wgt * (o - t) * (o - t) - o * o;
@@ -123,12 +124,15 @@ static __global__ void __launch_bounds__(kSpWarps * 32)
       }
     }
     sp = warp_sum(sp);
+    st = warp_sum(st);
     float alpha = 1.0f, lrow;
     if (loss == RCD_LOSS_NLL) {
       const float S = row_sum[row0 + r];
       const float lse = row_ref[r] + logf(s);
       alpha = (S != 0.f) ? S * inv_b / s : 0.f;
-      lrow = S * lse + sp;
+      // item-parallel mode: `stat` holds the all-reduced row sum, the stored targets are this rank's item shard —
+      // the rank's loss share is (sum of ITS targets) * lse + sp, so that the shares add up to S * lse + sum sp
+      lrow = (local_targets ? st : S) * lse + sp;
       if (!(s > 0.f) || !isfinite(s)) {
         if (lane == 0) atomicOr(bad, 1);
       }
@@ -188,14 +192,15 @@ RCD_EXPORT int rcd_sddmm(const uint16_t* Zb, int ldzb, const uint16_t* Wg, int l
 RCD_EXPORT int rcd_loss_finish(const float* stat, int stat_ld, int stat_cols, int rows, int loss, float confidence,
                                float inv_b, const float* row_ref, const float* row_sum, const int32_t* row_ptr,
                                const float* vals, const float* o_nnz, int row0, float* row_scale, const float* Z, int H,
-                               uint16_t* Zs, int ldzs, double* loss_acc, int32_t* bad_flag, void* stream) {
+                               uint16_t* Zs, int ldzs, double* loss_acc, int32_t* bad_flag, int local_targets,
+                               void* stream) {
   RCD_CHECK_ARG(stat && row_ptr && vals && o_nnz && loss_acc && bad_flag, "null pointer");
   RCD_CHECK_ARG(rows > 0 && stat_cols > 0 && stat_ld >= stat_cols && row0 >= 0, "bad shape");
   RCD_CHECK_ARG(loss != RCD_LOSS_NLL || (row_ref && row_sum && row_scale), "NLL needs row_ref, row_sum and row_scale");
   RCD_CHECK_ARG(!Zs || (Z && ldzs >= H), "Zs needs Z and ldzs >= H");
   k_loss_finish<<<rcd_div_up(rows, kSpWarps), kSpWarps * 32, 0, (cudaStream_t)stream>>>(
       stat, stat_ld, stat_cols, rows, loss, confidence, inv_b, row_ref, row_sum, row_ptr, vals, o_nnz, row0, row_scale,
-      Z, H, Zs, ldzs, loss_acc, bad_flag);
+      Z, H, Zs, ldzs, loss_acc, bad_flag, local_targets);
   RCD_LAUNCH_CHECK();
   return RCD_OK;
 }

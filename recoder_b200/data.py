@@ -188,6 +188,21 @@ class RecommendationDataset:
       self._device_target_csr = cls(self.target_interactions_matrix)
     return self._device_target_csr
 
+  def item_shard_csr(self, rank, world):
+    """Item-parallel mode (itempar.py): this rank's column shard of the matrix in HBM (or host-staged), carrying the
+    whole-row constants (1/||x_u||, sum_j x_uj) as device vectors indexed by user."""
+    key = (rank, world)
+    if getattr(self, '_item_shard_key', None) != key:
+      from .itempar import shard_matrix_by_items
+      local, inv_norm, row_sum = shard_matrix_by_items(self.interactions_matrix.tocsr(), rank, world)
+      cls = DeviceCSR if self.device_resident else HostStagedCSR
+      csr = cls(local)
+      csr.inv_norm_all = torch.from_numpy(inv_norm).to(csr.device)
+      csr.row_sum_all = torch.from_numpy(row_sum).to(csr.device)
+      self._item_shard = csr
+      self._item_shard_key = key
+    return self._item_shard
+
   def __getitem__(self, index):
     assert _issequence(index) or _isintlike(index)  # data.py:51
     users = np.array(index).reshape(-1,)
@@ -284,7 +299,8 @@ class PoolRing:
     return t[:numel]
 
 
-def collate_pool_launch(csr, users, negative_sampling: bool, stream=None, after=(), ring=None) -> PoolBatch:
+def collate_pool_launch(csr, users, negative_sampling: bool, stream=None, after=(), ring=None,
+                        row_constants=None) -> PoolBatch:
   """Enqueues K1 on the rows `users` of `csr` (DeviceCSR, or HostStagedCSR: staged over PCIe first) and an
   asynchronous read-back of the two counts (n, nnz) every downstream shape depends on.  The returned PoolBatch is
   usable after `collate_pool_finish`.  Launching the collate of pool i+1 before the training step of pool i is
@@ -293,12 +309,17 @@ def collate_pool_launch(csr, users, negative_sampling: bool, stream=None, after=
   `stream`: run the collate kernels on this (auxiliary) CUDA stream so that they overlap the training step the
   caller enqueues next on the current stream; the outputs are allocated on the CURRENT stream's pool and the auxiliary
   stream first waits for the current stream and for every stream in `after`, so recycled memory is never written
-  while an earlier kernel still reads it.  `collate_pool_finish` makes the current stream wait for the collate."""
+  while an earlier kernel still reads it.  `collate_pool_finish` makes the current stream wait for the collate.
+
+  `row_constants` = (inv_norm_all, row_sum_all), device vectors indexed by USER id: item-parallel mode, where `csr`
+  holds only this rank's columns and the row statistics of the collate must be replaced by whole-row values."""
   users = np.ascontiguousarray(np.asarray(users).reshape(-1), dtype=np.int64)
   assert users.size > 0
   assert users.min() >= 0 and users.max() < csr.shape[0], 'user index out of range'
   dev = csr.device
   P, I = int(users.size), int(csr.shape[1])
+  if row_constants is None and hasattr(csr, 'inv_norm_all'):
+    row_constants = (csr.inv_norm_all, csr.row_sum_all)
   slot = ring.next_slot() if ring is not None else None
 
   def buf(name, numel, dtype):
@@ -363,6 +384,10 @@ def collate_pool_launch(csr, users, negative_sampling: bool, stream=None, after=
                  _native.ptr(pb.raw_items), _native.ptr(pb.cols), _native.ptr(pb.vals), _native.ptr(pb.row_inv_norm),
                  _native.ptr(pb.row_sum), _native.ptr(pb.pos), _native.ptr(pb.items_buf), _native.ptr(pb.counts),
                  _native.ptr(scratch), sbytes)
+    if row_constants is not None:
+      _native.call('rcd_gather_vec', _native.ptr(row_constants[0]), _native.ptr(users_dev), P,
+                   _native.ptr(pb.row_inv_norm))
+      _native.call('rcd_gather_vec', _native.ptr(row_constants[1]), _native.ptr(users_dev), P, _native.ptr(pb.row_sum))
     counts_host.copy_(pb.counts, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()

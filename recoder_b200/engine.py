@@ -233,7 +233,7 @@ class TrainEngine:
   LOSS_RING = 4096
 
   def __init__(self, kind, params, loss, confidence, activation, optimizer: Optimizer, gemm_engine=None,
-               process_group=None, tied=False, p2p=None):
+               process_group=None, tied=False, p2p=None, item_parallel=None):
     _native.require_cuda()
     self.kind = kind
     self.params = params          # dict of role -> (name, tensor)
@@ -245,6 +245,7 @@ class TrainEngine:
     self.pg = process_group
     self.tied = tied
     self.p2p = p2p                # p2p.P2PContext: exchange through peer memory instead of an NCCL all-reduce
+    self.ip = item_parallel       # itempar.ItemParallel: every rank sees all rows, the item axis is sharded
     self._slab_shared = None
     import os
     self.overlap = os.environ.get('RCD_OVERLAP', '1') != '0'
@@ -341,7 +342,9 @@ class TrainEngine:
     is averaged over (model.py:483-484); defaults to `rows`."""
     inv_b = 1.0 / float(global_rows or rows)
     loss_slot = self._loss_slot()
-    if self.kind == 'ae':
+    if self.ip is not None:
+      self._ae_step_items(pool, row0, rows, inv_b, loss_slot, train=True)
+    elif self.kind == 'ae':
       self._ae_step(pool, target_pool or pool, row0, rows, inv_b, loss_slot, train=True)
     else:
       self._mf_step(pool, target_pool or pool, row0, rows, inv_b, loss_slot, train=True)
@@ -352,7 +355,9 @@ class TrainEngine:
     slot = self.buf.get('eval_loss', 1, torch.float64)
     self.join()
     slot.zero_()
-    if self.kind == 'ae':
+    if self.ip is not None:
+      self._ae_step_items(pool, row0, rows, 1.0 / rows, slot, train=False)
+    elif self.kind == 'ae':
       self._ae_step(pool, target_pool or pool, row0, rows, 1.0 / rows, slot, train=False)
     else:
       self._mf_step(pool, target_pool or pool, row0, rows, 1.0 / rows, slot, train=False)
@@ -409,7 +414,7 @@ class TrainEngine:
     Zs = b.get('Zs', rows * ldh, torch.bfloat16) if (nll and train) else None
     call('rcd_loss_finish', ptr(stat), stat_cols, stat_cols, rows, self.loss_id, self.confidence, inv_b,
          ptr(row_ref), ptr(tpool.row_sum), ptr(tpool.row_ptr), ptr(tpool.vals), ptr(o_nnz), row0, ptr(alpha),
-         ptr(Zf32), H, ptr(Zs), ldh, ptr(loss_slot), ptr(self.bad_flag))
+         ptr(Zf32), H, ptr(Zs), ldh, ptr(loss_slot), ptr(self.bad_flag), 0)
     return G, ldn, corr, alpha, (Zs if Zs is not None else Zb)
 
   def _sparse_dgrad(self, corr, W_master, tpool, row0, rows, n, H):
@@ -774,6 +779,109 @@ class TrainEngine:
     self.opt.step_param(en_name, dWe, H, pos=pool.pos, ids=pool.items_buf, n_ids=n_in)
     self.opt.step_param(enb_name, dbe, 1)
     self._step_inner(inner_grads, inner)
+
+  # ------------------------------------------------------------------------------------------------------
+  def _ae_step_items(self, pool, row0, rows, inv_b, loss_slot, train):
+    """Item-parallel autoencoder step (itempar.py): `pool` is the collate of the GLOBAL batch over this rank's item
+    shard of the matrix (local item ids; row_inv_norm / row_sum hold the whole-row constants), every parameter tensor
+    here is the local shard.  Four collectives: sum of the encoder partials [rows, H], max of the softmax reference
+    [rows], sum of the softmax row sums [rows] (NLL only), sum of dL/dZ [rows, H] (+ the loss in its tail)."""
+    import torch.distributed as dist
+    b = self.buf
+    pg = self.ip.pg
+    (en_name, We), (enb_name, be) = self.params['en_w'], self.params['en_b']
+    (de_name, Wd), (deb_name, bd) = self.params['de_w'], self.params['de_b']
+    H = We.shape[1]
+    ldh = _round_up(H, 8)
+    n = pool.n
+    none = _native.ACT_IDS['none']
+    nll = self.loss_id == _native.LOSS_IDS['logloss']
+    csc = None
+    if train:
+      with self._aux_stream():
+        csc = self._slice_csc(pool, row0, rows, n, 't_')
+      self._aux_done()
+
+    Wg = b.get('Wg', n * ldh, torch.bfloat16)
+    bg = b.get('bias_g', n, torch.float32)
+    self._wait_ready('de')
+    call('rcd_gather_rows', ptr(Wd), H, ptr(pool.items), n, 0, ptr(Wg), ldh, None)
+    call('rcd_gather_vec', ptr(bd), ptr(pool.items), n, ptr(bg))
+
+    # encoder: partial sums over this rank's items -> all-reduce -> bias + activation
+    Zp = b.get('Zp', rows * H, torch.float32)
+    zero_bias = b.get('zero_bias', H, torch.float32)
+    if not getattr(self, '_zero_bias_init', False):
+      zero_bias.zero_()
+      self._zero_bias_init = True
+    self._wait_ready('en')
+    call('rcd_ae_encoder_fwd', ptr(We), H, ptr(zero_bias), ptr(pool.row_ptr), ptr(pool.raw_items), ptr(pool.vals),
+         ptr(pool.row_inv_norm), row0, rows, none, ptr(Zp), None, ldh)
+    dist.all_reduce(Zp, op=dist.ReduceOp.SUM, group=pg)
+    Z = b.get('Z', rows * H, torch.float32)
+    Zb = b.get('Zb', rows * ldh, torch.bfloat16)
+    call('rcd_bias_act', ptr(Zp), ptr(be), rows, H, self.act, ptr(Z), ptr(Zb), ldh)
+
+    # decoder over the local items, loss with the softmax statistics combined across the shards
+    ldn = _round_up(n, 8)
+    nnz = max(int(pool.row_ptr_host[row0 + rows] - pool.row_ptr_host[row0]), 1)
+    G = b.get('G', rows * ldn, torch.bfloat16)
+    o_nnz = b.get('o_nnz', nnz, torch.float32)
+    corr = b.get('corr', nnz, torch.float32)
+    row_ref = b.get('row_ref', rows, torch.float32) if nll else None
+    call('rcd_sddmm', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bg), H, ptr(pool.row_ptr), ptr(pool.cols), ptr(pool.vals), row0,
+         rows, self.loss_id, self.confidence, inv_b, ptr(o_nnz), ptr(corr), ptr(row_ref))
+    if nll:
+      dist.all_reduce(row_ref, op=dist.ReduceOp.MAX, group=pg)
+    stat_cols = self.lib.rcd_decoder_stat_cols(n)
+    stat = b.get('stat', rows * stat_cols, torch.float32)
+    call('rcd_decoder_fwd_loss', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bg), rows, n, H, self.loss_id, inv_b, ptr(row_ref),
+         ptr(G), ldn, ptr(stat), stat_cols)
+    alpha = b.get('alpha', rows, torch.float32) if nll else None
+    Zs = b.get('Zs', rows * ldh, torch.bfloat16) if (nll and train) else None
+    if nll:
+      ssum = b.get('stat_sum', rows, torch.float32)
+      call('rcd_rowsum', ptr(stat), rows, stat_cols, stat_cols, ptr(ssum))
+      dist.all_reduce(ssum, op=dist.ReduceOp.SUM, group=pg)
+      stat, stat_ld, stat_n = ssum, 1, 1
+    else:
+      stat_ld = stat_n = stat_cols
+    call('rcd_loss_finish', ptr(stat), stat_ld, stat_n, rows, self.loss_id, self.confidence, inv_b, ptr(row_ref),
+         ptr(pool.row_sum), ptr(pool.row_ptr), ptr(pool.vals), ptr(o_nnz), row0, ptr(alpha), ptr(Z), H, ptr(Zs), ldh,
+         ptr(loss_slot), ptr(self.bad_flag), 1)
+    if not train:
+      dist.all_reduce(loss_slot, op=dist.ReduceOp.SUM, group=pg)
+      return
+    Zs = Zs if Zs is not None else Zb
+
+    # backward: local dW_d, then its update on the side stream underneath the dgrad GEMM / all-reduce / encoder backward
+    grads = b.get('ip_grads', 2 * n * H + _round_up(n, 4) + _round_up(H, 4), torch.float32)
+    dWe, dWd = grads[0:n * H], grads[n * H:2 * n * H]
+    dbd = grads[2 * n * H:2 * n * H + n]
+    dbe = grads[2 * n * H + _round_up(n, 4):2 * n * H + _round_up(n, 4) + H]
+    partials, splits = self._sparse_dgrad(corr, Wd, pool, row0, rows, n, H)
+    self._wait_ready('csc')
+    self._wgrad(G, ldn, Zs, ldh, Z, csc, corr, alpha, rows, n, H, dWd, dbd)
+    self.last = {'n': n, 'n_in': n, 'dWe': dWe.view(n, H), 'dWd': dWd.view(n, H), 'dbd': dbd, 'dbe': dbe}
+    with self._update_stream():
+      self._keep_for_side(pool)
+      self.opt.step_param(de_name, dWd, H, pos=pool.pos, ids=pool.items_buf, n_ids=n)
+      self.opt.step_param(deb_name, dbd, 1, pos=pool.pos)
+      self._mark_ready('de')
+
+    dZ = b.get('dZp', rows * H + 4, torch.float32)
+    self._dgrad(G, ldn, alpha, Wg, ldh, partials, splits, rows, n, H, Z, none, dZ, None)
+    self._stash_loss(dZ, loss_slot)            # the loss shares ride in the tail of the dL/dZ all-reduce
+    dist.all_reduce(dZ, op=dist.ReduceOp.SUM, group=pg)
+    loss_slot.copy_(dZ[-2:-1].to(torch.float64) + dZ[-1:].to(torch.float64))
+    dA = b.get('dA', rows * H, torch.float32)
+    call('rcd_act_grad', ptr(dZ), ptr(Z), rows * H, self.act, ptr(dA))
+    call('rcd_colsum', ptr(dA), rows, H, H, ptr(dbe))
+    csc_ptr, csc_row, csc_val, _ = csc
+    call('rcd_ae_encoder_wgrad', ptr(dA), H, ptr(csc_ptr), ptr(csc_row), ptr(csc_val), ptr(pool.row_inv_norm), row0, n,
+         ptr(dWe), None, None)
+    self.opt.step_param(en_name, dWe, H, pos=pool.pos, ids=pool.items_buf, n_ids=n)
+    self.opt.step_param(enb_name, dbe, 1)
 
   # ------------------------------------------------------------------------------------------------------
   def _mf_step(self, pool, tpool, row0, rows, inv_b, loss_slot, train):

@@ -62,6 +62,11 @@ class Recoder(object):
       gradient slab live in CUDA-IPC peer memory and one fused kernel per table does reduce-scatter -> Adam ->
       all-gather over NVLink (dense Adam, untied weights); 'nccl': one all-reduce of the slab, then a full Adam
       pass on every rank; 'auto' (default): 'p2p' when it applies, else 'nccl'.
+    parallel (optional, extension): what the ranks of a multi-GPU run split — 'rows' (default): the users of the
+      global batch (data parallel, gradients exchanged as above); 'items': the item axis (embedding tables, optimizer
+      state, matrix columns, decoder GEMM width; `itempar.py`) — every rank processes all rows of the global batch
+      and only two [B_global, H] activations cross NVLink per step.  Single-hidden-layer autoencoders without
+      noise / dropout / tied weights and with a dense optimizer; anything else falls back to 'rows'.
   """
 
   def __init__(self, model: FactorizationModel,
@@ -69,7 +74,7 @@ class Recoder(object):
                optimizer_type='sgd', loss='mse',
                loss_params=None, use_cuda=False,
                user_based=True, item_based=True,
-               process_group=None, gemm_engine=None, dp_exchange='auto'):
+               process_group=None, gemm_engine=None, dp_exchange='auto', parallel='rows'):
 
     self.model = model
     self.num_items = num_items
@@ -85,7 +90,11 @@ class Recoder(object):
     if dp_exchange not in ('auto', 'p2p', 'nccl'):
       raise ValueError("dp_exchange must be 'auto', 'p2p' or 'nccl'")
     self.dp_exchange = dp_exchange
+    if parallel not in ('rows', 'items'):
+      raise ValueError("parallel must be 'rows' or 'items'")
+    self.parallel = parallel
     self._p2p = None
+    self._ip = None
 
     if self.use_cuda:
       self.device = torch.device('cuda')
@@ -152,7 +161,11 @@ class Recoder(object):
 
     sparse_names = self.model._sparse_param_names()
     named = [(n, p.data) for n, p in self.model.named_parameters()]
+    if self._ip is not None:   # item-parallel: the optimizer owns the local shards of the item-indexed tensors
+      named = [(n, self._ip.sharded.get(n, t)) for n, t in named]
     self.optimizer = Optimizer(named, self.optimizer_type, lr, weight_decay, sparse_names=sparse_names)
+    if self._ip is not None and self.__optimizer_state_dict is not None:
+      self.__optimizer_state_dict = self.__shard_optimizer_state(self.__optimizer_state_dict)
 
     if self.__optimizer_state_dict is not None:
       self.optimizer.load_state_dict(self.__optimizer_state_dict, dense=True)
@@ -183,6 +196,18 @@ class Recoder(object):
       dist.broadcast(p.data, src=dist.get_global_rank(pg, 0), group=pg)
     self._dp_ready = True
     self._p2p_buffers = {}
+    if self.parallel == 'items':
+      kind, roles, _, tied = self.model._engine_spec()
+      ok = (kind == 'ae' and not tied and not roles['enc_layers'] and roles['noise_prob'] == 0.0
+            and roles['dropout_prob'] == 0.0 and not self.model._sparse_param_names())
+      if ok:
+        from .itempar import ItemParallel
+        self._ip = ItemParallel(pg)
+        for role in ('en_w', 'de_w', 'de_b'):
+          name, full = roles[role]
+          self._ip.shard(name, full)
+        return
+      log.warning("parallel='items' does not cover this model configuration; falling back to 'rows'")
     if self.dp_exchange == 'nccl':
       return
     from .p2p import P2PContext
@@ -203,14 +228,52 @@ class Recoder(object):
         named[name].data = view
         self._p2p_buffers[name] = buf
 
+  def __shard_optimizer_state(self, sd):
+    """Full-size optimizer state tensors (a checkpoint) -> this rank's item shard."""
+    names = [n for n, _ in self.model.named_parameters()]
+    out = {'state': {}, 'param_groups': sd.get('param_groups')}
+    for i, entry in sd['state'].items():
+      name = names[i]
+      if name in self._ip.sharded:
+        entry = {k: (self._ip.shard_like(v) if torch.is_tensor(v) and v.dim() >= 1 and
+                     v.shape[0] == dict(self.model.named_parameters())[name].shape[0] else v)
+                 for k, v in entry.items()}
+      out['state'][i] = entry
+    return out
+
+  def __full_optimizer_state(self, sd):
+    """This rank's optimizer state with the item-sharded tensors gathered to full size (collective)."""
+    names = [n for n, _ in self.model.named_parameters()]
+    full_rows = {n: p.shape[0] for n, p in self.model.named_parameters()}
+    for i, entry in sd['state'].items():
+      name = names[i]
+      if name in self._ip.sharded:
+        for k, v in list(entry.items()):
+          if torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == self._ip.sharded[name].shape[0]:
+            entry[k] = self._ip.gather_full(v.to(self.device), full_rows[name]).cpu()
+    return sd
+
+  def sync_parameters(self):
+    """Item-parallel mode: gathers the item shards back into the model's (full-size) parameters — called before
+    evaluation and checkpoints; collective.  A no-op otherwise."""
+    if self._ip is not None:
+      if self.engine is not None:
+        self.engine.join()
+      self._ip.sync_to_full({n: p.data for n, p in self.model.named_parameters()})
+
   def __init_engine(self):
     kind, roles, activation, tied = self.model._engine_spec()
+    if self._ip is not None:
+      for role in ('en_w', 'de_w', 'de_b'):
+        name, _ = roles[role]
+        roles[role] = (name, self._ip.sharded[name])
     loss_kind, confidence = self.__loss_spec()
     pg = self.__resolve_pg()
     for name, buf in getattr(self, '_p2p_buffers', {}).items():
       self.optimizer.states[name].shared = buf
     self.engine = TrainEngine(kind, roles, loss_kind, confidence, activation, self.optimizer,
-                              gemm_engine=self.gemm_engine, process_group=pg, tied=tied, p2p=self._p2p)
+                              gemm_engine=self.gemm_engine, process_group=pg, tied=tied, p2p=self._p2p,
+                              item_parallel=self._ip)
 
   def init_from_model_file(self, model_file):
     """
@@ -251,13 +314,17 @@ class Recoder(object):
     log.info("Saving model to {}".format(checkpoint_file))
     if self._p2p is not None and self.optimizer is not None:
       self.optimizer.gather_shards(self._p2p)   # collective: every rank must call save_state
+    self.sync_parameters()
+    optimizer_state = self.optimizer.state_dict(dense=True)
+    if self._ip is not None:
+      optimizer_state = self.__full_optimizer_state(optimizer_state)
     current_state = {
       'recoder_version': __version__,
       'model_params': self.model.model_params(),
       'last_epoch': self.current_epoch,
       'model': {k: v.detach().cpu() for k, v in self.model.state_dict().items()},
       'optimizer_type': self.optimizer_type,
-      'optimizer': self.optimizer.state_dict(dense=True),
+      'optimizer': optimizer_state,
       'items': self.items,
       'users': self.users,
       'num_items': self.num_items,
@@ -399,8 +466,13 @@ class Recoder(object):
     reference's `_default_data_generator` yields slices (data.py:138-144)."""
     world, rank = self._world()
     ds = dataloader.dataset
-    csr = ds.device_csr()
-    tcsr = ds.device_target_csr()
+    if self._ip is not None:
+      if ds.target_interactions_matrix is not None:
+        raise NotImplementedError("parallel='items' trains on datasets whose input is their own target")
+      csr, tcsr = ds.item_shard_csr(rank, world), None
+    else:
+      csr = ds.device_csr()
+      tcsr = ds.device_target_csr()
     gstep = batch_size * world
     ns = dataloader.negative_sampling
 
@@ -428,6 +500,11 @@ class Recoder(object):
         collate_pool_finish(tpool)
       index = next(pools, None)
       nxt = launch(index) if index is not None else None
+      if self._ip is not None:   # every rank takes all rows of the global slice; the item axis is what is split
+        for goff in range(0, pool.num_rows, gstep):
+          grows = min(gstep, pool.num_rows - goff)
+          yield pool, None, goff, grows, grows
+        continue
       for row0, rows, global_rows in shard_rows(pool.num_rows, gstep, world, rank):
         yield pool, tpool, row0, rows, global_rows
 
@@ -486,13 +563,17 @@ class Recoder(object):
 
       if self._sync_loss_every_step:
         self.engine.drain_deferred_loss()
+      if self._ip is not None and ((eval_freq > 0 and epoch % eval_freq == 0) or epoch == num_epochs or
+                                   (checkpoint_freq > 0 and epoch % checkpoint_freq == 0)):
+        self.sync_parameters()
       if steps_this_epoch:
         last_loss = float(self.engine.losses(1)[0])
       self.last_epoch_losses = self.engine.losses(steps_this_epoch).numpy() if steps_this_epoch else np.zeros(0)
       postfix = {'loss': last_loss}
       if eval_freq > 0 and epoch % eval_freq == 0 and val_dataloader is not None:
-        val_loss = self._validate(val_dataloader)
-        postfix['val_loss'] = val_loss
+        if self._ip is None:   # (item-parallel engines hold shards; the validation loss is skipped there)
+          val_loss = self._validate(val_dataloader)
+          postfix['val_loss'] = val_loss
         if metrics is not None and eval_num_recommendations is not None:
           results = self._evaluate(val_dataloader.dataset,
                                    num_recommendations=eval_num_recommendations,

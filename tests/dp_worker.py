@@ -29,8 +29,11 @@ def run(kind, loss, mode, pg, batch, steps, matrix, U, I, H, seed_params):
   if ':' in mode:   # 'p2p:ipc' = CUDA-IPC unicast ld/st, 'p2p:symm' = symmetric memory + NVLS multicast when available
     mode, backend = mode.split(':')
     os.environ['RCD_P2P_BACKEND'] = backend
+  parallel = 'rows'
+  if mode == 'items':   # item-parallel: every rank sees all rows, the item axis is sharded
+    mode, parallel = 'nccl', 'items'
   tr = Recoder(model=model, use_cuda=True, optimizer_type='adam', loss=loss, process_group=pg,
-               dp_exchange=mode if mode != 'single' else 'nccl')
+               dp_exchange=mode if mode != 'single' else 'nccl', parallel=parallel)
   ds = RecommendationDataset(matrix)
   order = np.random.default_rng(5).permutation(U)
   tr.train(ds, lr=1e-2, weight_decay=1e-4, num_epochs=1, iters_per_epoch=steps, batch_size=batch,
@@ -38,8 +41,14 @@ def run(kind, loss, mode, pg, batch, steps, matrix, U, I, H, seed_params):
   torch.cuda.synchronize()
   if tr._p2p is not None:
     tr.optimizer.gather_shards(tr._p2p)
+  tr.sync_parameters()
   params = {n: p.detach().float().cpu().clone() for n, p in model.named_parameters()}
   state = {n: (s.m.cpu().clone(), s.v.cpu().clone()) for n, s in tr.optimizer.states.items()}
+  if tr._ip is not None:
+    assert parallel == 'items'
+    full = tr._Recoder__full_optimizer_state(tr.optimizer.state_dict(dense=True))
+    names = [n for n, _ in model.named_parameters()]
+    state = {names[i]: (e['exp_avg'].clone(), e['exp_avg_sq'].clone()) for i, e in full['state'].items()}
   losses = tr.last_epoch_losses.copy()
   used_p2p = tr._p2p is not None
   if used_p2p and dist.get_rank() == 0:
@@ -68,7 +77,12 @@ def main():
     p2p_mc = run(kind, loss, 'p2p:auto', None, B, steps, matrix, U, I, H, 3)
     assert p2p[3] and p2p_mc[3], 'peer-memory exchange was not used'
     assert not nccl[3]
-    for tag, got in (('nccl', nccl), ('p2p-ipc', p2p), ('p2p-auto', p2p_mc)):
+    variants = [('nccl', nccl), ('p2p-ipc', p2p), ('p2p-auto', p2p_mc)]
+    if kind == 'ae':
+      items = run(kind, loss, 'items', None, B, steps, matrix, U, I, H, 3)
+      assert not items[3]
+      variants.append(('items', items))
+    for tag, got in variants:
       # every rank holds the same replica
       for n, t in got[0].items():
         g = [torch.zeros_like(t, device='cuda') for _ in range(world)]

@@ -201,7 +201,7 @@ def test_decoder_fwd_loss_and_finish(loss, rows, n, H):
   bad = torch.zeros(1, dtype=torch.int32, device='cuda')
   row_sum = T.sum(1).contiguous()
   call('rcd_loss_finish', ptr(stat), sc, sc, rows, lid, conf, inv_b, ptr(row_ref), ptr(row_sum), ptr(row_ptr),
-       ptr(vals), ptr(o_nnz), 0, ptr(alpha), ptr(Zf), H, ptr(Zs), ldh, ptr(acc), ptr(bad))
+       ptr(vals), ptr(o_nnz), 0, ptr(alpha), ptr(Zf), H, ptr(Zs), ldh, ptr(acc), ptr(bad), 0)
   torch.cuda.synchronize()
   assert int(bad.item()) == 0
   assert not torch.isnan(G[:, :n].float()).any()
