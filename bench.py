@@ -172,7 +172,8 @@ def workload_config(args, w, U, batch, world):
   return {'workload': w['desc'], 'users': U, 'items': w['items'], 'nnz_per_user': w['nnz'], 'model': w['model'],
           'width': w['width'], 'loss': w['loss'], 'optimizer': 'adam (dense, torch.optim.Adam semantics)',
           'batch_per_gpu': batch, 'global_batch': batch * world, 'negative_sampling': True,
-          'parallelism': 'dp%d' % world, 'dp_exchange': args.dp_exchange,
+          'parallelism': ('dp%d' if args.parallel == 'rows' or world == 1 else 'items%d') % world,
+          'dp_exchange': args.dp_exchange,
           'l2': 'per-step working set (embedding tables + Adam state + logits) is larger than the 126 MB L2'}
 
 
@@ -297,7 +298,8 @@ def b200_arm(args, w):
       model = DynamicAutoencoder(hidden_layers=[H], activation_type='tanh')
     else:
       model = MatrixFactorization(embedding_size=H, activation_type='none')
-    trainer = Recoder(model=model, use_cuda=True, optimizer_type='adam', loss=w['loss'], dp_exchange=args.dp_exchange)
+    trainer = Recoder(model=model, use_cuda=True, optimizer_type='adam', loss=w['loss'], dp_exchange=args.dp_exchange,
+                      parallel=args.parallel)
     ds = RecommendationDataset(matrix, device_resident=device_resident)
     st = {'n': [], 'launch0': 0, 'launch1': 0, 'bytes0': None, 'bytes1': None, 'clocks': None, 'warm': {},
           'dominant': None}
@@ -471,12 +473,17 @@ def main():
   ap.add_argument('--users', type=int, default=0, help='use a user prefix of the matrix (0 = all)')
   ap.add_argument('--dp-exchange', default='auto', choices=['auto', 'p2p', 'nccl'],
                   help='N>1: fused peer-memory reduce-scatter/Adam/all-gather kernel (p2p) or NCCL all-reduce + full Adam')
+  ap.add_argument('--parallel', default='auto', choices=['auto', 'rows', 'items'],
+                  help='N>1: split the users of the global batch (data parallel, gradient exchange per --dp-exchange) '
+                       'or the item axis (itempar.py); auto = items for the autoencoder configs, rows otherwise')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--skip-e2e', action='store_true', help='profiling runs only: skip the host-staged leg')
   ap.add_argument('--no-profile', action='store_true', help='no CUDA-event kernel breakdown during warm-up')
   ap.add_argument('--cpu-budget', type=float, default=150.0, help='seconds the CPU arm may take')
   args = ap.parse_args()
   w = WORKLOADS[args.config]
+  if args.parallel == 'auto':
+    args.parallel = 'items' if (w['model'] == 'ae' and int(os.environ.get('WORLD_SIZE', '1')) > 1) else 'rows'
   if args.impl == 'reference':
     reference_arm(args, w)
   else:
