@@ -177,7 +177,12 @@ int rcd_loss_finish(const float* stat, int stat_ld, int stat_cols, int rows, int
 int rcd_sparse_dgrad(const float* W, int H, const int32_t* row_ptr, const int32_t* raw_items, const float* corr,
                      int row0, int rows, float* out, int ldp, void* stream);
 int rcd_csc_rows_accumulate(const float* M, int H, const int32_t* csc_ptr, const int32_t* csc_row,
-                            const int32_t* csc_src, const float* coef, int n, float* out, float* db, void* stream);
+                            const int32_t* csc_src, const float* coef, int n, float* out, float* db, void* scratch,
+                            size_t scratch_bytes, long long nnz_slice, void* stream);
+/* Workspace of the two column-major accumulations (rcd_csc_rows_accumulate, rcd_ae_encoder_wgrad): item popularity is
+ * a power law, so a few columns hold an entry in nearly every row; columns with more than 128 entries are processed
+ * in 128-entry chunks by separate thread groups and summed in chunk order.  scratch == NULL: no chunking. */
+size_t rcd_csc_heavy_scratch_bytes(int n, long long nnz_slice, int H);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K6  decoder backward GEMMs — replace autograd's `mm` nodes of F.linear.
@@ -206,7 +211,8 @@ int rcd_dz_act(const float* partials, int splits, int n_scaled, const float* row
                int rows, int H, int act, float* dA, float* db, void* stream);
 int rcd_ae_encoder_wgrad(const float* dA, int H, const int32_t* csc_ptr, const int32_t* csc_row,
                          const float* csc_val, const float* row_inv_norm, int row0, int n, float* dWe_rows,
-                         const int32_t* csc_src, const float* csr_vals, void* stream);
+                         const int32_t* csc_src, const float* csr_vals, void* scratch, size_t scratch_bytes,
+                         long long nnz_slice, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K8  optimizers — replace torch.optim.{Adam,SGD,SparseAdam}.step as configured by

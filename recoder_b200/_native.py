@@ -46,12 +46,14 @@ _SIGNATURES = {
   'rcd_loss_finish': (c_int, [_P, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P, c_int, _P, _P,
                               c_int, _P, c_int, _P, _P, c_int, _P]),
   'rcd_sparse_dgrad': (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, _P, c_int, _P]),
-  'rcd_csc_rows_accumulate': (c_int, [_P, c_int, _P, _P, _P, _P, c_int, _P, _P, _P]),
+  'rcd_csc_rows_accumulate': (c_int, [_P, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, c_size_t, c_longlong, _P]),
+  'rcd_csc_heavy_scratch_bytes': (c_size_t, [c_int, c_longlong, c_int]),
   'rcd_decoder_dgrad_splits': (c_int, [c_int, c_int, c_int]),
   'rcd_decoder_dgrad': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
   'rcd_decoder_wgrad': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int, _P]),
   'rcd_dz_act': (c_int, [_P, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P]),
-  'rcd_ae_encoder_wgrad': (c_int, [_P, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P]),
+  'rcd_ae_encoder_wgrad': (c_int, [_P, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, c_size_t, c_longlong,
+                                   _P]),
   'rcd_adam_step': (c_int, [_P, _P, _P, c_longlong, c_int, _P, c_int, _P, c_double, c_double, c_double, c_double,
                             c_double, c_longlong, _P]),
   'rcd_sgd_step': (c_int, [_P, _P, c_longlong, c_int, _P, c_int, _P, c_double, c_double, c_double, _P]),

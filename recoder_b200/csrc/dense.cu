@@ -58,19 +58,31 @@ static __global__ void k_act_grad(const float* __restrict__ dy, const float* __r
     dpre[i] = dy[i] * act_grad_from_out(y[i], act);
 }
 
-static __global__ void k_colsum(const float* __restrict__ x, int rows, int H, int ld, float* __restrict__ out) {
-  __shared__ float part[8][33];
+// 32 columns per block, 32 warps stride the rows (tall inputs: the item-parallel mode sums over the GLOBAL batch), four
+// independent row loads in flight per warp, fixed-order reduction through shared memory
+constexpr int kColsumWarps = 32;
+static __global__ void __launch_bounds__(kColsumWarps * 32)
+    k_colsum(const float* __restrict__ x, int rows, int H, int ld, float* __restrict__ out) {
+  __shared__ float part[kColsumWarps][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int h = blockIdx.x * 32 + lane;
-  float s = 0.f;
-  if (h < H)
-    for (int r = w; r < rows; r += 8) s += x[(size_t)r * ld + h];
-  part[w][lane] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (h < H) {
+    int r = w;
+    for (; r + 3 * kColsumWarps < rows; r += 4 * kColsumWarps) {
+      s0 += x[(size_t)r * ld + h];
+      s1 += x[(size_t)(r + kColsumWarps) * ld + h];
+      s2 += x[(size_t)(r + 2 * kColsumWarps) * ld + h];
+      s3 += x[(size_t)(r + 3 * kColsumWarps) * ld + h];
+    }
+    for (; r < rows; r += kColsumWarps) s0 += x[(size_t)r * ld + h];
+  }
+  part[w][lane] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (w == 0 && h < H) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += part[k][lane];  // fixed order
+    for (int k = 0; k < kColsumWarps; ++k) t += part[k][lane];  // fixed order
     out[h] = t;
   }
 }
@@ -221,7 +233,7 @@ RCD_EXPORT int rcd_act_grad(const float* dy, const float* y, long long count, in
 
 RCD_EXPORT int rcd_colsum(const float* x, int rows, int H, int ld, float* out, void* stream) {
   RCD_CHECK_ARG(x && out && rows > 0 && H > 0 && ld >= H, "bad arguments");
-  k_colsum<<<rcd_div_up(H, 32), 256, 0, (cudaStream_t)stream>>>(x, rows, H, ld, out);
+  k_colsum<<<rcd_div_up(H, 32), kColsumWarps * 32, 0, (cudaStream_t)stream>>>(x, rows, H, ld, out);
   RCD_LAUNCH_CHECK();
   return RCD_OK;
 }

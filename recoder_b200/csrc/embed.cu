@@ -124,11 +124,13 @@ static __global__ void __launch_bounds__(kEmbThreads)
     k_encoder_wgrad(const float* __restrict__ dA, int H, const int32_t* __restrict__ csc_ptr,
                     const int32_t* __restrict__ csc_row, const float* __restrict__ csc_val,
                     const int32_t* __restrict__ src, const float* __restrict__ row_inv_norm, int row0, int n, int tpr,
-                    float* __restrict__ out, int accumulate, float* __restrict__ db) {
+                    float* __restrict__ out, int accumulate, float* __restrict__ db,
+                    const int32_t* __restrict__ slot_base) {
   const int rpb = kEmbThreads / tpr;
   const int c = blockIdx.x * rpb + threadIdx.x / tpr;
   const int t = threadIdx.x % tpr;
   if (c >= n) return;
+  if (slot_base && slot_base[c] >= 0) return;  // heavy column: chunked path below
   const int s = csc_ptr[c], e = csc_ptr[c + 1];
   Vec<VEC> acc[NV];
 #pragma unroll
@@ -154,6 +156,92 @@ static __global__ void __launch_bounds__(kEmbThreads)
     float sum = 0.f;
     for (int p = s; p < e; ++p) sum += src ? csc_val[src[p]] : csc_val[p];  // fixed order
     db[c] += sum;
+  }
+}
+
+// ---- heavy columns ---------------------------------------------------------------------------------------------------
+// Item popularity is a power law: a few columns of a slice hold an entry in almost every row (up to `rows` entries, 16K
+// in the item-parallel mode), and one thread group walking such a column alone is a serial chain of L2 round trips that
+// outlasts the whole rest of the kernel.  Columns with more than kHeavyChunk entries are therefore cut into chunks of
+// kHeavyChunk entries, one thread group per chunk writes a partial row, and the first chunk's group adds the partials up
+// in chunk order (deterministic).  Chunk slots are handed out with one atomic counter per launch.
+constexpr int kHeavyChunk = 128;
+
+static __global__ void k_heavy_setup(const int32_t* __restrict__ csc_ptr, int n, int32_t* __restrict__ counter,
+                                     int32_t* __restrict__ slot_base, int32_t* __restrict__ chunk_col, int cap) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const int cnt = csc_ptr[c + 1] - csc_ptr[c];
+  if (cnt <= kHeavyChunk) {
+    slot_base[c] = -1;
+    return;
+  }
+  const int nch = (cnt + kHeavyChunk - 1) / kHeavyChunk;
+  const int base = atomicAdd(counter, nch);
+  slot_base[c] = base;
+  for (int j = 0; j < nch; ++j)
+    if (base + j < cap) chunk_col[base + j] = c;
+}
+
+template <int VEC, int NV>
+static __global__ void __launch_bounds__(kEmbThreads)
+    k_encoder_wgrad_heavy(const float* __restrict__ dA, int H, const int32_t* __restrict__ csc_ptr,
+                          const int32_t* __restrict__ csc_row, const float* __restrict__ csc_val,
+                          const int32_t* __restrict__ src, const float* __restrict__ row_inv_norm, int row0, int tpr,
+                          const int32_t* __restrict__ counter, const int32_t* __restrict__ slot_base,
+                          const int32_t* __restrict__ chunk_col, int cap, float* __restrict__ partial,
+                          float* __restrict__ partial_db) {
+  const int rpb = kEmbThreads / tpr;
+  const int q = blockIdx.x * rpb + threadIdx.x / tpr;
+  const int t = threadIdx.x % tpr;
+  const int total = min(*counter, cap);
+  if (q >= total) return;
+  const int c = chunk_col[q];
+  const int j = q - slot_base[c];
+  const int s = csc_ptr[c] + j * kHeavyChunk, e = min(s + kHeavyChunk, csc_ptr[c + 1]);
+  Vec<VEC> acc[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc[k].zero();
+  seg_accumulate<VEC, NV>(acc, dA, H, t, tpr, s, e, [&](int p, int& idx, float& cf) {
+    idx = csc_row[p];
+    cf = src ? csc_val[src[p]] : csc_val[p];
+    if (row_inv_norm) cf *= row_inv_norm[row0 + idx];
+  });
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    int h = (t + k * tpr) * VEC;
+    if (h < H) acc[k].store(partial + (size_t)q * H + h);
+  }
+  if (partial_db && t == 0) {
+    float sum = 0.f;
+    for (int p = s; p < e; ++p) sum += src ? csc_val[src[p]] : csc_val[p];
+    partial_db[q] = sum;
+  }
+}
+
+static __global__ void __launch_bounds__(kEmbThreads)
+    k_heavy_reduce(const int32_t* __restrict__ csc_ptr, int H, int tpr, const int32_t* __restrict__ counter,
+                   const int32_t* __restrict__ slot_base, const int32_t* __restrict__ chunk_col, int cap,
+                   const float* __restrict__ partial, const float* __restrict__ partial_db, float* __restrict__ out,
+                   int accumulate, float* __restrict__ db) {
+  const int rpb = kEmbThreads / tpr;
+  const int q = blockIdx.x * rpb + threadIdx.x / tpr;
+  const int t = threadIdx.x % tpr;
+  const int total = min(*counter, cap);
+  if (q >= total) return;
+  const int c = chunk_col[q];
+  if (slot_base[c] != q) return;  // the first chunk of a column does the reduction
+  const int nch = (csc_ptr[c + 1] - csc_ptr[c] + kHeavyChunk - 1) / kHeavyChunk;
+  for (int h = t; h < H; h += tpr) {
+    float s = 0.f;
+    for (int j = 0; j < nch; ++j) s += partial[(size_t)(q + j) * H + h];  // fixed order
+    if (accumulate) s += out[(size_t)c * H + h];
+    out[(size_t)c * H + h] = s;
+  }
+  if (db && partial_db && t == 0) {
+    float s = 0.f;
+    for (int j = 0; j < nch; ++j) s += partial_db[q + j];
+    db[c] += s;
   }
 }
 
@@ -242,20 +330,31 @@ static __global__ void k_dz_act(const float* __restrict__ partials, int splits, 
   dA[i] = s * act_grad_from_out(Z[i], act);
 }
 
-// db[h] = sum_r x[r,h]; one block per 32 columns, 8 warps stride the rows, fixed-order smem reduction.
-static __global__ void k_colsum_f32(const float* __restrict__ x, int rows, int H, float* __restrict__ db) {
-  __shared__ float part[8][33];
+// db[h] = sum_r x[r,h]; one block per 32 columns, 32 warps stride the rows with four loads in flight, fixed-order
+// smem reduction.
+constexpr int kColsumWarpsE = 32;
+static __global__ void __launch_bounds__(kColsumWarpsE * 32)
+    k_colsum_f32(const float* __restrict__ x, int rows, int H, float* __restrict__ db) {
+  __shared__ float part[kColsumWarpsE][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int h = blockIdx.x * 32 + lane;
-  float s = 0.f;
-  if (h < H)
-    for (int r = w; r < rows; r += 8) s += x[(size_t)r * H + h];
-  part[w][lane] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (h < H) {
+    int r = w;
+    for (; r + 3 * kColsumWarpsE < rows; r += 4 * kColsumWarpsE) {
+      s0 += x[(size_t)r * H + h];
+      s1 += x[(size_t)(r + kColsumWarpsE) * H + h];
+      s2 += x[(size_t)(r + 2 * kColsumWarpsE) * H + h];
+      s3 += x[(size_t)(r + 3 * kColsumWarpsE) * H + h];
+    }
+    for (; r < rows; r += kColsumWarpsE) s0 += x[(size_t)r * H + h];
+  }
+  part[w][lane] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (w == 0 && h < H) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += part[k][lane];
+    for (int k = 0; k < kColsumWarpsE; ++k) t += part[k][lane];
     db[h] = t;
   }
 }
@@ -325,47 +424,102 @@ RCD_EXPORT int rcd_ae_encoder_fwd(const float* We, int H, const float* be, const
   return RCD_OK;
 }
 
-RCD_EXPORT int rcd_ae_encoder_wgrad(const float* dA, int H, const int32_t* csc_ptr, const int32_t* csc_row,
-                                    const float* csc_val, const float* row_inv_norm, int row0, int n,
-                                    float* dWe_rows, const int32_t* csc_src, const float* csr_vals, void* stream) {
-  RCD_CHECK_ARG(dA && csc_ptr && csc_row && csc_val && row_inv_norm && dWe_rows, "null pointer");
-  RCD_CHECK_ARG((csc_src == nullptr) == (csr_vals == nullptr), "csc_src and csr_vals come together");
-  if (csr_vals) csc_val = csr_vals;  // input values in CSR order of the slice (noised), reached through csc_src
-  RCD_CHECK_ARG(n > 0 && H > 0 && row0 >= 0, "bad shape");
-  cudaStream_t st = (cudaStream_t)stream;
-  const bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(dA) & 15) == 0);
-  const int units = vec ? H / 4 : H;
-  const int tpr = pick_tpr(units);
-  const int blocks = rcd_div_up(n, kEmbThreads / tpr);
-  if (vec)
-    RCD_DISPATCH_NV(k_encoder_wgrad, 4, units, tpr, <<<blocks, kEmbThreads, 0, st>>>(
-        dA, H, csc_ptr, csc_row, csc_val, csc_src, row_inv_norm, row0, n, tpr, dWe_rows, 0, nullptr));
-  else
-    RCD_DISPATCH_NV(k_encoder_wgrad, 1, units, tpr, <<<blocks, kEmbThreads, 0, st>>>(
-        dA, H, csc_ptr, csc_row, csc_val, csc_src, row_inv_norm, row0, n, tpr, dWe_rows, 0, nullptr));
-  RCD_LAUNCH_CHECK();
-  return RCD_OK;
-}
-
-RCD_EXPORT int rcd_csc_rows_accumulate(const float* M, int H, const int32_t* csc_ptr, const int32_t* csc_row,
-                                       const int32_t* csc_src, const float* coef, int n, float* out, float* db,
-                                       void* stream) {
-  RCD_CHECK_ARG(M && csc_ptr && csc_row && coef && out, "null pointer");
-  RCD_CHECK_ARG(n > 0 && H > 0, "bad shape");
-  cudaStream_t st = (cudaStream_t)stream;
+// shared driver of the two column-major accumulations (encoder weight gradient / sparse part of dW_d)
+static int csc_accumulate(const float* M, int H, const int32_t* csc_ptr, const int32_t* csc_row, const float* vals,
+                          const int32_t* src, const float* row_inv_norm, int row0, int n, float* out, int accumulate,
+                          float* db, void* scratch, size_t scratch_bytes, long long nnz_hint, cudaStream_t st,
+                          const char* who) {
   const bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(M) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   const int units = vec ? H / 4 : H;
   const int tpr = pick_tpr(units);
-  const int blocks = rcd_div_up(n, kEmbThreads / tpr);
-  if (vec)
-    RCD_DISPATCH_NV(k_encoder_wgrad, 4, units, tpr, <<<blocks, kEmbThreads, 0, st>>>(
-        M, H, csc_ptr, csc_row, coef, csc_src, nullptr, 0, n, tpr, out, 1, db));
-  else
-    RCD_DISPATCH_NV(k_encoder_wgrad, 1, units, tpr, <<<blocks, kEmbThreads, 0, st>>>(
-        M, H, csc_ptr, csc_row, coef, csc_src, nullptr, 0, n, tpr, out, 1, db));
-  RCD_LAUNCH_CHECK();
+  const int rpb = kEmbThreads / tpr;
+  const int nv = rcd_div_up(units, tpr);
+  if (nv > 8) {
+    rcd_set_error("%s: hidden size %d too large", who, H);
+    return RCD_ERR_UNSUPPORTED;
+  }
+  // heavy-column workspace: counter (4 ints) | slot_base[n] | chunk_col[cap] | partial[cap*H] | partial_db[cap]
+  int32_t *counter = nullptr, *slot_base = nullptr, *chunk_col = nullptr;
+  float *partial = nullptr, *partial_db = nullptr;
+  int cap = 0;
+  if (scratch) {
+    const size_t head = (size_t)(4 + n) * sizeof(int32_t);
+    if (scratch_bytes > head + 1024) {
+      const size_t per_chunk = sizeof(int32_t) + ((size_t)H + 1) * sizeof(float);
+      size_t c = (scratch_bytes - head - 64) / per_chunk;
+      const size_t want = (size_t)(2 * (nnz_hint > 0 ? nnz_hint : 0) / kHeavyChunk + 2);
+      cap = (int)(c < want ? c : want);
+      counter = reinterpret_cast<int32_t*>(scratch);
+      slot_base = counter + 4;
+      chunk_col = slot_base + n;
+      partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(chunk_col + cap) + 15) & ~(uintptr_t)15);
+      partial_db = partial + (size_t)cap * H;
+    }
+  }
+  if (cap > 0) {
+    RCD_CUDA(cudaMemsetAsync(counter, 0, 4 * sizeof(int32_t), st));
+    k_heavy_setup<<<rcd_div_up(n, 256), 256, 0, st>>>(csc_ptr, n, counter, slot_base, chunk_col, cap);
+    RCD_LAUNCH_CHECK();
+  } else {
+    slot_base = nullptr;
+  }
+  const int blocks = rcd_div_up(n, rpb);
+#define RCD_CSC_LAUNCH(VECW, NVV)                                                                                     \
+  do {                                                                                                                \
+    k_encoder_wgrad<VECW, NVV><<<blocks, kEmbThreads, 0, st>>>(M, H, csc_ptr, csc_row, vals, src, row_inv_norm, row0, \
+                                                               n, tpr, out, accumulate, db, slot_base);               \
+    RCD_LAUNCH_CHECK();                                                                                               \
+    if (cap > 0) {                                                                                                    \
+      const int hb = rcd_div_up(cap, rpb);                                                                            \
+      k_encoder_wgrad_heavy<VECW, NVV><<<hb, kEmbThreads, 0, st>>>(M, H, csc_ptr, csc_row, vals, src, row_inv_norm,   \
+                                                                   row0, tpr, counter, slot_base, chunk_col, cap,     \
+                                                                   partial, db ? partial_db : nullptr);               \
+      RCD_LAUNCH_CHECK();                                                                                             \
+      k_heavy_reduce<<<hb, kEmbThreads, 0, st>>>(csc_ptr, H, tpr, counter, slot_base, chunk_col, cap, partial,        \
+                                                 db ? partial_db : nullptr, out, accumulate, db);                     \
+      RCD_LAUNCH_CHECK();                                                                                             \
+    }                                                                                                                 \
+  } while (0)
+  if (vec) {
+    if (nv <= 1) RCD_CSC_LAUNCH(4, 1);
+    else if (nv <= 2) RCD_CSC_LAUNCH(4, 2);
+    else if (nv <= 4) RCD_CSC_LAUNCH(4, 4);
+    else RCD_CSC_LAUNCH(4, 8);
+  } else {
+    if (nv <= 1) RCD_CSC_LAUNCH(1, 1);
+    else if (nv <= 2) RCD_CSC_LAUNCH(1, 2);
+    else if (nv <= 4) RCD_CSC_LAUNCH(1, 4);
+    else RCD_CSC_LAUNCH(1, 8);
+  }
+#undef RCD_CSC_LAUNCH
   return RCD_OK;
+}
+
+RCD_EXPORT size_t rcd_csc_heavy_scratch_bytes(int n, long long nnz_slice, int H) {
+  const size_t cap = (size_t)(2 * (nnz_slice > 0 ? nnz_slice : 0) / kHeavyChunk + 2);
+  return (size_t)(4 + n) * sizeof(int32_t) + cap * (sizeof(int32_t) + ((size_t)H + 1) * sizeof(float)) + 2048;
+}
+
+RCD_EXPORT int rcd_ae_encoder_wgrad(const float* dA, int H, const int32_t* csc_ptr, const int32_t* csc_row,
+                                    const float* csc_val, const float* row_inv_norm, int row0, int n,
+                                    float* dWe_rows, const int32_t* csc_src, const float* csr_vals, void* scratch,
+                                    size_t scratch_bytes, long long nnz_slice, void* stream) {
+  RCD_CHECK_ARG(dA && csc_ptr && csc_row && csc_val && row_inv_norm && dWe_rows, "null pointer");
+  RCD_CHECK_ARG((csc_src == nullptr) == (csr_vals == nullptr), "csc_src and csr_vals come together");
+  if (csr_vals) csc_val = csr_vals;  // input values in CSR order of the slice (noised), reached through csc_src
+  RCD_CHECK_ARG(n > 0 && H > 0 && row0 >= 0, "bad shape");
+  return csc_accumulate(dA, H, csc_ptr, csc_row, csc_val, csc_src, row_inv_norm, row0, n, dWe_rows, 0, nullptr, scratch,
+                        scratch_bytes, nnz_slice, (cudaStream_t)stream, "rcd_ae_encoder_wgrad");
+}
+
+RCD_EXPORT int rcd_csc_rows_accumulate(const float* M, int H, const int32_t* csc_ptr, const int32_t* csc_row,
+                                       const int32_t* csc_src, const float* coef, int n, float* out, float* db,
+                                       void* scratch, size_t scratch_bytes, long long nnz_slice, void* stream) {
+  RCD_CHECK_ARG(M && csc_ptr && csc_row && coef && out, "null pointer");
+  RCD_CHECK_ARG(n > 0 && H > 0, "bad shape");
+  return csc_accumulate(M, H, csc_ptr, csc_row, coef, csc_src, nullptr, 0, n, out, 1, db, scratch, scratch_bytes,
+                        nnz_slice, (cudaStream_t)stream, "rcd_csc_rows_accumulate");
 }
 
 RCD_EXPORT int rcd_sparse_dgrad(const float* W, int H, const int32_t* row_ptr, const int32_t* raw_items,
@@ -398,7 +552,7 @@ RCD_EXPORT int rcd_dz_act(const float* partials, int splits, int n_scaled, const
                                                    (long long)rows * ldp, ldp, Z, rows, H, act, dA);
   RCD_LAUNCH_CHECK();
   if (db) {
-    k_colsum_f32<<<rcd_div_up(H, 32), 256, 0, st>>>(dA, rows, H, db);
+    k_colsum_f32<<<rcd_div_up(H, 32), kColsumWarpsE * 32, 0, st>>>(dA, rows, H, db);
     RCD_LAUNCH_CHECK();
   }
   return RCD_OK;

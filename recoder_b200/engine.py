@@ -380,6 +380,11 @@ class TrainEngine:
       ev.record(self._aux)
       self._ready['csc'] = ev
 
+  def _heavy_scratch(self, n, nnz, H):
+    """Workspace of the chunked heavy-column path of the column-major accumulations (rcd_csc_heavy_scratch_bytes)."""
+    sbytes = self.lib.rcd_csc_heavy_scratch_bytes(int(n), int(nnz), int(H))
+    return self.buf.get('heavy_scratch', sbytes, torch.uint8), sbytes, int(nnz)
+
   def _slice_csc(self, pool, row0, rows, n, tag):
     nnz = int(pool.row_ptr_host[row0 + rows] - pool.row_ptr_host[row0])
     b = self.buf
@@ -437,8 +442,9 @@ class TrainEngine:
     the stored targets)."""
     call('rcd_decoder_wgrad', ptr(G), ldn, ptr(Zs), ldh, rows, n, H, ptr(dW), H, ptr(alpha), ptr(db), self.gemm)
     csc_ptr, csc_row, _, csc_src = csc
+    scratch, sbytes, nnz = self._heavy_scratch(n, csc_row.numel(), H)
     call('rcd_csc_rows_accumulate', ptr(Zf32), H, ptr(csc_ptr), ptr(csc_row), ptr(csc_src), ptr(corr), n, ptr(dW),
-         ptr(db))
+         ptr(db), ptr(scratch), sbytes, nnz)
 
   # --- update stream: optimizer / exchange kernels overlap the rest of the backward ------------------------------
   def _update_stream(self):
@@ -743,12 +749,13 @@ class TrainEngine:
       self._mid_backward(dY, mid, rows, row0, H, dA, inner_grads, inner)
       call('rcd_colsum', ptr(dA), rows, H, H, ptr(dbe))
     csc_ptr, csc_row, csc_val, csc_src = csc_in
+    scratch, sbytes, nnz_c = self._heavy_scratch(n_in, csc_row.numel(), H)
     if in_vals is pool.vals:
       call('rcd_ae_encoder_wgrad', ptr(dA), H, ptr(csc_ptr), ptr(csc_row), ptr(csc_val), ptr(pool.row_inv_norm), row0,
-           n_in, ptr(dWe), None, None)
+           n_in, ptr(dWe), None, None, ptr(scratch), sbytes, nnz_c)
     else:
       call('rcd_ae_encoder_wgrad', ptr(dA), H, ptr(csc_ptr), ptr(csc_row), ptr(csc_val), ptr(pool.row_inv_norm), row0,
-           n_in, ptr(dWe), ptr(csc_src), ptr(in_vals[base:]))
+           n_in, ptr(dWe), ptr(csc_src), ptr(in_vals[base:]), ptr(scratch), sbytes, nnz_c)
 
     if self.p2p is not None:
       self._stash_loss(slab, loss_slot)
@@ -878,8 +885,9 @@ class TrainEngine:
     call('rcd_act_grad', ptr(dZ), ptr(Z), rows * H, self.act, ptr(dA))
     call('rcd_colsum', ptr(dA), rows, H, H, ptr(dbe))
     csc_ptr, csc_row, csc_val, _ = csc
+    scratch, sbytes, nnz_c = self._heavy_scratch(n, csc_row.numel(), H)
     call('rcd_ae_encoder_wgrad', ptr(dA), H, ptr(csc_ptr), ptr(csc_row), ptr(csc_val), ptr(pool.row_inv_norm), row0, n,
-         ptr(dWe), None, None)
+         ptr(dWe), None, None, ptr(scratch), sbytes, nnz_c)
     self.opt.step_param(en_name, dWe, H, pos=pool.pos, ids=pool.items_buf, n_ids=n)
     self.opt.step_param(enb_name, dbe, 1)
 
