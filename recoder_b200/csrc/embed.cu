@@ -36,6 +36,7 @@ struct Vec<1> {
 };
 
 constexpr int kEmbThreads = 256;
+constexpr int kHeavyChunk = 128;  // entries per chunk of a heavy column (see k_heavy_setup)
 
 // acc[k] (k < NV) += sum_e coef(e) * M[idx(e), (t + k*tpr)*VEC ...]
 template <int VEC, int NV, class Entry>
@@ -125,12 +126,42 @@ static __global__ void __launch_bounds__(kEmbThreads)
                     const int32_t* __restrict__ csc_row, const float* __restrict__ csc_val,
                     const int32_t* __restrict__ src, const float* __restrict__ row_inv_norm, int row0, int n, int tpr,
                     float* __restrict__ out, int accumulate, float* __restrict__ db,
-                    const int32_t* __restrict__ slot_base) {
+                    const int32_t* __restrict__ slot_base, int heavy_blocks, const int32_t* __restrict__ counter,
+                    const int32_t* __restrict__ chunk_col, int cap, float* __restrict__ partial,
+                    float* __restrict__ partial_db) {
   const int rpb = kEmbThreads / tpr;
-  const int c = blockIdx.x * rpb + threadIdx.x / tpr;
   const int t = threadIdx.x % tpr;
+  if ((int)blockIdx.x < heavy_blocks) {
+    // ---- one 128-entry chunk of a heavy column (scheduled first, so the long columns overlap the light ones) ----
+    const int q = blockIdx.x * rpb + threadIdx.x / tpr;
+    const int total = min(*counter, cap);
+    if (q >= total) return;
+    const int c = chunk_col[q];
+    const int j = q - slot_base[c];
+    const int s = csc_ptr[c] + j * kHeavyChunk, e = min(s + kHeavyChunk, csc_ptr[c + 1]);
+    Vec<VEC> acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k].zero();
+    seg_accumulate<VEC, NV>(acc, dA, H, t, tpr, s, e, [&](int p, int& idx, float& cf) {
+      idx = csc_row[p];
+      cf = src ? csc_val[src[p]] : csc_val[p];
+      if (row_inv_norm) cf *= row_inv_norm[row0 + idx];
+    });
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      int h = (t + k * tpr) * VEC;
+      if (h < H) acc[k].store(partial + (size_t)q * H + h);
+    }
+    if (partial_db && t == 0) {
+      float sum = 0.f;
+      for (int p = s; p < e; ++p) sum += src ? csc_val[src[p]] : csc_val[p];
+      partial_db[q] = sum;
+    }
+    return;
+  }
+  const int c = ((int)blockIdx.x - heavy_blocks) * rpb + threadIdx.x / tpr;
   if (c >= n) return;
-  if (slot_base && slot_base[c] >= 0) return;  // heavy column: chunked path below
+  if (slot_base && slot_base[c] >= 0) return;  // heavy column: chunked path above
   const int s = csc_ptr[c], e = csc_ptr[c + 1];
   Vec<VEC> acc[NV];
 #pragma unroll
@@ -165,8 +196,6 @@ static __global__ void __launch_bounds__(kEmbThreads)
 // outlasts the whole rest of the kernel.  Columns with more than kHeavyChunk entries are therefore cut into chunks of
 // kHeavyChunk entries, one thread group per chunk writes a partial row, and the first chunk's group adds the partials up
 // in chunk order (deterministic).  Chunk slots are handed out with one atomic counter per launch.
-constexpr int kHeavyChunk = 128;
-
 static __global__ void k_heavy_setup(const int32_t* __restrict__ csc_ptr, int n, int32_t* __restrict__ counter,
                                      int32_t* __restrict__ slot_base, int32_t* __restrict__ chunk_col, int cap) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,42 +210,6 @@ static __global__ void k_heavy_setup(const int32_t* __restrict__ csc_ptr, int n,
   slot_base[c] = base;
   for (int j = 0; j < nch; ++j)
     if (base + j < cap) chunk_col[base + j] = c;
-}
-
-template <int VEC, int NV>
-static __global__ void __launch_bounds__(kEmbThreads)
-    k_encoder_wgrad_heavy(const float* __restrict__ dA, int H, const int32_t* __restrict__ csc_ptr,
-                          const int32_t* __restrict__ csc_row, const float* __restrict__ csc_val,
-                          const int32_t* __restrict__ src, const float* __restrict__ row_inv_norm, int row0, int tpr,
-                          const int32_t* __restrict__ counter, const int32_t* __restrict__ slot_base,
-                          const int32_t* __restrict__ chunk_col, int cap, float* __restrict__ partial,
-                          float* __restrict__ partial_db) {
-  const int rpb = kEmbThreads / tpr;
-  const int q = blockIdx.x * rpb + threadIdx.x / tpr;
-  const int t = threadIdx.x % tpr;
-  const int total = min(*counter, cap);
-  if (q >= total) return;
-  const int c = chunk_col[q];
-  const int j = q - slot_base[c];
-  const int s = csc_ptr[c] + j * kHeavyChunk, e = min(s + kHeavyChunk, csc_ptr[c + 1]);
-  Vec<VEC> acc[NV];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) acc[k].zero();
-  seg_accumulate<VEC, NV>(acc, dA, H, t, tpr, s, e, [&](int p, int& idx, float& cf) {
-    idx = csc_row[p];
-    cf = src ? csc_val[src[p]] : csc_val[p];
-    if (row_inv_norm) cf *= row_inv_norm[row0 + idx];
-  });
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    int h = (t + k * tpr) * VEC;
-    if (h < H) acc[k].store(partial + (size_t)q * H + h);
-  }
-  if (partial_db && t == 0) {
-    float sum = 0.f;
-    for (int p = s; p < e; ++p) sum += src ? csc_val[src[p]] : csc_val[p];
-    partial_db[q] = sum;
-  }
 }
 
 static __global__ void __launch_bounds__(kEmbThreads)
@@ -465,17 +458,14 @@ static int csc_accumulate(const float* M, int H, const int32_t* csc_ptr, const i
     slot_base = nullptr;
   }
   const int blocks = rcd_div_up(n, rpb);
+  const int hb = cap > 0 ? rcd_div_up(cap, rpb) : 0;
 #define RCD_CSC_LAUNCH(VECW, NVV)                                                                                     \
   do {                                                                                                                \
-    k_encoder_wgrad<VECW, NVV><<<blocks, kEmbThreads, 0, st>>>(M, H, csc_ptr, csc_row, vals, src, row_inv_norm, row0, \
-                                                               n, tpr, out, accumulate, db, slot_base);               \
+    k_encoder_wgrad<VECW, NVV><<<hb + blocks, kEmbThreads, 0, st>>>(                                                  \
+        M, H, csc_ptr, csc_row, vals, src, row_inv_norm, row0, n, tpr, out, accumulate, db, slot_base, hb, counter,   \
+        chunk_col, cap, partial, db ? partial_db : nullptr);                                                          \
     RCD_LAUNCH_CHECK();                                                                                               \
     if (cap > 0) {                                                                                                    \
-      const int hb = rcd_div_up(cap, rpb);                                                                            \
-      k_encoder_wgrad_heavy<VECW, NVV><<<hb, kEmbThreads, 0, st>>>(M, H, csc_ptr, csc_row, vals, src, row_inv_norm,   \
-                                                                   row0, tpr, counter, slot_base, chunk_col, cap,     \
-                                                                   partial, db ? partial_db : nullptr);               \
-      RCD_LAUNCH_CHECK();                                                                                             \
       k_heavy_reduce<<<hb, kEmbThreads, 0, st>>>(csc_ptr, H, tpr, counter, slot_base, chunk_col, cap, partial,        \
                                                  db ? partial_db : nullptr, out, accumulate, db);                     \
       RCD_LAUNCH_CHECK();                                                                                             \
