@@ -121,7 +121,7 @@ static __global__ void __launch_bounds__(kEmbThreads)
 // weight gradient) or, when `src` is given, coef(e) = csc_val[src[e]] looked up through the CSC->CSR permutation
 // (sparse part of the decoder weight gradient); db[c] += sum_e coef(e) when db is given.
 template <int VEC, int NV>
-static __global__ void __launch_bounds__(kEmbThreads)
+static __global__ void __launch_bounds__(kEmbThreads, (NV <= 1) ? 8 : 1)  // latency-bound gather: keep 8 CTAs per SM
     k_encoder_wgrad(const float* __restrict__ dA, int H, const int32_t* __restrict__ csc_ptr,
                     const int32_t* __restrict__ csc_row, const float* __restrict__ csc_val,
                     const int32_t* __restrict__ src, const float* __restrict__ row_inv_norm, int row0, int n, int tpr,
