@@ -42,6 +42,19 @@ def reduce_slab(slab, loss_slot, pg):
   loss_slot.copy_(tail[0:1].to(torch.float64) + tail[1:2].to(torch.float64))
 
 
+def timed_all_reduce(tag, tensor, op, pg):
+  """dist.all_reduce with the same optional CUDA-event timing as the C-ABI entry points (bench.py breakdown)."""
+  import torch.distributed as dist
+  if _native.PROFILE is not None and (_native.PROFILE == 'all' or tag in _native.PROFILE):
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    dist.all_reduce(tensor, op=op, group=pg)
+    end.record()
+    _native.TIMINGS.setdefault(tag, []).append((start, end))
+  else:
+    dist.all_reduce(tensor, op=op, group=pg)
+
+
 def shard_rows(pool_rows, global_step_rows, world, rank):
   """Row ranges of one collated pool for data-parallel training: the pool is cut into global steps of
   `global_step_rows` rows (the reference's `batch_size` slices, recoder/data.py:231-249) and every global step
@@ -824,7 +837,7 @@ class TrainEngine:
     self._wait_ready('en')
     call('rcd_ae_encoder_fwd', ptr(We), H, ptr(zero_bias), ptr(pool.row_ptr), ptr(pool.raw_items), ptr(pool.vals),
          ptr(pool.row_inv_norm), row0, rows, none, ptr(Zp), None, ldh)
-    dist.all_reduce(Zp, op=dist.ReduceOp.SUM, group=pg)
+    timed_all_reduce('allreduce_Z', Zp, dist.ReduceOp.SUM, pg)
     Z = b.get('Z', rows * H, torch.float32)
     Zb = b.get('Zb', rows * ldh, torch.bfloat16)
     call('rcd_bias_act', ptr(Zp), ptr(be), rows, H, self.act, ptr(Z), ptr(Zb), ldh)
@@ -839,7 +852,7 @@ class TrainEngine:
     call('rcd_sddmm', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bg), H, ptr(pool.row_ptr), ptr(pool.cols), ptr(pool.vals), row0,
          rows, self.loss_id, self.confidence, inv_b, ptr(o_nnz), ptr(corr), ptr(row_ref))
     if nll:
-      dist.all_reduce(row_ref, op=dist.ReduceOp.MAX, group=pg)
+      timed_all_reduce('allreduce_rowmax', row_ref, dist.ReduceOp.MAX, pg)
     stat_cols = self.lib.rcd_decoder_stat_cols(n)
     stat = b.get('stat', rows * stat_cols, torch.float32)
     call('rcd_decoder_fwd_loss', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bg), rows, n, H, self.loss_id, inv_b, ptr(row_ref),
@@ -849,7 +862,7 @@ class TrainEngine:
     if nll:
       ssum = b.get('stat_sum', rows, torch.float32)
       call('rcd_rowsum', ptr(stat), rows, stat_cols, stat_cols, ptr(ssum))
-      dist.all_reduce(ssum, op=dist.ReduceOp.SUM, group=pg)
+      timed_all_reduce('allreduce_rowsum', ssum, dist.ReduceOp.SUM, pg)
       stat, stat_ld, stat_n = ssum, 1, 1
     else:
       stat_ld = stat_n = stat_cols
@@ -879,7 +892,7 @@ class TrainEngine:
     dZ = b.get('dZp', rows * H + 4, torch.float32)
     self._dgrad(G, ldn, alpha, Wg, ldh, partials, splits, rows, n, H, Z, none, dZ, None)
     self._stash_loss(dZ, loss_slot)            # the loss shares ride in the tail of the dL/dZ all-reduce
-    dist.all_reduce(dZ, op=dist.ReduceOp.SUM, group=pg)
+    timed_all_reduce('allreduce_dZ', dZ, dist.ReduceOp.SUM, pg)
     loss_slot.copy_(dZ[-2:-1].to(torch.float64) + dZ[-1:].to(torch.float64))
     dA = b.get('dA', rows * H, torch.float32)
     call('rcd_act_grad', ptr(dZ), ptr(Z), rows * H, self.act, ptr(dA))
