@@ -333,7 +333,9 @@ def b200_arm(args, w):
         st['bytes0'] = dict(rdata.TRANSFER_BYTES)
         trainer.engine.join()
         ev0.record()
+        st['host_t0'] = time.perf_counter()
       elif step == W + K:
+        st['host_enqueue_ms'] = (time.perf_counter() - st['host_t0']) * 1e3 / K   # host time to ENQUEUE one step
         trainer.engine.join()   # the optimizer / exchange kernels of the last step run on the update stream
         ev1.record()
         torch.cuda.synchronize()
@@ -454,6 +456,7 @@ def b200_arm(args, w):
     'roofline': roofline,
     'cpu_baseline': cpu,
     'items_per_batch': n_avg,
+    'host_enqueue_ms_per_step': round(s_dev.get('host_enqueue_ms', 0.0), 4),
     'final_loss': s_dev['loss'],
     'kernels': kinds,
   }
