@@ -10,6 +10,7 @@ step, model.py:404).
 """
 import logging
 import os
+import time
 
 import numpy as np
 import torch
@@ -493,13 +494,19 @@ class Recoder(object):
     pools = iter(dataloader.pools())
     first = next(pools, None)
     nxt = launch(first) if first is not None else None
+    import time as _time
+    ht = self._host_timing = getattr(self, '_host_timing', {'wait': 0.0, 'launch': 0.0, 'step': 0.0, 'n': 0})
     while nxt is not None:
       pool, tpool = nxt
+      t0 = _time.perf_counter()
       collate_pool_finish(pool)
       if tpool is not None:
         collate_pool_finish(tpool)
+      t1 = _time.perf_counter()
       index = next(pools, None)
       nxt = launch(index) if index is not None else None
+      ht['wait'] += t1 - t0                      # blocked on the GPU (counts of the collated pool)
+      ht['launch'] += _time.perf_counter() - t1  # host time to enqueue the next pool's collate
       if self._ip is not None:   # every rank takes all rows of the global slice; the item axis is what is split
         for goff in range(0, pool.num_rows, gstep):
           grows = min(gstep, pool.num_rows - goff)
@@ -543,7 +550,10 @@ class Recoder(object):
       last_loss = None
       num_items = None
       for batch_itr, (pool, tpool, row0, rows, global_rows) in iterator:
+        _t0 = time.perf_counter()
         self.engine.train_step(pool, row0, rows, target_pool=tpool, global_rows=global_rows)
+        self._host_timing['step'] += time.perf_counter() - _t0   # host time to enqueue one step
+        self._host_timing['n'] += 1
         steps_this_epoch += 1
         num_items = (tpool or pool).n
         if self._sync_loss_every_step:

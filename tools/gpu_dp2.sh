@@ -18,7 +18,7 @@ for mode in ${DP_MODES:-p2p nccl}; do
 import json
 try:
   d=[json.loads(l) for l in open("gpurun_out/bench_c3_$tag.json") if l.startswith("{")][-1]
-  print('ms_per_step', round(d['ms_per_step'],4), 'host_enqueue', d.get('host_enqueue_ms_per_step'), 'users/s', round(d['value']), 'e2e', round(d['e2e']['value']), 'n', d['items_per_batch'])
+  print('ms_per_step', round(d['ms_per_step'],4), 'host', d.get('host_ms_per_step'), 'users/s', round(d['value']), 'e2e', round(d['e2e']['value']), 'n', d['items_per_batch'])
   print({k:v['ms_per_step'] for k,v in d['kernels'].items()})
 except Exception as ex:
   print('no json', ex)
