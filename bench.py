@@ -481,7 +481,8 @@ def main():
                   help='N>1: fused peer-memory reduce-scatter/Adam/all-gather kernel (p2p) or NCCL all-reduce + full Adam')
   ap.add_argument('--parallel', default='auto', choices=['auto', 'rows', 'items'],
                   help='N>1: split the users of the global batch (data parallel, gradient exchange per --dp-exchange) '
-                       'or the item axis (itempar.py); auto = items for the autoencoder configs, rows otherwise')
+                       'or the item axis (itempar.py); auto = items for the autoencoder configs at 2-4 GPUs, rows '
+                       'otherwise (the faster of the two as measured, profiles/README.md)')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--skip-e2e', action='store_true', help='profiling runs only: skip the host-staged leg')
   ap.add_argument('--no-profile', action='store_true', help='no CUDA-event kernel breakdown during warm-up')
@@ -489,7 +490,12 @@ def main():
   args = ap.parse_args()
   w = WORKLOADS[args.config]
   if args.parallel == 'auto':
-    args.parallel = 'items' if (w['model'] == 'ae' and int(os.environ.get('WORLD_SIZE', '1')) > 1) else 'rows'
+    # measured on C3 (profiles/README.md r01d): item-parallel wins at 2 and 4 GPUs (1.80 M / 2.85 M users/s against
+    # 1.46 M / 2.42 M for row-parallel + fused peer-memory exchange); at 8 GPUs the row-parallel exchange (NVLS
+    # multicast) measured 4.66 M against 2.5-3.3 M for the item-parallel mode, whose four NCCL collectives per step
+    # absorb the skew between eight ranks
+    world_env = int(os.environ.get('WORLD_SIZE', '1'))
+    args.parallel = 'items' if (w['model'] == 'ae' and 1 < world_env <= 4) else 'rows'
   if args.impl == 'reference':
     reference_arm(args, w)
   else:
