@@ -249,7 +249,7 @@ int rcd_scatter_pos(const int64_t* ids, int n, int32_t* pos, int reset, void* st
  *     rcd_p2p_export/open/close : 64-byte IPC handle of an allocation / mapping of a peer's handle
  *     rcd_p2p_barrier      : stream-ordered barrier of all ranks; `flags` = per-rank uint32[RCD_MAX_PEERS] arrays,
  *                            `seq` strictly increasing per call; bad_flag |= 4 if a peer does not arrive in timeout_s
- *     rcd_p2p_reduce       : dst[i] = sum over ranks q (ascending) of src_q[offset + i], i < count (fp32)
+ *     rcd_p2p_reduce       : dst[i] = sum (or max) over ranks q (ascending) of src_q[offset + i], i < count (fp32)
  *     rcd_adam_step_p2p    : fused reduce-scatter -> Adam -> all-gather.  This rank owns table rows
  *                            [row_begin, row_end): g = sum_q grads_q[pos[row], :] (rank order; only rank
  *                            pos[row]/grad_block_rows when grad_block_rows > 0), torch.optim.Adam update of the local
@@ -269,8 +269,14 @@ int rcd_p2p_open(const unsigned char* handle_host, void** out_host);
 int rcd_p2p_close(void* p);
 int rcd_p2p_barrier(void* const* flags_host, int rank, int world, unsigned int seq, int32_t* bad_flag,
                     double timeout_s, void* stream);
-int rcd_p2p_reduce(const float* const* src_host, int world, long long offset, long long count, float* dst,
+#define RCD_REDUCE_SUM 0
+#define RCD_REDUCE_MAX 1
+int rcd_p2p_reduce(const float* const* src_host, int world, long long offset, long long count, float* dst, int op,
                    void* stream);
+/* two-shot all-reduce (sum, fp32) in place over a buffer every rank has mapped (count a multiple of 4, 16-byte aligned):
+ * this rank reduces its 1/world slice (multimem.ld_reduce through `mc`, the multicast address, or plain peer loads when
+ * mc == NULL) and stores the result into every rank's copy.  Bracket with rcd_p2p_barrier. */
+int rcd_p2p_allreduce(float* const* bufs_host, float* mc, long long count, int rank, int world, void* stream);
 int rcd_adam_step_p2p(float* const* tables_host, float* m, float* v, long long row_begin, long long row_end, int H,
                       const float* const* grads_host, int ldg, const int32_t* pos, int grad_block_rows, int rank,
                       int world, double lr, double beta1, double beta2, double eps, double weight_decay, long long t,

@@ -66,7 +66,8 @@ _SIGNATURES = {
   'rcd_p2p_open': (c_int, [_P, _P]),
   'rcd_p2p_close': (c_int, [_P]),
   'rcd_p2p_barrier': (c_int, [_P, c_int, c_int, ctypes.c_uint, _P, c_double, _P]),
-  'rcd_p2p_reduce': (c_int, [_P, c_int, c_longlong, c_longlong, _P, _P]),
+  'rcd_p2p_reduce': (c_int, [_P, c_int, c_longlong, c_longlong, _P, c_int, _P]),
+  'rcd_p2p_allreduce': (c_int, [_P, _P, c_longlong, c_int, c_int, _P]),
   'rcd_adam_step_p2p': (c_int, [_P, _P, _P, c_longlong, c_longlong, c_int, _P, c_int, _P, c_int, c_int, c_int,
                                 c_double, c_double, c_double, c_double, c_double, c_longlong, _P, _P, _P]),
   'rcd_adagrad_step': (c_int, [_P, _P, c_longlong, c_int, _P, c_int, _P, c_double, c_double, c_double, _P]),

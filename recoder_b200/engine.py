@@ -259,6 +259,7 @@ class TrainEngine:
     self.tied = tied
     self.p2p = p2p                # p2p.P2PContext: exchange through peer memory instead of an NCCL all-reduce
     self.ip = item_parallel       # itempar.ItemParallel: every rank sees all rows, the item axis is sharded
+    self._ip_shared = None
     self._slab_shared = None
     import os
     self.overlap = os.environ.get('RCD_OVERLAP', '1') != '0'
@@ -655,7 +656,7 @@ class TrainEngine:
   def _p2p_reduce(self, name, offset, count):
     """Sum over ranks of slab[offset : offset+count] into a private buffer (small replicated tensors)."""
     out = self.buf.get(name, count, torch.float32)
-    call('rcd_p2p_reduce', self._slab_shared.ptr_table(), self.p2p.world, int(offset), int(count), ptr(out))
+    call('rcd_p2p_reduce', self._slab_shared.ptr_table(), self.p2p.world, int(offset), int(count), ptr(out), 0)
     return out
 
   def _reduce_slab(self, slab, loss_slot):
@@ -800,6 +801,52 @@ class TrainEngine:
     self.opt.step_param(enb_name, dbe, 1)
     self._step_inner(inner_grads, inner)
 
+  # --- item-parallel collectives -----------------------------------------------------------------------------------
+  def _ip_buffers(self, rows, H):
+    """Buffers that cross ranks in the item-parallel step — encoder partial sums Zp [rows*H], dL/dZ (+ loss tail),
+    softmax reference and row sums [rows] — in peer-mapped memory when the peer-memory collectives are on."""
+    f32 = torch.float32
+    nz, r4 = _round_up(rows * H, 4), _round_up(rows, 4)
+    ctx = self.ip.p2p
+    if ctx is None:
+      b = self.buf
+      return {'Zp': b.get('Zp', nz, f32), 'dZ': b.get('dZp', nz + 4, f32), 'row_ref': b.get('row_ref', rows, f32),
+              'ssum': b.get('stat_sum', rows, f32), 'shared': None, 'off': (0, 0, 0, 0)}
+    need = 4 * (nz + nz + 4 + 2 * r4) + 64
+    if self._ip_shared is None or self._ip_shared.nbytes < need:
+      torch.cuda.synchronize()          # collective: every rank sees the same shapes at the same step
+      self._ip_shared = ctx.shared(need)
+    sh = self._ip_shared
+    o_z, o_dz = 0, 4 * nz
+    o_ref = o_dz + 4 * (nz + 4)
+    o_sum = o_ref + 4 * r4
+    return {'Zp': sh.view(f32, nz, o_z), 'dZ': sh.view(f32, nz + 4, o_dz), 'row_ref': sh.view(f32, rows, o_ref),
+            'ssum': sh.view(f32, rows, o_sum), 'shared': sh, 'off': (o_z, o_dz, o_ref, o_sum)}
+
+  def _ip_allreduce(self, tag, t, shared, off):
+    """In-place sum of `t` over ranks: two-shot peer-memory all-reduce between two barriers, or NCCL."""
+    import torch.distributed as dist
+    if shared is None:
+      timed_all_reduce(tag, t, dist.ReduceOp.SUM, self.ip.pg)
+      return
+    ctx = self.ip.p2p
+    ctx.barrier(self.bad_flag)
+    call('rcd_p2p_allreduce', shared.ptr_table(off), shared.mc(off), int(t.numel()), ctx.rank, ctx.world)
+    ctx.barrier(self.bad_flag)
+
+  def _ip_reduce_small(self, tag, t, shared, off, op_max):
+    """Sum / max of a [rows] vector over ranks; returns the tensor holding the result (a private buffer when the
+    peers read `t` directly, `t` itself with NCCL)."""
+    import torch.distributed as dist
+    if shared is None:
+      timed_all_reduce(tag, t, dist.ReduceOp.MAX if op_max else dist.ReduceOp.SUM, self.ip.pg)
+      return t
+    ctx = self.ip.p2p
+    out = self.buf.get(tag + '_out', t.numel(), torch.float32)
+    ctx.barrier(self.bad_flag)
+    call('rcd_p2p_reduce', shared.ptr_table(off), ctx.world, 0, int(t.numel()), ptr(out), 1 if op_max else 0)
+    return out
+
   # ------------------------------------------------------------------------------------------------------
   def _ae_step_items(self, pool, row0, rows, inv_b, loss_slot, train):
     """Item-parallel autoencoder step (itempar.py): `pool` is the collate of the GLOBAL batch over this rank's item
@@ -829,7 +876,9 @@ class TrainEngine:
     call('rcd_gather_vec', ptr(bd), ptr(pool.items), n, ptr(bg))
 
     # encoder: partial sums over this rank's items -> all-reduce -> bias + activation
-    Zp = b.get('Zp', rows * H, torch.float32)
+    xb = self._ip_buffers(rows, H)
+    sh, (o_z, o_dz, o_ref, o_sum) = xb['shared'], xb['off']
+    Zp = xb['Zp']
     zero_bias = b.get('zero_bias', H, torch.float32)
     if not getattr(self, '_zero_bias_init', False):
       zero_bias.zero_()
@@ -837,7 +886,7 @@ class TrainEngine:
     self._wait_ready('en')
     call('rcd_ae_encoder_fwd', ptr(We), H, ptr(zero_bias), ptr(pool.row_ptr), ptr(pool.raw_items), ptr(pool.vals),
          ptr(pool.row_inv_norm), row0, rows, none, ptr(Zp), None, ldh)
-    timed_all_reduce('allreduce_Z', Zp, dist.ReduceOp.SUM, pg)
+    self._ip_allreduce('allreduce_Z', Zp, sh, o_z)
     Z = b.get('Z', rows * H, torch.float32)
     Zb = b.get('Zb', rows * ldh, torch.bfloat16)
     call('rcd_bias_act', ptr(Zp), ptr(be), rows, H, self.act, ptr(Z), ptr(Zb), ldh)
@@ -848,11 +897,11 @@ class TrainEngine:
     G = b.get('G', rows * ldn, torch.bfloat16)
     o_nnz = b.get('o_nnz', nnz, torch.float32)
     corr = b.get('corr', nnz, torch.float32)
-    row_ref = b.get('row_ref', rows, torch.float32) if nll else None
+    row_ref = xb['row_ref'] if nll else None
     call('rcd_sddmm', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bg), H, ptr(pool.row_ptr), ptr(pool.cols), ptr(pool.vals), row0,
          rows, self.loss_id, self.confidence, inv_b, ptr(o_nnz), ptr(corr), ptr(row_ref))
     if nll:
-      timed_all_reduce('allreduce_rowmax', row_ref, dist.ReduceOp.MAX, pg)
+      row_ref = self._ip_reduce_small('allreduce_rowmax', row_ref, sh, o_ref, True)
     stat_cols = self.lib.rcd_decoder_stat_cols(n)
     stat = b.get('stat', rows * stat_cols, torch.float32)
     call('rcd_decoder_fwd_loss', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bg), rows, n, H, self.loss_id, inv_b, ptr(row_ref),
@@ -860,9 +909,9 @@ class TrainEngine:
     alpha = b.get('alpha', rows, torch.float32) if nll else None
     Zs = b.get('Zs', rows * ldh, torch.bfloat16) if (nll and train) else None
     if nll:
-      ssum = b.get('stat_sum', rows, torch.float32)
+      ssum = xb['ssum']
       call('rcd_rowsum', ptr(stat), rows, stat_cols, stat_cols, ptr(ssum))
-      timed_all_reduce('allreduce_rowsum', ssum, dist.ReduceOp.SUM, pg)
+      ssum = self._ip_reduce_small('allreduce_rowsum', ssum, sh, o_sum, False)
       stat, stat_ld, stat_n = ssum, 1, 1
     else:
       stat_ld = stat_n = stat_cols
@@ -889,10 +938,10 @@ class TrainEngine:
       self.opt.step_param(deb_name, dbd, 1, pos=pool.pos)
       self._mark_ready('de')
 
-    dZ = b.get('dZp', rows * H + 4, torch.float32)
+    dZ = xb['dZ']
     self._dgrad(G, ldn, alpha, Wg, ldh, partials, splits, rows, n, H, Z, none, dZ, None)
     self._stash_loss(dZ, loss_slot)            # the loss shares ride in the tail of the dL/dZ all-reduce
-    timed_all_reduce('allreduce_dZ', dZ, dist.ReduceOp.SUM, pg)
+    self._ip_allreduce('allreduce_dZ', dZ, sh, o_dz)
     loss_slot.copy_(dZ[-2:-1].to(torch.float64) + dZ[-1:].to(torch.float64))
     dA = b.get('dA', rows * H, torch.float32)
     call('rcd_act_grad', ptr(dZ), ptr(Z), rows * H, self.act, ptr(dA))

@@ -43,6 +43,7 @@ class ItemParallel:
     self.world = dist.get_world_size(pg)
     self.rank = dist.get_rank(pg)
     self.sharded = {}     # parameter name -> local shard tensor
+    self.p2p = None       # p2p.P2PContext: the step's four collectives run as peer-memory kernels instead of NCCL
 
   def local_rows(self, rows):
     return (rows - self.rank + self.world - 1) // self.world

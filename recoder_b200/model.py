@@ -203,7 +203,10 @@ class Recoder(object):
             and roles['dropout_prob'] == 0.0 and not self.model._sparse_param_names())
       if ok:
         from .itempar import ItemParallel
+        from .p2p import P2PContext
         self._ip = ItemParallel(pg)
+        if os.environ.get('RCD_IP_COLLECTIVES', 'p2p') != 'nccl' and P2PContext.available(pg):
+          self._ip.p2p = P2PContext(pg)
         for role in ('en_w', 'de_w', 'de_b'):
           name, full = roles[role]
           self._ip.shard(name, full)

@@ -29,9 +29,7 @@ def run(kind, loss, mode, pg, batch, steps, matrix, U, I, H, seed_params):
   if ':' in mode:   # 'p2p:ipc' = CUDA-IPC unicast ld/st, 'p2p:symm' = symmetric memory + NVLS multicast when available
     mode, backend = mode.split(':')
     os.environ['RCD_P2P_BACKEND'] = backend
-  parallel = 'rows'
-  if mode == 'items':   # item-parallel: every rank sees all rows, the item axis is sharded
-    mode, parallel = 'nccl', 'items'
+XX
   tr = Recoder(model=model, use_cuda=True, optimizer_type='adam', loss=loss, process_group=pg,
                dp_exchange=mode if mode != 'single' else 'nccl', parallel=parallel)
   ds = RecommendationDataset(matrix)
@@ -79,9 +77,10 @@ def main():
     assert not nccl[3]
     variants = [('nccl', nccl), ('p2p-ipc', p2p), ('p2p-auto', p2p_mc)]
     if kind == 'ae':
-      items = run(kind, loss, 'items', None, B, steps, matrix, U, I, H, 3)
-      assert not items[3]
-      variants.append(('items', items))
+      for tag in ('items', 'items-mc', 'items-nccl'):
+        got = run(kind, loss, tag, None, B, steps, matrix, U, I, H, 3)
+        assert not got[3]
+        variants.append((tag, got))
     for tag, got in variants:
       # every rank holds the same replica
       for n, t in got[0].items():
