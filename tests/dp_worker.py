@@ -29,7 +29,17 @@ def run(kind, loss, mode, pg, batch, steps, matrix, U, I, H, seed_params):
   if ':' in mode:   # 'p2p:ipc' = CUDA-IPC unicast ld/st, 'p2p:symm' = symmetric memory + NVLS multicast when available
     mode, backend = mode.split(':')
     os.environ['RCD_P2P_BACKEND'] = backend
-XX
+  parallel = 'rows'
+  os.environ.pop('RCD_IP_COLLECTIVES', None)
+  os.environ.pop('RCD_P2P_MULTICAST', None)
+  if mode.startswith('items'):   # item-parallel: every rank sees all rows, the item axis is sharded
+    # 'items' = peer-memory collectives (unicast below 4 ranks), 'items-mc' = the same through NVLS multicast,
+    # 'items-nccl' = NCCL all-reduces
+    if mode == 'items-nccl':
+      os.environ['RCD_IP_COLLECTIVES'] = 'nccl'
+    if mode == 'items-mc':
+      os.environ['RCD_P2P_MULTICAST'] = '1'
+    mode, parallel = 'nccl', 'items'
   tr = Recoder(model=model, use_cuda=True, optimizer_type='adam', loss=loss, process_group=pg,
                dp_exchange=mode if mode != 'single' else 'nccl', parallel=parallel)
   ds = RecommendationDataset(matrix)
