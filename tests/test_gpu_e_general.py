@@ -160,3 +160,24 @@ def test_philox_dropout_trains_and_differs_between_steps():
   assert len({round(x, 6) for x in losses}) == 3, losses   # same batch, same weights, different masks
   clean = eng.eval_loss(pool, 0, B)                         # eval mode: no noise, no dropout
   assert abs(clean - eng.eval_loss(pool, 0, B)) < 1e-9
+
+
+def test_chunked_heavy_columns_match_single_pass():
+  """Tall slices cut columns with more than 128 entries into chunks (k_heavy_setup / k_heavy_reduce); the result must
+  equal the single-pass kernel (same fp32 terms, different association only inside the heavy columns)."""
+  U, I, nnz, B, H = 3000, 4000, 80, 2048, 96       # item 0 sits in ~70 % of the rows: ~1400 entries in its column
+  indptr, indices, data = synthetic_csr(U, I, nnz, seed=8)
+  params = O.init_ae_params(I, [H], seed=2)
+  ds = device_dataset(indptr, indices, data, I)
+  pool = collate_pool(ds.device_csr(), np.arange(B), True)
+  got = []
+  for threshold in (1 << 30, 0):
+    model = make_model('ae', I, U, [H], 'tanh', {k: v.numpy() for k, v in params.items()})
+    eng = make_engine(model, 'logloss', 0.0, 'adam', 1e-3, 0.0, _native.GEMM_TCGEN05)
+    eng.HEAVY_COLUMN_ROWS = threshold
+    eng.train_step(pool, 0, B)
+    loss = float(eng.losses(1)[0])
+    got.append((loss, {k: eng.last[k].detach().cpu().numpy().copy() for k in ('dWe', 'dWd', 'dbd', 'dbe')}))
+  assert got[0][0] == got[1][0]
+  for k in got[0][1]:
+    assert rel_err(got[1][1][k], got[0][1][k]) < 1e-6, k
