@@ -337,6 +337,10 @@ def b200_arm(args, w):
         trainer.engine.join()
         ev0.record()
         st['host_t0'] = time.perf_counter()
+        ht = getattr(trainer, '_host_timing', None)
+        if ht is not None:     # host-side accounting covers the timed region only
+          for k in ht:
+            ht[k] = 0
       elif step == W + K:
         st['host_enqueue_ms'] = (time.perf_counter() - st['host_t0']) * 1e3 / K   # host time to ENQUEUE one step
         trainer.engine.join()   # the optimizer / exchange kernels of the last step run on the update stream
@@ -352,7 +356,17 @@ def b200_arm(args, w):
                   sync_loss_every_step=sync_loss)
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
+    ht = getattr(trainer, '_host_timing', None)
+    host = {k: round(v * 1e3 / max(ht['n'], 1), 4) for k, v in ht.items() if k != 'n'} if ht else {}
+    st['host'] = host
     if world > 1:
+      # per-rank view of the timed region (device ms/step, host ms/step enqueueing steps, enqueueing the next collate,
+      # blocked on the GPU): a rank whose host column approaches the device column is what the others wait for
+      mine = torch.tensor([ms / K, host.get('step', 0.0), host.get('launch', 0.0), host.get('wait', 0.0)],
+                          device='cuda', dtype=torch.float64)
+      every = [torch.zeros_like(mine) for _ in range(world)]
+      dist.all_gather(every, mine)
+      st['per_rank'] = [[round(float(x), 4) for x in t.tolist()] for t in every]
       t = torch.tensor([ms], device='cuda', dtype=torch.float64)
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
       ms = float(t.item())
@@ -363,9 +377,6 @@ def b200_arm(args, w):
       st['dom_launches_per_step'] = len(evs) / K
     _native.PROFILE = None
     _native.TIMINGS.clear()
-    ht = getattr(trainer, '_host_timing', None)
-    if ht and ht['n']:
-      st['host'] = {k: round(v * 1e3 / ht['n'], 4) for k, v in ht.items() if k != 'n'}
     st['loss'] = float(trainer.engine.losses(1)[0])
     st['params'] = sum(p.numel() for p in model.parameters())
     del trainer, model, ds
@@ -482,7 +493,8 @@ def b200_arm(args, w):
     'roofline': roofline,
     'cpu_baseline': cpu,
     'items_per_batch': n_avg,
-    'host_ms_per_step': s_dev.get('host'),   # wait = blocked on the GPU; launch / step = enqueue work
+    'host_ms_per_step': s_dev.get('host'),   # timed region; wait = blocked on the GPU, launch / step = enqueue work
+    'per_rank_ms': s_dev.get('per_rank'),    # N>1: [device ms/step, host step, host launch, host wait] per rank
     'final_loss': s_dev['loss'],
     'kernels': kinds,
   }

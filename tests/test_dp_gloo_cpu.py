@@ -76,3 +76,53 @@ def test_shard_rows_partition(P, g, world):
   assert all(0 <= r < P for r in covered)
   dropped = P - len(covered)
   assert dropped < world * ((P + g - 1) // g)
+
+
+# ---- item-parallel host logic (recoder_b200/itempar.py) -----------------------------------------------------------
+def _items_worker(rank, world, port, out):
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  try:
+    from recoder_b200.itempar import ItemParallel
+    ip = ItemParallel(dist.group.WORLD)
+    rows = 11                      # not a multiple of the world size: the last shard is shorter
+    full = torch.arange(rows * 3, dtype=torch.float32).view(rows, 3)
+    local = ip.shard('table', full)
+    ok_shard = torch.equal(local, full[rank::world]) and ip.local_rows(rows) == local.shape[0]
+    local.mul_(2.0)                # every rank updates only its own rows
+    back = ip.gather_full(local, rows)
+    ok_gather = torch.equal(back, full * 2.0)
+    target = {'table': torch.zeros_like(full)}
+    ip.sync_to_full(target)
+    out[rank] = (ok_shard, ok_gather, torch.equal(target['table'], full * 2.0))
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_item_shards_gather_back(world):
+  mgr = mp.Manager()
+  out = mgr.dict()
+  mp.spawn(_items_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+  assert all(all(out[r]) for r in range(world)), dict(out)
+
+
+def test_shard_matrix_by_items_partitions_the_matrix():
+  from recoder_b200.itempar import shard_matrix_by_items
+  from recoder_b200.synth import synthetic_csr, to_scipy
+  indptr, indices, data = synthetic_csr(400, 257, 25, seed=3)
+  data = (1 + np.arange(len(data)) % 5).astype(np.float32)           # ratings, so the row constants are not trivial
+  m = to_scipy(indptr, indices, data, 257)
+  dense = m.toarray()
+  world = 4
+  total = 0
+  for r in range(world):
+    local, inv_norm, row_sum = shard_matrix_by_items(m, r, world)
+    assert local.shape == (400, len(range(r, 257, world)))
+    assert np.array_equal(local.toarray(), dense[:, r::world])        # columns r, r+R, ... renumbered 0, 1, ...
+    assert np.all(np.diff(local.indices[local.indptr[5]:local.indptr[6]]) > 0)   # stored order kept (sorted)
+    np.testing.assert_allclose(inv_norm, 1.0 / np.maximum(np.linalg.norm(dense, axis=1), 1e-12), rtol=1e-6)
+    np.testing.assert_allclose(row_sum, dense.sum(axis=1), rtol=1e-6)
+    total += local.nnz
+  assert total == m.nnz
