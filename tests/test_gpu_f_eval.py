@@ -155,3 +155,39 @@ def test_model_golden_metrics(sparse, exp_recall_20, exp_recall_50, exp_ndcg_100
   trainer = Recoder(model=model, use_cuda=True, optimizer_type='adam', loss='logloss')
   trainer.init_from_model_file(state_file)
   check(trainer)
+
+
+def test_resume_from_reference_checkpoint_matches_reference():
+  """`init_from_model_file` on a checkpoint written by the unmodified reference, optimizer state hand-over included:
+  the next training step must give the loss, gradients, parameters and Adam state the reference itself computed after
+  resuming from the same file (tests/golden/make_checkpoint_fixture.py)."""
+  from recoder_b200.data import collate_pool
+  z = np.load(os.path.join(GOLDEN_DIR, 'ref_checkpoint_resume.npz'))
+  lr, wd, batch = float(z['hyper'][0]), float(z['hyper'][1]), int(z['hyper'][2])
+  matrix = sp.csr_matrix((z['csr_data'], z['csr_indices'], z['csr_indptr']))
+  ds = RecommendationDataset(matrix)
+  trainer = Recoder(model=DynamicAutoencoder(), use_cuda=True, optimizer_type='sgd', loss='mse')   # overwritten by the file
+  trainer.init_from_model_file(os.path.join(GOLDEN_DIR, 'ref_checkpoint_epoch_2.model'))
+  assert trainer.current_epoch == int(z['current_epoch']) and trainer.optimizer_type == 'adam' and trainer.loss == 'logloss'
+  trainer._Recoder__init_training(train_dataset=ds, lr=lr, weight_decay=wd)
+  pool = collate_pool(ds.device_csr(), z['users'], True)
+  assert np.array_equal(pool.items.cpu().numpy(), z['items'])
+  trainer.engine.train_step(pool, 0, batch)
+  assert float(trainer.engine.losses(1)[0]) == pytest.approx(float(z['loss']), rel=1e-3)
+  items = z['items']
+  names = [str(n) for n in z['param_names']]
+  grads = {'en_embedding_layer.weight': trainer.engine.last['dWe'], 'de_embedding_layer.weight': trainer.engine.last['dWd']}
+  for n, g in grads.items():
+    want = z['grad/' + n][items]
+    got = g.detach().cpu().numpy()
+    assert np.linalg.norm(got) == pytest.approx(np.linalg.norm(want), rel=3e-3), n
+  params = dict(trainer.model.named_parameters())
+  for n in names:
+    got = params[n].detach().cpu().numpy()
+    want = z['param/' + n]
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 2e-2, n
+    st = trainer.optimizer.states[n]
+    assert st.step == int(z['step/' + n])                       # the step counter continued from the checkpoint
+    m_want, v_want = z['exp_avg/' + n], z['exp_avg_sq/' + n]
+    assert np.linalg.norm(st.m.cpu().numpy() - m_want) / np.linalg.norm(m_want) < 2e-2, n
+    assert np.linalg.norm(st.v.cpu().numpy() - v_want) / np.linalg.norm(v_want) < 2e-2, n
