@@ -506,7 +506,7 @@ def b200_arm(args, w):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=30)
+  ap.add_argument('--steps', type=int, default=100)
   ap.add_argument('--warmup', type=int, default=5)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--config', default='c3', choices=sorted(WORKLOADS))

@@ -263,7 +263,6 @@ class TrainEngine:
     self._slab_shared = None
     import os
     self.overlap = os.environ.get('RCD_OVERLAP', '1') != '0'
-    self.late_update = os.environ.get('RCD_LATE_UPDATE', '0') == '1'   # experiment: decoder-side update at the end
     self._side = None
     self._aux = None
     self._ready = {}
@@ -744,7 +743,7 @@ class TrainEngine:
     self._wgrad(G, ldn, Zs, ldh, Y, csc_t, corr, alpha, rows, n, H, dWd, dbd)
     self.last = {'n': n, 'n_in': n_in, 'dWe': dWe.view(n_in, H), 'dWd': dWd.view(n, H), 'dbd': dbd, 'dbe': dbe,
                  'inner': inner_grads, 'inner_layout': inner}
-    sequential = self.tied or (self.pg is not None and self.p2p is None) or (self.late_update and self.pg is None)
+    sequential = self.tied or (self.pg is not None and self.p2p is None)
     if not sequential:
       with self._update_stream():
         self._keep_for_side(pool, tpool)
