@@ -246,11 +246,14 @@ class TrainEngine:
   LOSS_RING = 4096
 
   def __init__(self, kind, params, loss, confidence, activation, optimizer: Optimizer, gemm_engine=None,
-               process_group=None, tied=False, p2p=None, item_parallel=None):
+               process_group=None, tied=False, p2p=None, item_parallel=None, loss_module=None):
     _native.require_cuda()
     self.kind = kind
     self.params = params          # dict of role -> (name, tensor)
-    self.loss_id = _native.LOSS_IDS[loss]
+    self.loss_module = loss_module   # kind 'custom': any nn.Module with sum reduction (recoder/model.py:88-89)
+    self.loss_id = _native.LOSS_IDS[loss] if loss != 'custom' else -1
+    if loss == 'custom' and loss_module is None:
+      raise ValueError("loss kind 'custom' needs the loss module")
     self.confidence = float(confidence)
     self.act = _native.ACT_IDS[activation]
     self.opt = optimizer
@@ -424,6 +427,8 @@ class TrainEngine:
     b = self.buf
     ldn = _round_up(n, 8)
     nnz = max(int(tpool.row_ptr_host[row0 + rows] - tpool.row_ptr_host[row0]), 1)
+    if self.loss_module is not None:
+      return self._custom_loss(Zb, ldh, Wg, bias_g, rows, n, H, inv_b, tpool, row0, loss_slot, train, ldn, nnz)
     nll = self.loss_id == _native.LOSS_IDS['logloss']
     G = b.get('G', rows * ldn, torch.bfloat16)
     o_nnz = b.get('o_nnz', nnz, torch.float32)
@@ -441,6 +446,36 @@ class TrainEngine:
          ptr(row_ref), ptr(tpool.row_sum), ptr(tpool.row_ptr), ptr(tpool.vals), ptr(o_nnz), row0, ptr(alpha),
          ptr(Zf32), H, ptr(Zs), ldh, ptr(loss_slot), ptr(self.bad_flag), 0)
     return G, ldn, corr, alpha, (Zs if Zs is not None else Zb)
+
+  def _custom_loss(self, Zb, ldh, Wg, bias_g, rows, n, H, inv_b, tpool, row0, loss_slot, train, ldn, nnz):
+    """Generic loss path for user-supplied `nn.Module`s (sum reduction): fp32 logits [rows, n] from the tcgen05 GEMM,
+    the dense target scattered from the pool's CSR, loss and dL/dlogits through torch autograd (the module is opaque),
+    dL/dlogits rounded to bf16 for the same backward GEMMs as the fused losses.  Materialises three [rows, n] fp32
+    matrices, like the reference does (recoder/model.py:457-458, 473-484) — the price of an arbitrary module."""
+    b = self.buf
+    ldo = ldn
+    O = b.get('custom_O', rows * ldo, torch.float32).view(rows, ldo)
+    call('rcd_decoder_fwd', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bias_g), rows, n, H, None, ptr(O), ldo, None, None,
+         _native.GEMM_TCGEN05)
+    T = b.get('custom_T', rows * n, torch.float32).view(rows, n)
+    T.zero_()
+    lo, hi = int(tpool.row_ptr_host[row0]), int(tpool.row_ptr_host[row0 + rows])
+    if hi > lo:
+      coo = b.get('custom_coo', 2 * (hi - lo), torch.int64).view(2, hi - lo)
+      call('rcd_collate_coo', ptr(tpool.row_ptr), ptr(tpool.cols), int(row0), int(rows), ptr(coo))
+      T[coo[0], coo[1]] = tpool.vals[lo:hi]
+    logits = O[:, :n].detach().requires_grad_(train)
+    with torch.enable_grad():
+      loss = self.loss_module(logits, T) * inv_b                      # `/ B` of recoder/model.py:483-484
+      if train:
+        loss.backward()
+    loss_slot.add_(loss.detach().to(torch.float64).reshape(1))
+    G = b.get('G', rows * ldn, torch.bfloat16)
+    corr = b.get('corr', nnz, torch.float32)
+    if train:
+      call('rcd_f32_to_bf16_rows', ptr(logits.grad.contiguous()), rows, n, ptr(G), ldn)
+      corr.zero_()                                                    # the whole gradient is in G: no sparse part
+    return G, ldn, corr, None, Zb
 
   def _sparse_dgrad(self, corr, W_master, tpool, row0, rows, n, H):
     """fp32 sparse part of dZ (reads the MASTER table, so it is issued before that table's optimizer update).

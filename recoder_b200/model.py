@@ -127,28 +127,32 @@ class Recoder(object):
     self.__model_initialized = True
 
   def __loss_spec(self):
-    """Resolves `self.loss` like `__init_loss_module` (reference model.py:87-99) into (kind, confidence)."""
+    """Resolves `self.loss` like `__init_loss_module` (reference model.py:87-99) into (kind, confidence, module).
+    'mse' / 'logloss' / 'logistic' with sum reduction are fused into the decoder GEMM's epilogue; any other
+    `nn.Module` (the reference accepts every module with sum reduction, model.py:36-37, 88-89) takes the generic
+    path: dense fp32 logits from the tcgen05 GEMM, the module and its gradient through torch autograd, then the
+    same backward kernels (kind 'custom')."""
     loss = self.loss
     if isinstance(loss, torch.nn.Module):
-      if isinstance(loss, MSELoss):
-        return 'mse', float(loss.confidence)
-      if isinstance(loss, MultinomialNLLLoss):
-        return 'logloss', 0.0
-      if isinstance(loss, BCEWithLogitsLoss):
-        return 'logistic', 0.0
-      raise NotImplementedError('custom loss modules need dense logits and autograd; the B200 path fuses '
-                                "'mse', 'logistic' and 'logloss' (got %s)" % type(loss).__name__)
+      if isinstance(loss, MSELoss) and loss.reduction == 'sum':
+        return 'mse', float(loss.confidence), None
+      if isinstance(loss, MultinomialNLLLoss) and loss.reduction == 'sum':
+        return 'logloss', 0.0, None
+      if (isinstance(loss, BCEWithLogitsLoss) and loss.reduction == 'sum' and loss.weight is None
+          and loss.pos_weight is None):
+        return 'logistic', 0.0, None
+      return 'custom', 0.0, loss
     elif loss == 'logistic':
       if self.loss_params:
-        raise NotImplementedError('BCEWithLogitsLoss extra parameters are not supported on the B200 path')
-      return 'logistic', 0.0
+        return 'custom', 0.0, BCEWithLogitsLoss(reduction='sum', **self.loss_params)   # model.py:91
+      return 'logistic', 0.0, None
     elif loss == 'mse':
       unknown = set(self.loss_params) - {'confidence'}
       if unknown:
         raise TypeError("__init__() got an unexpected keyword argument '%s'" % sorted(unknown)[0])
-      return 'mse', float(self.loss_params.get('confidence', 0))
+      return 'mse', float(self.loss_params.get('confidence', 0)), None
     elif loss == 'logloss':
-      return 'logloss', 0.0
+      return 'logloss', 0.0, None
     elif loss is None:
       raise ValueError('No loss function defined')
     else:
@@ -200,7 +204,8 @@ class Recoder(object):
     if self.parallel == 'items':
       kind, roles, _, tied = self.model._engine_spec()
       ok = (kind == 'ae' and not tied and not roles['enc_layers'] and roles['noise_prob'] == 0.0
-            and roles['dropout_prob'] == 0.0 and not self.model._sparse_param_names())
+            and roles['dropout_prob'] == 0.0 and not self.model._sparse_param_names()
+            and self.__loss_spec()[0] != 'custom')
       if ok:
         from .itempar import ItemParallel
         from .p2p import P2PContext
@@ -271,13 +276,15 @@ class Recoder(object):
       for role in ('en_w', 'de_w', 'de_b'):
         name, _ = roles[role]
         roles[role] = (name, self._ip.sharded[name])
-    loss_kind, confidence = self.__loss_spec()
+    loss_kind, confidence, loss_module = self.__loss_spec()
+    if loss_module is not None:
+      loss_module = loss_module.to(self.device)
     pg = self.__resolve_pg()
     for name, buf in getattr(self, '_p2p_buffers', {}).items():
       self.optimizer.states[name].shared = buf
     self.engine = TrainEngine(kind, roles, loss_kind, confidence, activation, self.optimizer,
                               gemm_engine=self.gemm_engine, process_group=pg, tied=tied, p2p=self._p2p,
-                              item_parallel=self._ip)
+                              item_parallel=self._ip, loss_module=loss_module)
 
   def init_from_model_file(self, model_file):
     """

@@ -32,6 +32,9 @@ def make_engine(model, loss, confidence, opt_type, lr, wd, gemm_engine):
   kind, roles, act, tied = model._engine_spec()
   named = [(n, p.data) for n, p in model.named_parameters()]
   opt = Optimizer(named, opt_type, lr, wd, sparse_names=model._sparse_param_names())
+  if isinstance(loss, torch.nn.Module):   # user-supplied module: the generic (autograd) loss path
+    return TrainEngine(kind, roles, 'custom', confidence, act, opt, gemm_engine=gemm_engine, tied=tied,
+                       loss_module=loss.to('cuda'))
   return TrainEngine(kind, roles, loss, confidence, act, opt, gemm_engine=gemm_engine, tied=tied)
 
 

@@ -49,6 +49,22 @@ def test_loss_selection_errors_before_touching_the_device():
     tr.train(ds, batch_size=4)
 
 
+def test_loss_resolution_fused_or_generic():
+  spec = lambda loss, **kw: Recoder(model=DynamicAutoencoder(hidden_layers=[4]), loss=loss, **kw)._Recoder__loss_spec()  # noqa: E731
+  assert spec('mse', loss_params={'confidence': 2})[:2] == ('mse', 2.0)
+  assert spec('logloss')[0] == 'logloss' and spec('logistic')[0] == 'logistic'
+  assert spec(MSELoss(confidence=1.5, reduction='sum'))[:2] == ('mse', 1.5)
+  assert spec(MultinomialNLLLoss(reduction='sum'))[0] == 'logloss'
+  assert spec(torch.nn.BCEWithLogitsLoss(reduction='sum'))[0] == 'logistic'
+  # anything else is used as it is (recoder/model.py:88-89) through the generic path
+  for module in (MSELoss(reduction='mean'), torch.nn.BCEWithLogitsLoss(reduction='sum', pos_weight=torch.ones(1)),
+                 torch.nn.SmoothL1Loss(reduction='sum')):
+    kind, _, got = spec(module)
+    assert kind == 'custom' and got is module
+  kind, _, module = spec('logistic', loss_params={'pos_weight': torch.ones(1)})
+  assert kind == 'custom' and isinstance(module, torch.nn.BCEWithLogitsLoss) and module.reduction == 'sum'
+
+
 def test_sampling_users_must_be_a_multiple_of_the_batch():
   ds = _dataset()
   tr = Recoder(model=DynamicAutoencoder(hidden_layers=[4]), use_cuda=False)

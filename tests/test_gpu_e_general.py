@@ -181,3 +181,43 @@ def test_chunked_heavy_columns_match_single_pass():
   assert got[0][0] == got[1][0]
   for k in got[0][1]:
     assert rel_err(got[1][1][k], got[0][1][k]) < 1e-6, k
+
+
+class _SumHuber(torch.nn.Module):
+  """A loss the library does not know: Huber with sum reduction (any nn.Module is accepted, recoder/model.py:88-89)."""
+
+  def forward(self, input, target):
+    return torch.nn.functional.smooth_l1_loss(input, target, reduction='sum', beta=0.5)
+
+
+@pytest.mark.parametrize('kind,loss_module', [('ae', _SumHuber()), ('mf', _SumHuber()),
+                                              ('ae', torch.nn.BCEWithLogitsLoss(reduction='sum',
+                                                                               pos_weight=torch.tensor(3.0)))])
+def test_custom_loss_module_step_matches_oracle(kind, loss_module):
+  U, I, nnz, B, H = 2000, 6000, 60, 384, 64
+  indptr, indices, data = synthetic_csr(U, I, nnz, seed=13)
+  params = O.init_ae_params(I, [H], seed=6) if kind == 'ae' else O.init_mf_params(I, U, H, seed=6)
+  act = 'tanh' if kind == 'ae' else 'none'
+  tr = O.OracleTrainer(kind, params, loss=loss_module, optimizer='adam', lr=1e-3, weight_decay=0.0, activation=act)
+  model = make_model(kind, I, U, [H] if kind == 'ae' else H, act, {k: v.numpy() for k, v in params.items()})
+  import copy
+  eng = make_engine(model, copy.deepcopy(loss_module), 0.0, 'adam', 1e-3, 0.0, _native.GEMM_TCGEN05)   # .to('cuda') moves a module in place
+  ds = device_dataset(indptr, indices, data, I)
+  users = np.random.default_rng(3).permutation(U)[:B]
+  pool = collate_pool(ds.device_csr(), users, True)
+  ob = O.collate(indptr, indices, data, I, users, B, True)[0]
+  oloss, ograds = tr.step(ob)
+  eng.train_step(pool, 0, B)
+  assert float(eng.losses(1)[0]) == pytest.approx(oloss, rel=1e-3)
+  if kind == 'ae':
+    want = {'dWe': ograds[O.AE_EN_W].numpy()[ob.items], 'dWd': ograds[O.AE_DE_W].numpy()[ob.items],
+            'dbd': ograds[O.AE_DE_B].numpy()[ob.items], 'dbe': ograds[O.AE_EN_B].numpy()}
+  else:
+    want = {'dV': ograds[O.MF_ITEM_W].numpy()[ob.items], 'dbias': ograds[O.MF_BIAS].numpy()[ob.items],
+            'dU': ograds[O.MF_USER_W].numpy()[ob.users]}
+  for key, w in want.items():
+    got = eng.last[key].detach().cpu().numpy()
+    # the whole dL/dlogits goes through bf16 here (no fp32 sparse part), hence the wider gate
+    assert np.linalg.norm(got) == pytest.approx(np.linalg.norm(w), rel=5e-3), key
+    assert rel_err(got, w) < 3e-2, key
+  assert abs(eng.eval_loss(pool, 0, B) - float(tr.compute_loss(ob).item())) < 2e-3 * abs(oloss) + 1e-2
