@@ -8,8 +8,15 @@ A step = GPU collate of one batch of users + forward + loss + backward + optimiz
   value     users/sec with the interaction matrix resident in HBM (whole job, all ranks)
   e2e       the same through `Recoder.train()` with the matrix in HOST memory: every step stages its rows in pinned
             memory, copies them H2D and reads the loss back D2H inside the timed region
-  roofline  the dominant kernel of the step against the measured peak (MEASURED_PEAKS.json)
+  roofline  the dominant kernel of the step against the measured peak (MEASURED_PEAKS.json): `achieved` is timed inside
+            the benchmarked multi-stream step, `single_stream` is the same kernel with nothing else on the GPU;
+            `traffic` = DRAM bytes per launch from the newest committed ncu summary (profiles/)
   cpu_baseline  the CPU oracle port of the reference's step on this box's host cores (rank 0, N=1 only)
+  kernels / host_ms_per_step / per_rank_ms  CUDA-event breakdown per entry point (warm-up steps), host enqueue vs
+            wait time, per-rank times for N>1
+N>1: `--parallel rows` splits the users of the global batch (gradient exchange per `--dp-exchange`: the fused
+peer-memory reduce-scatter/Adam/all-gather kernel or one NCCL all-reduce); `--parallel items` splits the item axis
+(recoder_b200/itempar.py); `auto` picks the faster one as measured (profiles/README.md r01d).
 `--impl reference` times that CPU port alone (the reference is a pure-Python library: there is nothing to compile
 into oracle/_ref, so the arm runs the oracle restatement, which executes the same torch CPU ops).
 Under torchrun (N>1) one process per GPU, NCCL; timing = CUDA events, max over ranks, barrier + synchronize on
