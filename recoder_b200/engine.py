@@ -2,15 +2,21 @@
 
 Replaces the per-batch body of `Recoder._train` (recoder/model.py:383-404) and `Recoder.__compute_loss`
 (recoder/model.py:454-485): no dense [B, n] fp32 input/target is ever materialised, no autograd graph is
-built, the loss stays on the device.  Data-parallel mode shards the rows of a *global* batch over ranks and
-sums one contiguous gradient slab with a single all-reduce.
+built, the loss stays on the device.
 
-Launch sequence of an autoencoder step (names are include/recoder_b200.h entry points):
-  rcd_slice_csc -> rcd_gather_rows/rcd_gather_vec (W_d, b_d of the n batch items) -> rcd_ae_encoder_fwd ->
-  rcd_sddmm (logits at the stored targets, softmax reference) -> rcd_decoder_fwd_loss (tcgen05 GEMM, loss/dlogits
-  epilogue) -> rcd_loss_finish -> rcd_decoder_dgrad + rcd_sparse_dgrad -> rcd_dz_act -> rcd_decoder_wgrad (+ bias
-  gradient side product) -> rcd_csc_rows_accumulate -> rcd_ae_encoder_wgrad -> [all-reduce] -> rcd_adam_step x4
-  (or SGD / SparseAdam)
+Launch sequence of an autoencoder step (names are include/recoder_b200.h entry points; DESIGN.md §5 "Streams"):
+  aux stream   rcd_slice_csc (CSC views of the slice, needed late) ; rcd_collate of the NEXT pool
+  main stream  rcd_gather_rows / rcd_gather_vec (W_d, b_d of the n batch items) -> rcd_ae_encoder_fwd ->
+               [inner layers / dropout: rcd_sgemm, rcd_dropout] -> rcd_sddmm (logits at the stored targets, softmax
+               reference) -> rcd_decoder_fwd_loss (tcgen05 GEMM, loss / dlogits epilogue) -> rcd_loss_finish ->
+               rcd_sparse_dgrad -> rcd_decoder_wgrad (+ bias gradient side product) -> rcd_csc_rows_accumulate ->
+               rcd_decoder_dgrad -> rcd_dz_act -> [inner backward] -> rcd_ae_encoder_wgrad -> W_e / b_e update
+  update stream  W_d / b_d update as soon as dW_d is complete (rcd_adam_step | rcd_sgd_step | ...), underneath the
+               dgrad GEMM and the encoder backward
+
+Multi-GPU: rows of a global batch sharded over ranks with the gradient slab exchanged by
+`rcd_adam_step_p2p` (fused reduce-scatter -> Adam -> all-gather over peer memory) or one NCCL all-reduce; or the item
+axis sharded (`_ae_step_items`, itempar.py) with four small peer-memory collectives per step.
 """
 import math
 
