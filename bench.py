@@ -419,6 +419,8 @@ def b200_arm(args, w):
   # ---- roofline of the dominant kernel ------------------------------------------------------------------------
   dom = s_dev['dominant']
   n_tab = 2 if w['model'] == 'ae' else 1
+  if args.parallel == 'items' and world > 1:
+    s_dev['params'] = s_dev['params'] / world    # each rank owns (and updates) 1/world of the item-indexed tensors
   if w['model'] == 'ae':
     grads = 2 * n_avg * H + n_avg + H
   else:
@@ -450,7 +452,8 @@ def b200_arm(args, w):
       else:
         ach, peak, unit = per_launch / sec / 1e9, peaks['hbm'], 'GB/s'
       # the committed ncu summaries are captures of the default workload (C3, 2048 users per GPU)
-      traffic, traffic_src = ncu_traffic(dom) if (args.config == 'c3' and B == WORKLOADS['c3']['batch']) else (None, None)
+      traffic, traffic_src = ncu_traffic(dom) if (args.config == 'c3' and B == WORKLOADS['c3']['batch'] and
+                                                  world == 1) else (None, None)
       if traffic is not None and dom == 'rcd_adam_step':
         # the ncu figure is the mean over the table launches; a step also has the (KB-sized) bias launches, and
         # `achieved` averages over all `lps` launches of a step — put both on the same per-launch footing
