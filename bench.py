@@ -374,6 +374,12 @@ def b200_arm(args, w):
       every = [torch.zeros_like(mine) for _ in range(world)]
       dist.all_gather(every, mine)
       st['per_rank'] = [[round(float(x), 4) for x in t.tolist()] for t in every]
+      if args.per_rank_kernels and st.get('warm'):
+        # diagnostic (off by default): every rank's warm-up breakdown, to find the rank / entry point the others wait
+        # for at the barriers of the multi-GPU modes
+        warms = [None] * world
+        dist.all_gather_object(warms, {k: round(v, 4) for k, v in st['warm'].items()})
+        st['per_rank_kernels'] = warms
       t = torch.tensor([ms], device='cuda', dtype=torch.float64)
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
       ms = float(t.item())
@@ -505,6 +511,7 @@ def b200_arm(args, w):
     'items_per_batch': n_avg,
     'host_ms_per_step': s_dev.get('host'),   # timed region; wait = blocked on the GPU, launch / step = enqueue work
     'per_rank_ms': s_dev.get('per_rank'),    # N>1: [device ms/step, host step, host launch, host wait] per rank
+    'per_rank_kernels': s_dev.get('per_rank_kernels'),
     'final_loss': s_dev['loss'],
     'kernels': kinds,
   }
@@ -528,6 +535,8 @@ def main():
                   help='N>1: split the users of the global batch (data parallel, gradient exchange per --dp-exchange) '
                        'or the item axis (itempar.py); auto = items for the autoencoder configs at 2-4 GPUs, rows '
                        'otherwise (the faster of the two as measured, profiles/README.md)')
+  ap.add_argument('--per-rank-kernels', action='store_true',
+                  help='N>1 diagnostic: gather every rank\'s per-entry-point warm-up timings into the JSON line')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--skip-e2e', action='store_true', help='profiling runs only: skip the host-staged leg')
   ap.add_argument('--no-profile', action='store_true', help='no CUDA-event kernel breakdown during warm-up')
