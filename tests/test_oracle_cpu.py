@@ -134,3 +134,54 @@ def test_oracle_matches_live_reference():
   st = tr.state()
   for n, p in model.named_parameters():
     np.testing.assert_allclose(st[n], p.detach().numpy(), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.skipif(not ref_shims.reference_available(), reason='reference tree not mounted')
+@pytest.mark.parametrize('hidden,tied,noise,dropout,loss,opt', [
+  ([24, 12], False, 0.0, 0.0, 'mse', 'adagrad'),
+  ([24, 12, 6], True, 0.0, 0.0, 'logloss', 'rmsprop'),
+  ([32], False, 0.4, 0.3, 'logistic', 'adam'),
+  ([24, 8], True, 0.25, 0.5, 'logloss', 'sgd'),
+])
+def test_oracle_matches_live_reference_general_models(hidden, tied, noise, dropout, loss, opt):
+  """Multi-layer / tied autoencoders, input noise and bottleneck dropout, the remaining optimizers: the oracle against
+  the live reference over several steps.  nn.Dropout's keep masks are obtained by replaying the draws the reference's
+  forward is about to make on the global CPU generator (same shapes, same order) and rewinding it."""
+  rdata, rnn, rlosses, rmodel = ref_shims.import_reference()
+  import warnings
+  warnings.simplefilter('ignore')
+  from recoder_b200.synth import synthetic_csr, to_scipy
+  U, I, B = 200, 181, 50
+  indptr, indices, data = synthetic_csr(U, I, 15, seed=9)
+  csr = to_scipy(indptr, indices, data, I)
+  ds = rdata.RecommendationDataset(csr)
+  torch.manual_seed(3)
+  model = rnn.DynamicAutoencoder(hidden_layers=hidden, activation_type='tanh', is_constrained=tied, noise_prob=noise,
+                                 dropout_prob=dropout)
+  trainer = rmodel.Recoder(model=model, use_cuda=False, optimizer_type=opt, loss=loss)
+  trainer._Recoder__init_training(train_dataset=ds, lr=1e-2, weight_decay=1e-4)
+  model.train()
+  params = {n: p.detach().clone() for n, p in model.named_parameters()}
+  tr = O.OracleTrainer('ae', params, loss=loss, optimizer=opt, lr=1e-2, weight_decay=1e-4, is_constrained=tied)
+  order = np.random.default_rng(1).permutation(U)
+  for step, off in enumerate(range(0, U, B)):
+    users = order[off:off + B]
+    ui, _ = ds[users]
+    rb = rdata.BatchCollator(B, True).collate(ui)[0]
+    ob = O.collate(indptr, indices, data, I, users, B, True)[0]
+    nk = dk = None
+    torch.manual_seed(500 + step)
+    if noise > 0:
+      nk = (torch.nn.functional.dropout(torch.ones(tuple(rb.size)), noise, True) != 0).numpy().astype(np.float32)
+    if dropout > 0:
+      dk = (torch.nn.functional.dropout(torch.ones(rb.size[0], hidden[-1]), dropout, True) != 0).numpy().astype(np.float32)
+    torch.manual_seed(500 + step)
+    trainer.optimizer.zero_grad()
+    ref_loss = trainer._Recoder__compute_loss(rb, None)
+    ref_loss.backward()
+    trainer.optimizer.step()
+    oloss, _ = tr.step(ob, noise_keep=nk, noise_prob=noise, dropout_keep=dk, dropout_prob=dropout)
+    assert oloss == pytest.approx(ref_loss.item(), rel=1e-5), step
+  st = tr.state()
+  for n, p in model.named_parameters():
+    np.testing.assert_allclose(st[n], p.detach().numpy(), rtol=2e-4, atol=1e-6, err_msg=n)
