@@ -80,10 +80,15 @@ class _Buffers:
   def __init__(self, device):
     self.device = device
     self._store = {}
+    self.retired = []   # outgrown buffers: kernels on the update / auxiliary streams may still read them
 
   def get(self, name, numel, dtype):
     t = self._store.get(name)
     if t is None or t.numel() < numel or t.dtype != dtype:
+      if t is not None:
+        # do not hand the old block back to the allocator yet: it would be reused in main-stream order while a kernel
+        # of the previous step may still be reading it on another stream (released in TrainEngine.join)
+        self.retired.append(t)
       cap = int(numel * 1.2) + 64 if t is not None else int(numel)
       t = torch.empty(max(cap, 1), dtype=dtype, device=self.device)
       self._store[name] = t
@@ -546,6 +551,14 @@ class TrainEngine:
     """Makes the current stream wait for every update still running on the side stream."""
     for tag in list(self._ready):
       self._wait_ready(tag)
+    if self.buf.retired:
+      # everything enqueued on the other streams so far is now ordered before later main-stream work, which is the
+      # order the caching allocator assumes when it recycles a block
+      if self._side is not None:
+        torch.cuda.current_stream().wait_stream(self._side)
+      if self._aux is not None:
+        torch.cuda.current_stream().wait_stream(self._aux)
+      self.buf.retired.clear()
 
   def _stash_loss(self, slab, loss_slot):
     """The step loss (float64) rides in the slab's last two floats as a hi/lo split."""
