@@ -11,14 +11,18 @@ A step = GPU collate of one batch of users + forward + loss + backward + optimiz
   roofline  the dominant kernel of the step against the measured peak (MEASURED_PEAKS.json): `achieved` is timed inside
             the benchmarked multi-stream step, `single_stream` is the same kernel with nothing else on the GPU;
             `traffic` = DRAM bytes per launch from the newest committed ncu summary (profiles/)
-  cpu_baseline  the CPU oracle port of the reference's step on this box's host cores (rank 0, N=1 only)
-  kernels / host_ms_per_step / per_rank_ms  CUDA-event breakdown per entry point (warm-up steps), host enqueue vs
-            wait time, per-rank times for N>1
+  cpu_baseline  the reference's own CPU path on this box's host cores (rank 0, N=1 only): the UNMODIFIED reference
+            (`recoder.model.Recoder.train(use_cuda=False)`, imported from baseline/_ref or /root/reference through
+            oracle/ref_shims.py; kind "reference") or, when it is not importable, the oracle port (kind "port")
+  parity_check  loss of the FIRST timed-run step against the CPU oracle evaluated with batch_size = global batch on the
+            same users and initial parameters, and (N>1) whether every rank ended with bit-identical parameters
+  kernels / host_ms_per_step / per_rank_ms  CUDA-event breakdown per entry point (separate profiling leg: `value` and
+            `e2e` are timed with no per-kernel events), host enqueue vs wait time, per-rank times for N>1
 N>1: `--parallel rows` splits the users of the global batch (gradient exchange per `--dp-exchange`: the fused
 peer-memory reduce-scatter/Adam/all-gather kernel or one NCCL all-reduce); `--parallel items` splits the item axis
 (recoder_b200/itempar.py); `auto` picks the faster one as measured (profiles/README.md r01d).
-`--impl reference` times that CPU port alone (the reference is a pure-Python library: there is nothing to compile
-into oracle/_ref, so the arm runs the oracle restatement, which executes the same torch CPU ops).
+`--impl reference` times that CPU arm alone, on the same config (global batch = per-GPU batch x N; steps of more
+than --cpu-max-batch users are sampled at that many users, stated in `cpu_baseline.sample`).
 Under torchrun (N>1) one process per GPU, NCCL; timing = CUDA events, max over ranks, barrier + synchronize on
 both sides of the timed region.
 """
@@ -113,9 +117,9 @@ def cpu_threads():
     return os.cpu_count() or 1
 
 
-def run_cpu_port(w, U, indptr, indices, data, steps, warmup, batch, budget_s):
-  """Times `steps` reference train steps on `batch` users each with the CPU oracle; shrinks the per-step sample if
-  the run would exceed `budget_s`.  Returns (users_per_sec, ms_per_step, batch_used, cores, steps_done)."""
+def run_cpu_port(w, U, indptr, indices, data, steps, warmup, batch):
+  """Times `steps` reference train steps of `batch` users each with the CPU oracle port (kind "port").
+  Returns (users_per_sec, ms_per_step, cores, what)."""
   import torch
   from oracle import recoder_oracle as O
   from recoder_b200.synth import epoch_user_order
@@ -131,46 +135,96 @@ def run_cpu_port(w, U, indptr, indices, data, steps, warmup, batch, budget_s):
   tr = O.OracleTrainer(w['model'], params, loss=w['loss'], optimizer='adam', lr=LR, weight_decay=0.0, activation=act)
   order = epoch_user_order(U, 1)
 
-  def one_step(s, b):
-    users = order[(s * b) % max(U - b, 1):][:b]
-    ob = O.collate(indptr, indices, data, I, users, b, True)[0]
+  def one_step(s):
+    users = order[(s * batch) % max(U - batch, 1):][:batch]
+    ob = O.collate(indptr, indices, data, I, users, batch, True)[0]
     tr.step(ob)
-    return ob.size[1]
 
-  # calibrate on one full-size step, then pick the per-step sample so that the whole run fits the budget
-  t0 = time.perf_counter()
-  n_full = one_step(0, batch)
-  t_full = time.perf_counter() - t0
-  total = steps + warmup
-  b = batch
-  while b > 128 and t_full * (b / batch) * total > budget_s:
-    b //= 2
-  log('[bench/cpu] calibration step: B=%d n=%d %.2fs -> per-step sample B=%d' % (batch, n_full, t_full, b))
-  for s in range(max(warmup - 1, 0)):
-    one_step(s + 1, b)
+  for s in range(warmup):
+    one_step(s)
   t0 = time.perf_counter()
   for s in range(steps):
-    one_step(s + warmup, b)
+    one_step(s + warmup)
   dt = time.perf_counter() - t0
-  return steps * b / dt, dt / steps * 1e3, b, cores, steps
+  what = ('oracle/recoder_oracle.py (CPU port of recoder/data.py collate + model.py __compute_loss + autograd + '
+          'torch.optim.Adam: the same torch CPU ops as the reference)')
+  return steps * batch / dt, dt / steps * 1e3, cores, what
+
+
+def run_cpu_reference(w, matrix, steps, warmup, batch):
+  """Times the UNMODIFIED reference: `recoder.model.Recoder.train(use_cuda=False)` (recoder/model.py:256) on the same
+  matrix, model and hyper-parameters — its own sampler, SciPy/NumPy collate, autograd and torch.optim.Adam (kind
+  "reference").  One `train()` call of `warmup` steps, then a timed call of `steps` steps on the same instance.
+  Returns (users_per_sec, ms_per_step, cores, what)."""
+  import logging
+  import torch
+  from oracle import ref_shims
+  rdata, rnn, _, rmodel = ref_shims.import_reference()
+  logging.getLogger('glog').setLevel(logging.WARNING)
+  cores = cpu_threads()
+  torch.set_num_threads(cores)
+  torch.manual_seed(0)
+  H = w['width']
+  if w['model'] == 'ae':
+    model = rnn.DynamicAutoencoder(hidden_layers=[H], activation_type='tanh')
+  else:
+    model = rnn.MatrixFactorization(embedding_size=H, activation_type='none')
+  trainer = rmodel.Recoder(model=model, use_cuda=False, optimizer_type='adam', loss=w['loss'])
+  ds = rdata.RecommendationDataset(matrix)
+  kw = dict(lr=LR, weight_decay=0, num_epochs=1, batch_size=batch, negative_sampling=True, num_data_workers=0)
+  trainer.train(ds, iters_per_epoch=max(warmup, 1), **kw)
+  t0 = time.perf_counter()
+  trainer.train(ds, iters_per_epoch=steps, **kw)
+  dt = time.perf_counter() - t0
+  what = ('unmodified reference recoder.model.Recoder.train(use_cuda=False) from %s (oracle/ref_shims.py compat '
+          'shims only)' % ref_shims.REFERENCE_ROOT)
+  return steps * batch / dt, dt / steps * 1e3, cores, what
+
+
+def cpu_arm(w, U, indptr, indices, data, matrix, steps, warmup, global_batch, max_batch, kind='auto'):
+  """The reference's CPU path on this box's host cores; returns the `cpu_baseline` object.  The per-step sample is
+  the config's global batch unless that exceeds `max_batch` users (the reference densifies [B, n] fp32 matrices:
+  16384 x 199K x 4 B = 13 GB apiece at C3 / 8 GPUs), in which case steps of `max_batch` users are timed and said so."""
+  b = min(global_batch, max_batch)
+  note = '' if b == global_batch else ' (global batch %d sampled at %d users per step)' % (global_batch, b)
+  out = None
+  if kind in ('auto', 'reference'):
+    try:
+      from oracle import ref_shims
+      if ref_shims.reference_available():
+        ups, ms, cores, what = run_cpu_reference(w, matrix, steps, warmup, b)
+        out = ('reference', ups, ms, cores, what)
+    except Exception as exc:  # pragma: no cover
+      log('[bench/cpu] reference arm failed (%r); falling back to the oracle port' % (exc,))
+      if kind == 'reference':
+        raise
+  if out is None:
+    ups, ms, cores, what = run_cpu_port(w, U, indptr, indices, data, steps, warmup, b)
+    out = ('port', ups, ms, cores, what)
+  k, ups, ms, cores, what = out
+  return {'value': ups, 'unit': 'users/s', 'cores': cores, 'kind': k, 'ms_per_step': ms,
+          'sample': '%d timed + %d warm-up steps of %d users each on the full matrix%s; %s; torch %d threads' %
+                    (steps, warmup, b, note, what, cores)}
 
 
 def reference_arm(args, w):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  from recoder_b200.synth import to_scipy
   U, indptr, indices, data = make_matrix(w, args.users)
-  ups, ms, b, cores, _ = run_cpu_port(w, U, indptr, indices, data, args.steps, args.warmup, args.batch or w['batch'],
-                                      budget_s=args.cpu_budget)
-  sample = ('oracle/recoder_oracle.py (CPU port of recoder/data.py collate + model.py __compute_loss + autograd + '
-            'torch.optim.Adam, same torch CPU ops as the reference), %d users per step on the full matrix' % b)
+  B = args.batch or w['batch']
+  matrix = to_scipy(indptr, indices, data, w['items'])
+  cpu = cpu_arm(w, U, indptr, indices, data, matrix, args.steps, args.warmup, B * world, args.cpu_max_batch,
+                kind=args.cpu_kind)
   line = {
-    'impl': 'reference', 'metric': 'users/sec (train step)', 'value': ups, 'unit': 'users/s', 'n_gpus': args.gpus,
-    'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
-    'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-    'config': workload_config(args, w, U, b, 1),
-    'cpu_baseline': {'value': ups, 'unit': 'users/s', 'cores': cores, 'kind': 'port', 'sample': sample},
-    'e2e': {'value': ups, 'unit': 'users/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    'impl': 'reference', 'metric': 'users/sec (train step)', 'value': cpu['value'], 'unit': 'users/s',
+    'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': cpu['ms_per_step'],
+    'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+    'config': workload_config(args, w, U, B, world),
+    'cpu_baseline': cpu,
+    'e2e': {'value': cpu['value'], 'unit': 'users/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
   }
   print(json.dumps(line), flush=True)
 
@@ -246,21 +300,51 @@ def kernel_work(name, w, rows, n, n_in, nnz_rows, tables):
     # per rank: NVLink ingress = the other ranks' gradient rows of the owned shard + the other ranks' pushed rows
     params, grads, world = tables if len(tables) == 3 else (tables[0], tables[1], 1)
     return 'nvlink', 4.0 * (grads + params) * (world - 1) / max(world, 1)
-  if name == 'rcd_loss_grad':
-    return 'hbm', 4.0 * rows * n            # read bf16 logits, write bf16 dlogits
+  # HBM-bound kernels: ALGORITHMIC DRAM bytes.  The embedding-row gathers of the sparse kernels touch
+  # nnz rows but only the n DISTINCT rows of the batch have to come from DRAM (repeats are L2 hits), and the [rows, H]
+  # activations they re-read (Z, dA: a few MB) live in L2 — counting those as HBM traffic is what made r01's
+  # fractions exceed 1.
   if name == 'rcd_gather_rows':
     return 'hbm', n * H * (4.0 + 2.0)       # fp32 master rows in, bf16 operand out
   if name == 'rcd_ae_encoder_fwd':
-    return 'hbm', nnz_rows * H * 4.0 + rows * H * 6.0
+    return 'hbm', n_in * H * 4.0 + rows * H * 6.0 + nnz_rows * 8.0
   if name == 'rcd_ae_encoder_wgrad':
-    return 'hbm', nnz_rows * H * 4.0 + n_in * H * 4.0
+    return 'hbm', n_in * H * 4.0 + rows * H * 4.0 + nnz_rows * 8.0
   if name == 'rcd_csc_rows_accumulate':
-    return 'hbm', nnz_rows * H * 4.0 + 2 * n * H * 4.0
+    return 'hbm', 2 * n * H * 4.0 + rows * H * 4.0 + nnz_rows * 12.0   # read-modify-write of dW_d rows
   if name == 'rcd_sparse_dgrad':
-    return 'hbm', nnz_rows * H * 4.0 + rows * H * 4.0
-  if name == 'rcd_dz_act':
-    return 'hbm', None
+    return 'hbm', n * H * 4.0 + rows * H * 4.0 + nnz_rows * 8.0
   return 'hbm', None
+
+
+def parity_check(w, U, indptr, indices, data, global_batch, gpu_first_loss):
+  """Loss of the first step of the benchmarked run against the CPU oracle: same users (the first `global_batch`
+  entries of epoch 1's order), same initial parameters (the model initialised under torch.manual_seed(0), as every
+  rank's replica is), the reference's semantics with batch_size = global batch.  Forward only, over
+  row chunks (oracle.loss_in_row_chunks): a 16384 x 199K batch is never densified at once."""
+  import torch
+  from oracle import recoder_oracle as O
+  from recoder_b200.nn import DynamicAutoencoder, MatrixFactorization
+  from recoder_b200.synth import epoch_user_order
+  if gpu_first_loss is None:
+    return {'error': 'first-step loss not recorded'}
+  I, H = w['items'], w['width']
+  torch.manual_seed(0)
+  if w['model'] == 'ae':
+    model, act = DynamicAutoencoder(hidden_layers=[H], activation_type='tanh'), 'tanh'
+  else:
+    model, act = MatrixFactorization(embedding_size=H, activation_type='none'), 'none'
+  model.init_model(num_items=I, num_users=U)
+  params = {k: v.detach().cpu() for k, v in model.named_parameters()}
+  tr = O.OracleTrainer(w['model'], params, loss=w['loss'], optimizer='adam', lr=LR, weight_decay=0.0, activation=act)
+  users = epoch_user_order(U, 1)[:global_batch]
+  ob = O.collate(indptr, indices, data, I, users, global_batch, True)[0]
+  t0 = time.perf_counter()
+  want = tr.loss_in_row_chunks(ob, 2048)
+  rel = abs(gpu_first_loss - want) / max(abs(want), 1e-30)
+  return {'first_step_loss': gpu_first_loss, 'oracle_first_step_loss': want, 'rel_err': rel, 'tolerance': 1e-3,
+          'ok': bool(rel <= 1e-3), 'oracle': 'oracle/recoder_oracle.py forward with batch_size = %d (global batch), '
+          '%d items, %.1f s on the host' % (global_batch, ob.size[1], time.perf_counter() - t0)}
 
 
 def b200_arm(args, w):
@@ -333,7 +417,7 @@ def b200_arm(args, w):
             tot = sum(a.elapsed_time(b) for a, b in use)
             warm[name] = tot / max(W - 1, 1)
           st['warm'] = warm
-          cand = {k: v for k, v in warm.items() if k not in ('rcd_collate', 'rcd_adam_step_p2p', 'rcd_p2p_barrier')}
+          cand = {k: v for k, v in warm.items() if k not in ('rcd_collate', 'rcd_p2p_barrier')}
           st['dominant'] = max(cand, key=cand.get) if cand else None
           _native.PROFILE = {st['dominant']} if st['dominant'] else None
           _native.TIMINGS.clear()
@@ -390,8 +474,19 @@ def b200_arm(args, w):
       st['dom_launches_per_step'] = len(evs) / K
     _native.PROFILE = None
     _native.TIMINGS.clear()
-    st['loss'] = float(trainer.engine.losses(1)[0])
+    all_losses = trainer.engine.losses(W + K)
+    st['loss'] = float(all_losses[-1])
+    st['first_loss'] = float(all_losses[0]) if len(all_losses) == W + K else None
     st['params'] = sum(p.numel() for p in model.parameters())
+    if world > 1 and not profile:
+      # every rank must hold bit-identical parameters after the run (item-parallel: after gathering the shards)
+      trainer.sync_parameters()
+      torch.cuda.synchronize()
+      sig = torch.stack([torch.stack([p.data.double().sum(), p.data.double().abs().sum(),
+                                      (p.data.double().flatten()[::7]).sum()]) for p in model.parameters()])
+      sigs = [torch.zeros_like(sig) for _ in range(world)]
+      dist.all_gather(sigs, sig)
+      st['replicas_identical'] = bool(all(torch.equal(sigs[0], t) for t in sigs[1:]))
     del trainer, model, ds
     torch.cuda.empty_cache()
     if prev_overlap is None:
@@ -400,21 +495,28 @@ def b200_arm(args, w):
       os.environ['RCD_OVERLAP'] = prev_overlap
     return ms, st
 
-  # ---- leg 1: matrix resident in HBM (value) ------------------------------------------------------------------
-  ms_dev, s_dev = run(device_resident=True, sync_loss=False, profile=not args.no_profile)
-  # ---- leg 1b: the dominant kernel alone — in leg 1 the optimizer kernels share the GPU with the dgrad GEMM and the
+  # ---- leg 1: matrix resident in HBM (value) — no per-kernel events anywhere in this run -----------------------------
+  ms_dev, s_dev = run(device_resident=True, sync_loss=False, profile=False)
+  # ---- leg 1p: the same run with CUDA events around every entry point during warm-up (breakdown) and around the
+  # dominant one during its timed steps (roofline `achieved`: the kernel inside the multi-stream step) -----------------
+  s_prof = None
+  if not args.no_profile:
+    _, s_prof = run(device_resident=True, sync_loss=False, profile=True, K=max(6, min(K, 20)))
+  # ---- leg 1b: the dominant kernel alone — in the step the optimizer kernels share the GPU with the dgrad GEMM and the
   # encoder backward (update stream), which stretches their event-timed duration; a few more steps on ONE stream give
   # the kernel's own launch duration for the roofline (both figures are reported)
   iso = None
-  if not args.no_profile and world == 1 and s_dev.get('dominant'):
+  if s_prof is not None and world == 1 and s_prof.get('dominant'):
     _, s_iso = run(device_resident=True, sync_loss=False, profile=True, overlap=False, K=max(6, min(K, 10)))
-    if s_iso.get('dominant') == s_dev['dominant'] and s_iso.get('dom_ms'):
+    if s_iso.get('dominant') == s_prof['dominant'] and s_iso.get('dom_ms'):
       iso = s_iso
   # ---- leg 2: host-resident matrix, H2D staging + loss readback every step (e2e) ------------------------------
   if args.skip_e2e:
     ms_e2e, s_e2e = ms_dev, {'bytes0': {'h2d': 0, 'd2h': 0}, 'bytes1': {'h2d': 0, 'd2h': 0}}
   else:
     ms_e2e, s_e2e = run(device_resident=False, sync_loss=True, profile=False)
+  if s_prof is None:
+    s_prof = {'warm': {}, 'dominant': None, 'dom_ms': None}
 
   users_per_step = B * world
   value = K * users_per_step / (ms_dev / 1e3)
@@ -423,7 +525,7 @@ def b200_arm(args, w):
   nnz_rows = float(B * (len(indices) / U))
 
   # ---- roofline of the dominant kernel ------------------------------------------------------------------------
-  dom = s_dev['dominant']
+  dom = s_prof['dominant']
   n_tab = 2 if w['model'] == 'ae' else 1
   if args.parallel == 'items' and world > 1:
     s_dev['params'] = s_dev['params'] / world    # each rank owns (and updates) 1/world of the item-indexed tensors
@@ -431,9 +533,12 @@ def b200_arm(args, w):
     grads = 2 * n_avg * H + n_avg + H
   else:
     grads = n_avg * H + n_avg + users_per_step * H
+  items_mode = args.parallel == 'items' and world > 1
+  rows_k = B * world if items_mode else B     # item-parallel: every rank runs all rows over its item shard
+  nnz_k = nnz_rows if items_mode else nnz_rows  # (all rows x 1/world of the columns == one rank's rows)
   kinds = {}
-  for name, ms in sorted(s_dev['warm'].items(), key=lambda kv: -kv[1]):
-    bound, work = kernel_work(name, w, B, n_avg, n_avg, nnz_rows, (s_dev['params'], grads, world))
+  for name, ms in sorted(s_prof['warm'].items(), key=lambda kv: -kv[1]):
+    bound, work = kernel_work(name, w, rows_k, n_avg, n_avg, nnz_k, (s_dev['params'], grads, world))
     entry = {'ms_per_step': round(ms, 4), 'bound': bound}
     if work:
       if bound == 'nvlink':
@@ -447,14 +552,16 @@ def b200_arm(args, w):
         entry['frac_of_measured'] = round(entry['achieved_gbs'] / peaks['hbm'], 4)
     kinds[name] = entry
   roofline = None
-  if dom and s_dev['dom_ms']:
-    bound, work = kernel_work(dom, w, B, n_avg, n_avg, nnz_rows, (s_dev['params'], grads, world))
-    lps = s_dev.get('dom_launches_per_step', 1.0)
+  if dom and s_prof['dom_ms']:
+    bound, work = kernel_work(dom, w, rows_k, n_avg, n_avg, nnz_k, (s_dev['params'], grads, world))
+    lps = s_prof.get('dom_launches_per_step', 1.0)
     if work:
       per_launch = work / lps
-      sec = s_dev['dom_ms'] * 1e-3
+      sec = s_prof['dom_ms'] * 1e-3
       if bound == 'tensor':
         ach, peak, unit = per_launch / sec / 1e12, peaks['tensor_sustained'], 'TFLOP/s'
+      elif bound == 'nvlink':
+        ach, peak, unit = per_launch / sec / 1e9, 900.0, 'GB/s'
       else:
         ach, peak, unit = per_launch / sec / 1e9, peaks['hbm'], 'GB/s'
       # the committed ncu summaries are captures of the default workload (C3, 2048 users per GPU)
@@ -467,11 +574,13 @@ def b200_arm(args, w):
       if iso is not None:
         sec_iso = iso['dom_ms'] * 1e-3
         ach_iso = per_launch / sec_iso / (1e12 if bound == 'tensor' else 1e9)
-      roofline = {'kernel': dom, 'bound': 'tensor' if bound == 'tensor' else 'hbm', 'achieved': round(ach, 2),
+      roofline = {'kernel': dom, 'bound': bound, 'achieved': round(ach, 2),
                   'peak': peak, 'unit': unit, 'frac': round(ach / peak, 4), 'traffic': traffic,
                   'traffic_source': traffic_src, 'algorithmic_per_launch': per_launch,
-                  'peak_source': peaks['source'] + (' (sustained)' if bound == 'tensor' else ''),
-                  'launches_per_step': lps, 'avg_launch_ms': round(s_dev['dom_ms'], 4)}
+                  'peak_source': ('NVLink 5 nominal per direction per GPU (B200_PROFILING.md: 770 GB/s measured peer '
+                                  'copy); ingress bytes of this rank' if bound == 'nvlink' else
+                                  peaks['source'] + (' (sustained)' if bound == 'tensor' else '')),
+                  'launches_per_step': lps, 'avg_launch_ms': round(s_prof['dom_ms'], 4)}
       if iso is not None:
         # `achieved` above is timed inside the benchmarked (multi-stream) region; this is the same kernel with nothing
         # else on the GPU
@@ -483,15 +592,22 @@ def b200_arm(args, w):
       dist.destroy_process_group()
     return
 
+  # ---- parity of the benchmarked run: loss of its FIRST step against the CPU oracle with batch_size = global batch
+  # (the reference's step on the same users, forward only, evaluated over row chunks), replicas bit-identical ---------
+  parity = None
+  if not args.no_parity_check:
+    try:
+      parity = parity_check(w, U, indptr, indices, data, users_per_step, s_dev.get('first_loss'))
+      if world > 1:
+        parity['replicas_identical'] = s_dev.get('replicas_identical')
+    except Exception as exc:  # pragma: no cover
+      parity = {'error': repr(exc)}
+
   # ---- CPU baseline beside it (rank 0, N=1 only) ----------------------------------------------------------------
   cpu = None
   if world == 1 and not args.no_cpu_baseline:
     try:
-      ups, ms_cpu, b_cpu, cores, nsteps = run_cpu_port(w, U, indptr, indices, data, steps=2, warmup=1, batch=B,
-                                                       budget_s=args.cpu_budget / 6.0)
-      cpu = {'value': ups, 'unit': 'users/s', 'cores': cores, 'kind': 'port', 'ms_per_step': ms_cpu,
-             'sample': '%d timed steps of %d users each on the same matrix/model (oracle/recoder_oracle.py, torch CPU '
-                       'fp32, %d threads)' % (nsteps, b_cpu, cores)}
+      cpu = cpu_arm(w, U, indptr, indices, data, matrix, 2, 1, B, args.cpu_max_batch, kind=args.cpu_kind)
     except Exception as exc:  # pragma: no cover
       cpu = {'value': None, 'unit': 'users/s', 'cores': cpu_threads(), 'kind': 'port', 'sample': 'failed: %r' % exc}
 
@@ -508,6 +624,7 @@ def b200_arm(args, w):
     'clocks': s_dev['clocks'],
     'roofline': roofline,
     'cpu_baseline': cpu,
+    'parity_check': parity,
     'items_per_batch': n_avg,
     'host_ms_per_step': s_dev.get('host'),   # timed region; wait = blocked on the GPU, launch / step = enqueue work
     'per_rank_ms': s_dev.get('per_rank'),    # N>1: [device ms/step, host step, host launch, host wait] per rank
@@ -540,7 +657,11 @@ def main():
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--skip-e2e', action='store_true', help='profiling runs only: skip the host-staged leg')
   ap.add_argument('--no-profile', action='store_true', help='no CUDA-event kernel breakdown during warm-up')
-  ap.add_argument('--cpu-budget', type=float, default=150.0, help='seconds the CPU arm may take')
+  ap.add_argument('--cpu-max-batch', type=int, default=4096,
+                  help='CPU arm: largest per-step user sample (the reference densifies [B, n] fp32 matrices)')
+  ap.add_argument('--cpu-kind', default='auto', choices=['auto', 'reference', 'port'],
+                  help='CPU arm: the unmodified reference (needs baseline/_ref or /root/reference) or the oracle port')
+  ap.add_argument('--no-parity-check', action='store_true', help='skip the first-step loss check against the oracle')
   args = ap.parse_args()
   w = WORKLOADS[args.config]
   if args.parallel == 'auto':

@@ -42,6 +42,11 @@ extern "C" {
 #define RCD_LOSS_NLL 1      /* recoder/losses.py:50-71  MultinomialNLLLoss('sum') ('logloss') */
 #define RCD_LOSS_LOGISTIC 2 /* torch BCEWithLogitsLoss('sum') ('logistic'), recoder/model.py:90-91 */
 
+/* rcd_decoder_fwd_loss modes; multinomial-NLL exponent clamp (see K4 / K5 below) */
+#define RCD_DEC_MODE_LOSS 0    /* loss / dL/dlogits epilogue */
+#define RCD_DEC_MODE_ROWMAX 1  /* NLL redo pass: stat = per-tile row maxima of logit*log2(e), nothing else is written */
+#define RCD_NLL_CLAMP_LOG2 64  /* G = exp(o - ref) is clamped at 2^64; rows whose sum reaches it are redone */
+
 /* GEMM engines: the tcgen05/TMA kernels are the product; the SIMT engine is a slow reference of the same
  * math (same bf16 operands, fp32 accumulation) used by the tests to localise faults. */
 #define RCD_GEMM_TCGEN05 0
@@ -139,6 +144,14 @@ int rcd_ae_encoder_fwd(const float* We, int H, const float* be, const int32_t* r
  *     sum softplus(o) (LOGISTIC).  The SPARSE part at the stored targets (fp32, never quantised to bf16) comes
  *     from rcd_sddmm:  MSE 2*((w-1)*o - w*t)/B with w = 1+conf*[t>0];  NLL / LOGISTIC -t/B.
  *     row_ref (NLL): any per-row reference; rcd_sddmm supplies the largest logit among the row's own targets.
+ *     That is not an upper bound of the row, so G is clamped at 2^RCD_NLL_CLAMP_LOG2 (everything stays finite) and
+ *     rows whose sum reaches the clamp are REDONE ON THE DEVICE with their true maximum as reference, which makes
+ *     the loss as unconditionally stable as F.log_softmax (recoder/losses.py:69):
+ *        rcd_decoder_fwd_loss(mode LOSS) -> rcd_loss_finish(redo_flag, row_redo)            every step
+ *        rcd_decoder_fwd_loss(mode ROWMAX, cond = redo_flag) -> rcd_nll_ref_fix(cond) ->
+ *        rcd_decoder_fwd_loss(mode LOSS, cond) -> rcd_loss_finish(cond)                     no-ops while *cond == 0
+ *        rcd_loss_sum (adds the per-block loss partials to loss_acc in fixed order, clears redo_flag)
+ *     `cond` (device int32, may be NULL = always run): the kernel returns immediately when *cond == 0.
  *
  *     rcd_decoder_fwd is the plain logits GEMM (fp32 or bf16 out, optional online-softmax partials laid out
  *     [n_tiles, rows]) used by the inference path (recoder/model.py:487-511) and the kernel tests.
@@ -150,19 +163,26 @@ int rcd_decoder_fwd(const uint16_t* Zb, int ldzb, const uint16_t* Wg, int ldw, c
 int rcd_decoder_stat_cols(int n); /* number of per-row partials rcd_decoder_fwd_loss writes for n items */
 int rcd_decoder_fwd_loss(const uint16_t* Zb, int ldzb, const uint16_t* Wg, int ldw, const float* bias, int rows, int n,
                          int H, int loss, float inv_b, const float* row_ref, uint16_t* G, int ldg, float* stat,
-                         int stat_ld, void* stream);
+                         int stat_ld, int mode, const int32_t* cond, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K5  sparse side of the loss (fp32) — the stored targets of the slice rows [row0, row0+rows).
  *     rcd_sddmm       : o_nnz[p] = Zb[r,:].Wg[cols[p],:] + bias_g[cols[p]], corr[p] = sparse part of dL/dlogits,
  *                       row_ref[r] = max_p o_nnz[p] (0 for an empty row; optional).  p is relative to
  *                       row_ptr[row0].  cols index Wg/bias_g (gathered rows).
- *     rcd_loss_finish : reduces stat, adds the loss of the slice (divided by B) to loss_acc (double), writes
+ *     rcd_loss_finish : reduces stat, finishes the loss of the slice (divided by B), writes
  *                       row_scale[r] = alpha[r] (1 for MSE/LOGISTIC) and, when Zs != NULL, Zs = bf16(alpha*Z)
- *                       [rows, ldzs] — the operand of the decoder weight gradient.  bad_flag |= 1 when a softmax
- *                       row sum is not positive/finite, |= 2 when the loss is not finite.  local_targets != 0
+ *                       [rows, ldzs] — the operand of the decoder weight gradient.  The loss goes to
+ *                       loss_blocks[block] (double, one per 8 rows; summed by rcd_loss_sum in fixed order) or, when
+ *                       loss_blocks == NULL, straight into loss_acc with one atomic per block.
+ *                       NLL rows whose row sum reached 2^RCD_NLL_CLAMP_LOG2 (a logit far above the reference): with
+ *                       redo_flag != NULL they set row_redo[r] = 1 and *redo_flag (see K4); otherwise, and for any
+ *                       row sum that is not positive/finite, bad_flag |= 1.  bad_flag |= 2 when the loss is not
+ *                       finite.  Rows without targets contribute 0 (never 0 * log 0).  local_targets != 0
  *                       (item-parallel mode): stat is the row sum over ALL item shards, the stored targets are this
  *                       rank's shard only, and the loss added is this rank's share.
+ *     rcd_nll_ref_fix : row_ref[r] = ln2 * max_t stat[r,t] for the rows with row_redo[r] != 0 (after a ROWMAX pass)
+ *     rcd_loss_sum    : loss_acc += sum of loss_blocks[0..nblocks) in index order; *redo_flag = 0 (if given)
  *     rcd_sparse_dgrad: out[r,0:H] = sum_p corr[p] * W[raw_items[p],:]  (fp32 master table; out fp32 [rows, ldp])
  *     rcd_csc_rows_accumulate: out[c,0:H] += sum_{e in column c} coef[csc_src[e]] * M[csc_row[e],:] and
  *                       db[c] += sum_e coef[csc_src[e]]  (csc_src == NULL: coef is already in CSC order)
@@ -173,7 +193,12 @@ int rcd_sddmm(const uint16_t* Zb, int ldzb, const uint16_t* Wg, int ldw, const f
 int rcd_loss_finish(const float* stat, int stat_ld, int stat_cols, int rows, int loss, float confidence, float inv_b,
                     const float* row_ref, const float* row_sum, const int32_t* row_ptr, const float* vals,
                     const float* o_nnz, int row0, float* row_scale, const float* Z, int H, uint16_t* Zs, int ldzs,
-                    double* loss_acc, int32_t* bad_flag, int local_targets, void* stream);
+                    double* loss_acc, int32_t* bad_flag, int local_targets, double* loss_blocks, int32_t* redo_flag,
+                    int32_t* row_redo, const int32_t* cond, void* stream);
+int rcd_loss_finish_blocks(int rows); /* number of loss_blocks entries rcd_loss_finish writes for `rows` rows */
+int rcd_nll_ref_fix(const float* stat, int stat_ld, int stat_cols, int rows, const int32_t* row_redo, float* row_ref,
+                    const int32_t* cond, void* stream);
+int rcd_loss_sum(const double* loss_blocks, int nblocks, double* loss_acc, int32_t* redo_flag, void* stream);
 int rcd_sparse_dgrad(const float* W, int H, const int32_t* row_ptr, const int32_t* raw_items, const float* corr,
                      int row0, int rows, float* out, int ldp, void* stream);
 int rcd_csc_rows_accumulate(const float* M, int H, const int32_t* csc_ptr, const int32_t* csc_row,

@@ -15,7 +15,13 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("RECODER_REFERENCE_ROOT", "/root/reference")
+# /root/reference exists in the build container only; `baseline/_ref` (pip install --target of the unmodified
+# reference, git-ignored, travels with gpurun) is what bench.py's reference arm finds on the GPU box.
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CANDIDATES = [os.environ.get("RECODER_REFERENCE_ROOT"), "/root/reference",
+               os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+REFERENCE_ROOT = next((c for c in _CANDIDATES if c and os.path.isfile(os.path.join(c, "recoder", "model.py"))),
+                      "/root/reference")
 
 
 def reference_available() -> bool:

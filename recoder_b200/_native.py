@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, 'csrc', 'librecoder_b200.so')
 ACT_IDS = {'none': 0, 'tanh': 1, 'sigmoid': 2, 'relu': 3}
 LOSS_IDS = {'mse': 0, 'logloss': 1, 'logistic': 2}
 GEMM_TCGEN05, GEMM_SIMT = 0, 1
+DEC_MODE_LOSS, DEC_MODE_ROWMAX = 0, 1
 
 _P = c_void_p
 # name -> (restype, argtypes); mirrors include/recoder_b200.h one to one
@@ -40,11 +41,14 @@ _SIGNATURES = {
   'rcd_decoder_fwd': (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P]),
   'rcd_decoder_stat_cols': (c_int, [c_int]),
   'rcd_decoder_fwd_loss': (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, c_int, _P,
-                                   c_int, _P]),
+                                   c_int, c_int, _P, _P]),
   'rcd_sddmm': (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P,
                         _P]),
   'rcd_loss_finish': (c_int, [_P, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P, c_int, _P, _P,
-                              c_int, _P, c_int, _P, _P, c_int, _P]),
+                              c_int, _P, c_int, _P, _P, c_int, _P, _P, _P, _P, _P]),
+  'rcd_loss_finish_blocks': (c_int, [c_int]),
+  'rcd_nll_ref_fix': (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P]),
+  'rcd_loss_sum': (c_int, [_P, c_int, _P, _P, _P]),
   'rcd_sparse_dgrad': (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, _P, c_int, _P]),
   'rcd_csc_rows_accumulate': (c_int, [_P, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, c_size_t, c_longlong, _P]),
   'rcd_csc_heavy_scratch_bytes': (c_size_t, [c_int, c_longlong, c_int]),

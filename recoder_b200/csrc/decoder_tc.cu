@@ -10,7 +10,14 @@
 // (recoder/losses.py:43-47, 68-71; BCEWithLogitsLoss, recoder/model.py:91) and the first node of their backward.
 // For the multinomial NLL the usual two passes (row max/sum, then softmax) collapse into one because any per-row
 // reference value `ref` gives exp(o-ref)/sum exp(o-ref) = softmax; the caller passes the largest logit among the
-// row's own positives (rcd_sddmm), so exp() stays far from the fp32 range and the row sum is >= 1.
+// row's own positives (rcd_sddmm), so the row sum is >= 1.  That reference is not an upper bound of the row: a
+// non-target logit far above it would overflow exp().  The exponent is therefore clamped at 2^kNllClampLog2 (G and
+// the row sums stay finite whatever the logits are), a row whose sum reaches that value is flagged by
+// rcd_loss_finish, and the flagged step is redone on the device with the TRUE row maxima as reference: MAXMODE
+// instantiation below (same GEMM, the epilogue reduces max instead of exp/sum and stores nothing) ->
+// rcd_nll_ref_fix -> this kernel again.  All three extra launches return at once while the flag is clear, which
+// is every step of a sane model: F.log_softmax's unconditional stability (recoder/losses.py:69) for a few
+// microseconds of empty launches.
 //
 // One persistent CTA per SM, 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer (tcgen05.mma cta_group::1,
 // M=128, N=256, K=16) + TMEM allocator, warps 2-9 = epilogue.  Tile 128 rows x 256 items, K = H in 64-wide blocks
@@ -38,6 +45,7 @@ constexpr int kDecBiasBytes = 2 * kDecTileN * 4;
 constexpr int kDecSmem = kDecStages * kDecStage + kDecStaging + kDecBiasBytes + 256 + 1024;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kNllClampLog2 = 64.0f;   // == RCD_NLL_CLAMP_LOG2 (rcd_loss_finish redoes rows with sum >= 2^64)
 
 struct DecFusedParams {
   int M, N;             // rows, items
@@ -46,12 +54,21 @@ struct DecFusedParams {
   const float* row_ref; // [M] or nullptr (NLL only)
   float* stat;          // [M, stat_ld]
   int stat_ld;
+  const int32_t* cond;  // device flag: the kernel returns at once when *cond == 0 (nullptr: always run)
 };
 
 // 32 accumulator values of one row -> 32 outputs (packed bf16x2) + row partial.  MASK: columns >= n_valid are dead.
-template <int LOSS, bool MASK>
+template <int LOSS, bool MASK, bool MAXMODE>
 __device__ __forceinline__ void dec_chunk32(const float (&v)[32], const float* __restrict__ bias_s, float m2,
                                             float scale, int n_valid, uint32_t (&packed)[16], float& racc) {
+  if (MAXMODE) {  // row maximum of the logits in log2 units (o * log2 e); nothing is stored
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float o2 = fmaf(v[i], kLog2e, bias_s[i]);
+      if (!MASK || i < n_valid) racc = fmaxf(racc, o2);
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
     const float4 b = *reinterpret_cast<const float4*>(bias_s + i);  // warp-wide broadcast read
@@ -62,7 +79,8 @@ __device__ __forceinline__ void dec_chunk32(const float (&v)[32], const float* _
       const float a = v[i + k];
       float out, part;
       if (LOSS == RCD_LOSS_NLL) {
-        out = ex2_approx(fmaf(a, kLog2e, bb[k]) - m2);  // bias and ref arrive pre-multiplied by log2(e)
+        // bias and ref arrive pre-multiplied by log2(e); clamped: see the header comment
+        out = ex2_approx(fminf(fmaf(a, kLog2e, bb[k]) - m2, kNllClampLog2));
         part = out;
       } else if (LOSS == RCD_LOSS_MSE) {
         const float o = a + bb[k];
@@ -87,11 +105,12 @@ __device__ __forceinline__ void dec_chunk32(const float (&v)[32], const float* _
   }
 }
 
-template <int LOSS>
+template <int LOSS, bool MAXMODE>
 static __global__ void __launch_bounds__(kDecThreads, 1)
     k_decoder_fused(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmG, DecFusedParams p, int m_tiles, int n_tiles, int kblocks,
                     uint32_t idesc) {
+  if (p.cond != nullptr && __ldg(p.cond) == 0) return;  // uniform over the grid: nobody has touched a barrier yet
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t tiles = (raw_addr + 1023u) & ~1023u;
@@ -209,14 +228,16 @@ static __global__ void __launch_bounds__(kDecThreads, 1)
       mbar_wait(tfull_bar(acc), acc_phase, 13);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kDecTileN + half * 128);
-      float racc = 0.f;
+      float racc = MAXMODE ? -INFINITY : 0.f;
 #pragma unroll 1
       for (int box = 0; box < 2; ++box) {
         const int col0 = n0 + half * 128 + box * 64;
         if (col0 >= p.N) break;  // warp-uniform
         const uint32_t sdst = my_staging + (uint32_t)(sbuf * kDecBoxBytes);
-        if (lane == 0) tma_store_wait_read<1>();  // the store that last used this buffer has read it
-        __syncwarp();
+        if (!MAXMODE) {
+          if (lane == 0) tma_store_wait_read<1>();  // the store that last used this buffer has read it
+          __syncwarp();
+        }
 #pragma unroll
         for (int c32 = 0; c32 < 2; ++c32) {
           float v[32];
@@ -224,8 +245,9 @@ static __global__ void __launch_bounds__(kDecThreads, 1)
           uint32_t packed[16];
           const float* bs = bias_s + acc * kDecTileN + half * 128 + box * 64 + c32 * 32;
           const int n_valid = p.N - (col0 + c32 * 32);
-          if (n_valid >= 32) dec_chunk32<LOSS, false>(v, bs, m2, scale, 32, packed, racc);
-          else dec_chunk32<LOSS, true>(v, bs, m2, scale, n_valid, packed, racc);
+          if (n_valid >= 32) dec_chunk32<LOSS, false, MAXMODE>(v, bs, m2, scale, 32, packed, racc);
+          else dec_chunk32<LOSS, true, MAXMODE>(v, bs, m2, scale, n_valid, packed, racc);
+          if (MAXMODE) continue;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t chunk = (uint32_t)(c32 * 4 + j);
@@ -235,6 +257,7 @@ static __global__ void __launch_bounds__(kDecThreads, 1)
                          : "memory");
           }
         }
+        if (MAXMODE) continue;
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -248,7 +271,7 @@ static __global__ void __launch_bounds__(kDecThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
-    if (lane == 0) tma_store_wait_all<0>();
+    if (!MAXMODE && lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -267,11 +290,13 @@ RCD_EXPORT int rcd_decoder_stat_cols(int n) { return 2 * rcd_div_up(n > 0 ? n : 
 
 RCD_EXPORT int rcd_decoder_fwd_loss(const uint16_t* Zb, int ldzb, const uint16_t* Wg, int ldw, const float* bias,
                                     int rows, int n, int H, int loss, float inv_b, const float* row_ref, uint16_t* G,
-                                    int ldg, float* stat, int stat_ld, void* stream) {
+                                    int ldg, float* stat, int stat_ld, int mode, const int32_t* cond, void* stream) {
   RCD_CHECK_ARG(Zb && Wg && bias && G && stat, "null pointer");
   RCD_CHECK_ARG(rows > 0 && n > 0 && H > 0, "bad shape");
   RCD_CHECK_ARG(ldzb >= H && ldw >= H && ldg >= n && ldg % 8 == 0, "bad leading dimension");
   RCD_CHECK_ARG(stat_ld >= rcd_decoder_stat_cols(n), "stat_ld too small");
+  RCD_CHECK_ARG(mode == RCD_DEC_MODE_LOSS || (mode == RCD_DEC_MODE_ROWMAX && loss == RCD_LOSS_NLL),
+                "mode must be RCD_DEC_MODE_LOSS, or RCD_DEC_MODE_ROWMAX with the multinomial NLL");
   CUtensorMap tmA, tmB, tmG;
   int rc = encode_map(&tmA, Zb, H, rows, ldzb, kTileK, kTileM);
   if (rc != RCD_OK) return rc;
@@ -284,23 +309,29 @@ RCD_EXPORT int rcd_decoder_fwd_loss(const uint16_t* Zb, int ldzb, const uint16_t
                          ((uint32_t)(kTileM >> 4) << 24);
   DecFusedParams p{};
   p.M = rows; p.N = n; p.inv_b = inv_b; p.bias = bias; p.row_ref = row_ref; p.stat = stat; p.stat_ld = stat_ld;
+  p.cond = cond;
   const int units = m_tiles * n_tiles;
   const int sms = rcd_num_sms();
   const int grid = units < sms ? units : sms;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set[3] = {false, false, false};
-#define RCD_DEC_LAUNCH(L)                                                                                         \
+  static bool attr_set[4] = {false, false, false, false};
+#define RCD_DEC_LAUNCH(L, MAXM, SLOT)                                                                             \
   do {                                                                                                            \
-    if (!attr_set[L]) {                                                                                           \
-      RCD_CUDA(cudaFuncSetAttribute(k_decoder_fused<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmem));  \
-      attr_set[L] = true;                                                                                         \
+    if (!attr_set[SLOT]) {                                                                                        \
+      RCD_CUDA(cudaFuncSetAttribute(k_decoder_fused<L, MAXM>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                    kDecSmem));                                                                   \
+      attr_set[SLOT] = true;                                                                                      \
     }                                                                                                             \
-    k_decoder_fused<L><<<grid, kDecThreads, kDecSmem, st>>>(tmA, tmB, tmG, p, m_tiles, n_tiles, kblocks, idesc);  \
+    k_decoder_fused<L, MAXM><<<grid, kDecThreads, kDecSmem, st>>>(tmA, tmB, tmG, p, m_tiles, n_tiles, kblocks,    \
+                                                                  idesc);                                         \
   } while (0)
   switch (loss) {
-    case RCD_LOSS_MSE: RCD_DEC_LAUNCH(RCD_LOSS_MSE); break;
-    case RCD_LOSS_NLL: RCD_DEC_LAUNCH(RCD_LOSS_NLL); break;
-    case RCD_LOSS_LOGISTIC: RCD_DEC_LAUNCH(RCD_LOSS_LOGISTIC); break;
+    case RCD_LOSS_MSE: RCD_DEC_LAUNCH(RCD_LOSS_MSE, false, 0); break;
+    case RCD_LOSS_NLL:
+      if (mode == RCD_DEC_MODE_ROWMAX) RCD_DEC_LAUNCH(RCD_LOSS_NLL, true, 3);
+      else RCD_DEC_LAUNCH(RCD_LOSS_NLL, false, 1);
+      break;
+    case RCD_LOSS_LOGISTIC: RCD_DEC_LAUNCH(RCD_LOSS_LOGISTIC, false, 2); break;
     default:
       rcd_set_error("rcd_decoder_fwd_loss: unknown loss id %d", loss);
       return RCD_ERR_INVALID;

@@ -101,7 +101,10 @@ static __global__ void __launch_bounds__(kSpWarps * 32)
                   const int32_t* __restrict__ row_ptr, const float* __restrict__ vals,
                   const float* __restrict__ o_nnz, int row0, float* __restrict__ row_scale,
                   const float* __restrict__ Z, int H, uint16_t* __restrict__ Zs, int ldzs,
-                  double* __restrict__ loss_acc, int32_t* __restrict__ bad, int local_targets) {
+                  double* __restrict__ loss_acc, int32_t* __restrict__ bad, int local_targets,
+                  double* __restrict__ loss_blocks, int32_t* __restrict__ redo_flag, int32_t* __restrict__ row_redo,
+                  const int32_t* __restrict__ cond) {
+  if (cond != nullptr && *cond == 0) return;
   __shared__ double s_part[kSpWarps];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * kSpWarps + w;
@@ -128,12 +131,24 @@ static __global__ void __launch_bounds__(kSpWarps * 32)
     float alpha = 1.0f, lrow;
     if (loss == RCD_LOSS_NLL) {
       const float S = row_sum[row0 + r];
-      const float lse = row_ref[r] + logf(s);
+      // a row sum at the clamp means some logit sat >= 64 octaves above the reference: the row is redone with its
+      // true maximum (decoder_tc.cu); without the redo machinery (item-parallel mode) it is an error
+      const bool clamped = s >= 18446744073709551616.0f;  // 2^RCD_NLL_CLAMP_LOG2
+      if (row_redo && lane == 0) row_redo[r] = clamped ? 1 : 0;
+      const float T = local_targets ? st : S;
+      if (T != 0.f) {
+        const float lse = row_ref[r] + logf(s);
+        // item-parallel mode: `stat` holds the all-reduced row sum, the stored targets are this rank's item shard —
+        // the rank's loss share is (sum of ITS targets) * lse + sp, so that the shares add up to S * lse + sum sp
+        lrow = T * lse + sp;
+      } else {  // no target mass: the log-sum-exp term vanishes whatever the logits are (never 0 * log 0)
+        lrow = sp;
+      }
       alpha = (S != 0.f) ? S * inv_b / s : 0.f;
-      // item-parallel mode: `stat` holds the all-reduced row sum, the stored targets are this rank's item shard —
-      // the rank's loss share is (sum of ITS targets) * lse + sp, so that the shares add up to S * lse + sum sp
-      lrow = (local_targets ? st : S) * lse + sp;
-      if (!(s > 0.f) || !isfinite(s)) {
+      if (clamped && redo_flag) {
+        if (lane == 0) atomicOr(redo_flag, 1);
+        lrow = 0.f;   // recomputed by the redo pass
+      } else if (clamped || ((S != 0.f || T != 0.f) && (!(s > 0.f) || !isfinite(s)))) {
         if (lane == 0) atomicOr(bad, 1);
       }
     } else {
@@ -155,7 +170,41 @@ static __global__ void __launch_bounds__(kSpWarps * 32)
     double t = 0.0;
 #pragma unroll
     for (int k = 0; k < kSpWarps; ++k) t += s_part[k];
-    atomicAdd(loss_acc, t * (double)inv_b);
+    if (loss_blocks) loss_blocks[blockIdx.x] = t * (double)inv_b;
+    else atomicAdd(loss_acc, t * (double)inv_b);
+  }
+}
+
+// row_ref[r] = ln2 * max_t stat[r, t] for flagged rows (stat holds per-tile maxima of logit * log2 e)
+static __global__ void k_nll_ref_fix(const float* __restrict__ stat, int stat_ld, int stat_cols, int rows,
+                                     const int32_t* __restrict__ row_redo, float* __restrict__ row_ref,
+                                     const int32_t* __restrict__ cond) {
+  if (cond != nullptr && *cond == 0) return;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kSpWarps + w;
+  if (r >= rows || row_redo[r] == 0) return;
+  float m = -INFINITY;
+  for (int t = lane; t < stat_cols; t += 32) m = fmaxf(m, stat[(size_t)r * stat_ld + t]);
+  m = warp_max(m);
+  if (lane == 0) row_ref[r] = m * 0.6931471805599453f;
+}
+
+// loss_acc += sum_b loss_blocks[b] in index order (one thread: a few hundred doubles); clears the redo flag
+static __global__ void k_loss_sum(const double* __restrict__ loss_blocks, int nblocks, double* __restrict__ loss_acc,
+                                  int32_t* __restrict__ redo_flag) {
+  __shared__ double part[32];
+  // 32 lanes take contiguous chunks, then a fixed-order sum of the 32 partials: deterministic
+  const int lane = threadIdx.x;
+  const int per = (nblocks + 31) / 32;
+  double t = 0.0;
+  for (int i = lane * per; i < min((lane + 1) * per, nblocks); ++i) t += loss_blocks[i];
+  part[lane] = t;
+  __syncwarp();
+  if (lane == 0) {
+    double s = 0.0;
+    for (int k = 0; k < 32; ++k) s += part[k];
+    *loss_acc += s;
+    if (redo_flag) *redo_flag = 0;
   }
 }
 
@@ -193,14 +242,35 @@ RCD_EXPORT int rcd_loss_finish(const float* stat, int stat_ld, int stat_cols, in
                                float inv_b, const float* row_ref, const float* row_sum, const int32_t* row_ptr,
                                const float* vals, const float* o_nnz, int row0, float* row_scale, const float* Z, int H,
                                uint16_t* Zs, int ldzs, double* loss_acc, int32_t* bad_flag, int local_targets,
+                               double* loss_blocks, int32_t* redo_flag, int32_t* row_redo, const int32_t* cond,
                                void* stream) {
-  RCD_CHECK_ARG(stat && row_ptr && vals && o_nnz && loss_acc && bad_flag, "null pointer");
+  RCD_CHECK_ARG(stat && row_ptr && vals && o_nnz && (loss_acc || loss_blocks) && bad_flag, "null pointer");
+  RCD_CHECK_ARG(!redo_flag || row_redo, "redo_flag needs row_redo");
   RCD_CHECK_ARG(rows > 0 && stat_cols > 0 && stat_ld >= stat_cols && row0 >= 0, "bad shape");
   RCD_CHECK_ARG(loss != RCD_LOSS_NLL || (row_ref && row_sum && row_scale), "NLL needs row_ref, row_sum and row_scale");
   RCD_CHECK_ARG(!Zs || (Z && ldzs >= H), "Zs needs Z and ldzs >= H");
   k_loss_finish<<<rcd_div_up(rows, kSpWarps), kSpWarps * 32, 0, (cudaStream_t)stream>>>(
       stat, stat_ld, stat_cols, rows, loss, confidence, inv_b, row_ref, row_sum, row_ptr, vals, o_nnz, row0, row_scale,
-      Z, H, Zs, ldzs, loss_acc, bad_flag, local_targets);
+      Z, H, Zs, ldzs, loss_acc, bad_flag, local_targets, loss_blocks, redo_flag, row_redo, cond);
+  RCD_LAUNCH_CHECK();
+  return RCD_OK;
+}
+
+RCD_EXPORT int rcd_loss_finish_blocks(int rows) { return rcd_div_up(rows > 0 ? rows : 1, kSpWarps); }
+
+RCD_EXPORT int rcd_nll_ref_fix(const float* stat, int stat_ld, int stat_cols, int rows, const int32_t* row_redo,
+                               float* row_ref, const int32_t* cond, void* stream) {
+  RCD_CHECK_ARG(stat && row_redo && row_ref && rows > 0 && stat_cols > 0 && stat_ld >= stat_cols, "bad arguments");
+  k_nll_ref_fix<<<rcd_div_up(rows, kSpWarps), kSpWarps * 32, 0, (cudaStream_t)stream>>>(stat, stat_ld, stat_cols, rows,
+                                                                                      row_redo, row_ref, cond);
+  RCD_LAUNCH_CHECK();
+  return RCD_OK;
+}
+
+RCD_EXPORT int rcd_loss_sum(const double* loss_blocks, int nblocks, double* loss_acc, int32_t* redo_flag,
+                            void* stream) {
+  RCD_CHECK_ARG(loss_blocks && loss_acc && nblocks > 0, "bad arguments");
+  k_loss_sum<<<1, 32, 0, (cudaStream_t)stream>>>(loss_blocks, nblocks, loss_acc, redo_flag);
   RCD_LAUNCH_CHECK();
   return RCD_OK;
 }

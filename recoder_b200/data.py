@@ -5,6 +5,10 @@ Same class names, constructor arguments, field names and assertion behaviour as 
 (data.py:86-167), `Batch` (data.py:170-187), `BatchCollator` (data.py:190-251).  The difference is where the
 work happens: the interaction matrix lives in HBM as CSR and `BatchCollator.collate` launches the K1 kernels
 (`rcd_collate`), so a `Batch` holds CUDA tensors (plus a handle on the compute layout the trainer consumes).
+
+Attribution: the public interface of this module (class / method names, argument lists and their documentation, log
+messages, checkpoint keys) mirrors amoussawi/recoder (MIT License, Copyright (c) 2018 Abdallah Moussawi) so that it is
+a drop-in for that library; see LICENSE.  The implementation underneath is original.
 """
 import numbers
 
@@ -267,6 +271,7 @@ class PoolBatch:
     self.row_inv_norm = self.row_sum = self.pos = self.items_buf = self.counts = None
     self.n = 0
     self.nnz = 0
+    self.max_user = -1
     self.row_ptr_host = None
     self._pending = None
 
@@ -300,7 +305,7 @@ class PoolRing:
 
 
 def collate_pool_launch(csr, users, negative_sampling: bool, stream=None, after=(), ring=None,
-                        row_constants=None) -> PoolBatch:
+                        row_constants=None, table_rows=None) -> PoolBatch:
   """Enqueues K1 on the rows `users` of `csr` (DeviceCSR, or HostStagedCSR: staged over PCIe first) and an
   asynchronous read-back of the two counts (n, nnz) every downstream shape depends on.  The returned PoolBatch is
   usable after `collate_pool_finish`.  Launching the collate of pool i+1 before the training step of pool i is
@@ -312,12 +317,21 @@ def collate_pool_launch(csr, users, negative_sampling: bool, stream=None, after=
   while an earlier kernel still reads it.  `collate_pool_finish` makes the current stream wait for the collate.
 
   `row_constants` = (inv_norm_all, row_sum_all), device vectors indexed by USER id: item-parallel mode, where `csr`
-  holds only this rank's columns and the row statistics of the collate must be replaced by whole-row values."""
+  holds only this rank's columns and the row statistics of the collate must be replaced by whole-row values.
+
+  `table_rows`: rows of the embedding tables the pool will train (the model's `num_items`).  The reference allows a
+  model wider than the matrix (`assert num_items >= max item id + 1`, recoder/model.py:241): the item -> column map
+  `pos`, which the optimizer kernels read for EVERY table row, is then `table_rows` long with -1 beyond the matrix
+  width.  A matrix wider than the model is an error (the reference fails inside its embedding lookup)."""
   users = np.ascontiguousarray(np.asarray(users).reshape(-1), dtype=np.int64)
   assert users.size > 0
   assert users.min() >= 0 and users.max() < csr.shape[0], 'user index out of range'
   dev = csr.device
   P, I = int(users.size), int(csr.shape[1])
+  if table_rows is not None and I > int(table_rows):
+    raise ValueError('the interactions matrix has %d columns but the model represents only %d items' % (I, table_rows))
+  pos_len = max(I, int(table_rows or 0))
+  max_user = int(users.max())
   if row_constants is None and hasattr(csr, 'inv_norm_all'):
     row_constants = (csr.inv_norm_all, csr.row_sum_all)
   slot = ring.next_slot() if ring is not None else None
@@ -368,7 +382,8 @@ def collate_pool_launch(csr, users, negative_sampling: bool, stream=None, after=
   pb.vals = buf('vals', cap, torch.float32)
   pb.row_inv_norm = buf('row_inv_norm', P, torch.float32)
   pb.row_sum = buf('row_sum', P, torch.float32)
-  pb.pos = buf('pos', I, torch.int32)
+  pb.pos = buf('pos', pos_len, torch.int32)
+  pb.max_user = max_user
   pb.items_buf = buf('items_buf', min(I, cap) if negative_sampling else I, torch.int64)
   pb.counts = buf('counts', 2, torch.int32)
   lib = _native.load()
@@ -379,6 +394,8 @@ def collate_pool_launch(csr, users, negative_sampling: bool, stream=None, after=
     stream.wait_stream(torch.cuda.current_stream())   # the copies above went to the current stream
   with ctx():
     pb.counts.zero_()
+    if pos_len > I:
+      pb.pos[I:].fill_(-1)   # table rows beyond the matrix width never receive a gradient
     _native.call('rcd_collate', _native.ptr(csr.indptr), _native.ptr(csr.indices), _native.ptr(csr.data),
                  _native.ptr(rows_dev), P, I, int(bool(negative_sampling)), cap, _native.ptr(pb.row_ptr),
                  _native.ptr(pb.raw_items), _native.ptr(pb.cols), _native.ptr(pb.vals), _native.ptr(pb.row_inv_norm),
@@ -433,9 +450,9 @@ def collate_pool_finish(pb: PoolBatch) -> PoolBatch:
   return pb
 
 
-def collate_pool(csr, users, negative_sampling: bool) -> PoolBatch:
+def collate_pool(csr, users, negative_sampling: bool, table_rows=None) -> PoolBatch:
   """Runs K1 on the rows `users` of `csr` and returns the pool's compute layout."""
-  return collate_pool_finish(collate_pool_launch(csr, users, negative_sampling))
+  return collate_pool_finish(collate_pool_launch(csr, users, negative_sampling, table_rows=table_rows))
 
 
 def pool_of(users_interactions, negative_sampling):

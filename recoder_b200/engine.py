@@ -297,6 +297,7 @@ class TrainEngine:
     self.tile_n = self.lib.rcd_decoder_tile_n()
     self.last = {}                # views of the last step's compact gradients (tests / telemetry)
     self.bad_flag = torch.zeros(1, dtype=torch.int32, device=dev)   # set by rcd_loss_finish on non-finite rows
+    self.redo_flag = torch.zeros(1, dtype=torch.int32, device=dev)  # NLL rows to redo with their true maximum
     self._loss_host = None
 
   # ------------------------------------------------------------------------------------------------------
@@ -368,6 +369,7 @@ class TrainEngine:
     own target (model.py:473-476).  `global_rows` is the number of rows of the whole (all-rank) batch the loss
     is averaged over (model.py:483-484); defaults to `rows`."""
     inv_b = 1.0 / float(global_rows or rows)
+    self._check_pool(pool, target_pool)
     loss_slot = self._loss_slot()
     if self.ip is not None:
       self._ae_step_items(pool, row0, rows, inv_b, loss_slot, train=True)
@@ -379,6 +381,7 @@ class TrainEngine:
 
   def eval_loss(self, pool, row0, rows, target_pool=None):
     """Loss of one batch without touching the parameters (`Recoder._validate`, recoder/model.py:439-452)."""
+    self._check_pool(pool, target_pool)
     slot = self.buf.get('eval_loss', 1, torch.float64)
     self.join()
     slot.zero_()
@@ -389,6 +392,28 @@ class TrainEngine:
     else:
       self._mf_step(pool, target_pool or pool, row0, rows, 1.0 / rows, slot, train=False)
     return float(slot.item())
+
+  def _check_pool(self, pool, target_pool=None):
+    """The kernels index the embedding tables by raw item id (encoder, sparse dgrad, gathers) and read the pool's
+    item -> column map `pos` for EVERY table row (optimizers): the pool must have been collated against a matrix no
+    wider than the tables and with `table_rows` = the table height (`data.collate_pool_launch`).  The reference
+    allows `Recoder(num_items=N)` with N larger than the matrix width (recoder/model.py:241) and fails inside its
+    embedding lookup when the matrix is wider."""
+    if self.kind == 'ae':
+      tables = [(pool, self.params['en_w'][1].shape[0]), (target_pool or pool, self.params['de_w'][1].shape[0])]
+    else:
+      tables = [(target_pool or pool, self.params['item_w'][1].shape[0])]
+      users = self.params['user_w'][1].shape[0]
+      if pool.max_user >= users:
+        raise ValueError('recoder_b200: user id %d in the batch but the model represents %d users' %
+                         (pool.max_user, users))
+    for pb, rows in tables:
+      if pb.num_items > rows:
+        raise ValueError('recoder_b200: the interactions matrix has %d columns but the model represents only %d items'
+                         % (pb.num_items, rows))
+      if pb.pos.numel() < rows:
+        raise ValueError('recoder_b200: the pool was collated for %d items but the model represents %d: collate it '
+                         'with table_rows=%d' % (pb.pos.numel(), rows, rows))
 
   def _aux_stream(self):
     """Context manager: the column-major views of the slice (needed only by the weight gradients, late in the step)
@@ -449,13 +474,37 @@ class TrainEngine:
          ptr(tpool.vals), row0, rows, self.loss_id, self.confidence, inv_b, ptr(o_nnz), ptr(corr), ptr(row_ref))
     stat_cols = self.lib.rcd_decoder_stat_cols(n)
     stat = b.get('stat', rows * stat_cols, torch.float32)
-    call('rcd_decoder_fwd_loss', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bias_g), rows, n, H, self.loss_id, inv_b,
-         ptr(row_ref), ptr(G), ldn, ptr(stat), stat_cols)
     alpha = b.get('alpha', rows, torch.float32) if nll else None
     Zs = b.get('Zs', rows * ldh, torch.bfloat16) if (nll and train) else None
-    call('rcd_loss_finish', ptr(stat), stat_cols, stat_cols, rows, self.loss_id, self.confidence, inv_b,
-         ptr(row_ref), ptr(tpool.row_sum), ptr(tpool.row_ptr), ptr(tpool.vals), ptr(o_nnz), row0, ptr(alpha),
-         ptr(Zf32), H, ptr(Zs), ldh, ptr(loss_slot), ptr(self.bad_flag), 0)
+    nblocks = self.lib.rcd_loss_finish_blocks(rows)
+    loss_blocks = b.get('loss_blocks', nblocks, torch.float64)
+    row_redo = b.get('row_redo', rows, torch.int32) if nll else None
+
+    def fused(mode, cond):
+      call('rcd_decoder_fwd_loss', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bias_g), rows, n, H, self.loss_id, inv_b,
+           ptr(row_ref), ptr(G), ldn, ptr(stat), stat_cols, mode, ptr(cond))
+
+    def finish(redo_flag, redo_rows, cond):
+      call('rcd_loss_finish', ptr(stat), stat_cols, stat_cols, rows, self.loss_id, self.confidence, inv_b,
+           ptr(row_ref), ptr(tpool.row_sum), ptr(tpool.row_ptr), ptr(tpool.vals), ptr(o_nnz), row0, ptr(alpha),
+           ptr(Zf32), H, ptr(Zs), ldh, None, ptr(self.bad_flag), 0, ptr(loss_blocks), ptr(redo_flag), ptr(redo_rows),
+           ptr(cond))
+
+    fused(_native.DEC_MODE_LOSS, None)
+    if nll:
+      # F.log_softmax is stable for any logits (recoder/losses.py:69).  The fused pass takes the largest TARGET logit as
+      # the softmax reference; a row in which some other logit towers over it has its exponentials clamped, is flagged
+      # by the row finish and redone with its true maximum — four launches that return at once while the flag is clear
+      flag = self.redo_flag
+      finish(flag, row_redo, None)
+      fused(_native.DEC_MODE_ROWMAX, flag)
+      call('rcd_nll_ref_fix', ptr(stat), stat_cols, stat_cols, rows, ptr(row_redo), ptr(row_ref), ptr(flag))
+      fused(_native.DEC_MODE_LOSS, flag)
+      finish(None, None, flag)
+      call('rcd_loss_sum', ptr(loss_blocks), nblocks, ptr(loss_slot), ptr(flag))
+    else:
+      finish(None, None, None)
+      call('rcd_loss_sum', ptr(loss_blocks), nblocks, ptr(loss_slot), None)
     return G, ldn, corr, alpha, (Zs if Zs is not None else Zb)
 
   def _custom_loss(self, Zb, ldh, Wg, bias_g, rows, n, H, inv_b, tpool, row0, loss_slot, train, ldn, nnz):
@@ -965,7 +1014,7 @@ class TrainEngine:
     stat_cols = self.lib.rcd_decoder_stat_cols(n)
     stat = b.get('stat', rows * stat_cols, torch.float32)
     call('rcd_decoder_fwd_loss', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bg), rows, n, H, self.loss_id, inv_b, ptr(row_ref),
-         ptr(G), ldn, ptr(stat), stat_cols)
+         ptr(G), ldn, ptr(stat), stat_cols, _native.DEC_MODE_LOSS, None)
     alpha = b.get('alpha', rows, torch.float32) if nll else None
     Zs = b.get('Zs', rows * ldh, torch.bfloat16) if (nll and train) else None
     if nll:
@@ -977,7 +1026,7 @@ class TrainEngine:
       stat_ld = stat_n = stat_cols
     call('rcd_loss_finish', ptr(stat), stat_ld, stat_n, rows, self.loss_id, self.confidence, inv_b, ptr(row_ref),
          ptr(pool.row_sum), ptr(pool.row_ptr), ptr(pool.vals), ptr(o_nnz), row0, ptr(alpha), ptr(Z), H, ptr(Zs), ldh,
-         ptr(loss_slot), ptr(self.bad_flag), 1)
+         ptr(loss_slot), ptr(self.bad_flag), 1, None, None, None, None)
     if not train:
       dist.all_reduce(loss_slot, op=dist.ReduceOp.SUM, group=pg)
       return

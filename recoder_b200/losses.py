@@ -5,6 +5,10 @@ and the loss together with dL/dlogits comes out of the fused decoder epilogue (`
 `rcd_sddmm`, `rcd_loss_finish`).  `forward(input, target)` on dense tensors is kept for user code that calls the modules
 directly, and it is what the generic path (`engine._custom_loss`) runs when a module is configured in a way the fused
 epilogue does not cover (for instance a reduction other than 'sum').
+
+Attribution: the public interface of this module (class / method names, argument lists and their documentation, log
+messages, checkpoint keys) mirrors amoussawi/recoder (MIT License, Copyright (c) 2018 Abdallah Moussawi) so that it is
+a drop-in for that library; see LICENSE.  The implementation underneath is original.
 """
 import torch
 from torch import nn

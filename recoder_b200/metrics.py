@@ -5,6 +5,10 @@ names, constructor arguments and per-user result lists, so `Recoder.train(..., m
 the reference's golden-metric test (tests/test_model.py:14-84) run unchanged.  The recommendations themselves come
 from the GPU (`Recoder.recommend`: CSR encoder -> full-width tcgen05 decoder -> `rcd_mask_seen` -> `rcd_topk_rows`);
 the metric arithmetic on the k recommended ids per user is host-side NumPy, as in the reference.
+
+Attribution: the public interface of this module (class / method names, argument lists and their documentation, log
+messages, checkpoint keys) mirrors amoussawi/recoder (MIT License, Copyright (c) 2018 Abdallah Moussawi) so that it is
+a drop-in for that library; see LICENSE.  The implementation underneath is original.
 """
 import numpy as np
 

@@ -7,6 +7,10 @@ training step is a fixed sequence of C-ABI kernel launches (engine.TrainEngine) 
 `__compute_loss` → autograd → torch.optim (recoder/model.py:383-404, 454-485).  The loss is kept on the
 device and read back only when the progress bar refreshes (the reference syncs with `loss.item()` every
 step, model.py:404).
+
+Attribution: the public interface of this module (class / method names, argument lists and their documentation, log
+messages, checkpoint keys) mirrors amoussawi/recoder (MIT License, Copyright (c) 2018 Abdallah Moussawi) so that it is
+a drop-in for that library; see LICENSE.  The implementation underneath is original.
 """
 import logging
 import os
@@ -492,10 +496,15 @@ class Recoder(object):
 
     ring, tring = PoolRing(), PoolRing()
 
+    # the model may represent more items than the matrix has columns (reference model.py:241)
+    table_rows = self.num_items if (self._ip is None or self.num_items is None) else \
+      self._ip.local_rows(self.num_items)
+
     def launch(index):
       after = (self.engine._side,) if self.engine is not None else ()
-      pool = collate_pool_launch(csr, index, ns, stream=aux, after=after, ring=ring)
-      tpool = collate_pool_launch(tcsr, index, ns, stream=aux, after=after, ring=tring) if tcsr is not None else None
+      pool = collate_pool_launch(csr, index, ns, stream=aux, after=after, ring=ring, table_rows=table_rows)
+      tpool = collate_pool_launch(tcsr, index, ns, stream=aux, after=after, ring=tring, table_rows=table_rows) \
+        if tcsr is not None else None
       return pool, tpool
 
     # One-pool-ahead software pipeline: the collate of pool i+1 is enqueued BEFORE the training steps of pool i, so
@@ -618,8 +627,9 @@ class Recoder(object):
     csr, tcsr = ds.device_csr(), ds.device_target_csr()
     itr = 0
     for index in val_dataloader.pools():
-      pool = collate_pool(csr, index, val_dataloader.negative_sampling)
-      tpool = collate_pool(tcsr, index, val_dataloader.negative_sampling) if tcsr is not None else None
+      pool = collate_pool(csr, index, val_dataloader.negative_sampling, table_rows=self.num_items)
+      tpool = collate_pool(tcsr, index, val_dataloader.negative_sampling, table_rows=self.num_items) \
+        if tcsr is not None else None
       for off in range(0, pool.num_rows, val_dataloader.batch_size):
         rows = min(val_dataloader.batch_size, pool.num_rows - off)
         total_loss += self.engine.eval_loss(pool, off, rows, target_pool=tpool)
@@ -674,6 +684,9 @@ class Recoder(object):
     # the pool is collated on the GPU (no negative sampling: columns are raw item ids) and goes through the encoder as
     # CSR; the dense [B, I] input and the boolean mask pass of the reference (model.py:502-510, 541) never exist
     pool, _ = pool_of(users_interactions, False)
+    if self.num_items is not None and pool.num_items > self.num_items:
+      raise ValueError('recoder_b200: the interactions matrix has %d columns but the model represents only %d items'
+                       % (pool.num_items, self.num_items))
     logits = self.model.forward_pool(pool)
     rows, n = logits.shape
     ld = logits.stride(0)

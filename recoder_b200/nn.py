@@ -7,6 +7,10 @@ checkpoints interchange with the reference — the exact `state_dict()` keys and
 calls `torch.nn.Linear`, `F.linear`, `nn.Embedding.forward` or autograd.  Training does not go through
 `forward()` at all (see engine.TrainEngine); `forward()` is the inference path and also launches only
 C-ABI kernels.
+
+Attribution: the public interface of this module (class / method names, argument lists and their documentation, log
+messages, checkpoint keys) mirrors amoussawi/recoder (MIT License, Copyright (c) 2018 Abdallah Moussawi) so that it is
+a drop-in for that library; see LICENSE.  The implementation underneath is original.
 """
 import math
 

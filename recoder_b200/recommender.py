@@ -1,6 +1,11 @@
 """Recommender adapters with the reference's interface (recoder/recommender.py:8-24, 104-118).  The Annoy-based
 `SimilarityRecommender` (recommender.py:27-101) is a serving-side component outside the training path
- and is not rebuilt."""
+ and is not rebuilt.
+
+Attribution: the public interface of this module (class / method names, argument lists and their documentation, log
+messages, checkpoint keys) mirrors amoussawi/recoder (MIT License, Copyright (c) 2018 Abdallah Moussawi) so that it is
+a drop-in for that library; see LICENSE.  The implementation underneath is original.
+"""
 
 
 class Recommender(object):

@@ -193,7 +193,7 @@ def test_decoder_fwd_loss_and_finish(loss, rows, n, H):
   sc = lib.rcd_decoder_stat_cols(n)
   stat = torch.full((rows, sc), float('nan'), device='cuda')
   call('rcd_decoder_fwd_loss', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bias), rows, n, H, lid, inv_b,
-       ptr(row_ref) if loss == 'logloss' else None, ptr(G), ldn, ptr(stat), sc)
+       ptr(row_ref) if loss == 'logloss' else None, ptr(G), ldn, ptr(stat), sc, _native.DEC_MODE_LOSS, None)
   alpha = torch.empty(rows, device='cuda')
   Zf = Zb[:, :H].float().contiguous()
   Zs = torch.empty(rows, ldh, dtype=torch.bfloat16, device='cuda')
@@ -201,7 +201,7 @@ def test_decoder_fwd_loss_and_finish(loss, rows, n, H):
   bad = torch.zeros(1, dtype=torch.int32, device='cuda')
   row_sum = T.sum(1).contiguous()
   call('rcd_loss_finish', ptr(stat), sc, sc, rows, lid, conf, inv_b, ptr(row_ref), ptr(row_sum), ptr(row_ptr),
-       ptr(vals), ptr(o_nnz), 0, ptr(alpha), ptr(Zf), H, ptr(Zs), ldh, ptr(acc), ptr(bad), 0)
+       ptr(vals), ptr(o_nnz), 0, ptr(alpha), ptr(Zf), H, ptr(Zs), ldh, ptr(acc), ptr(bad), 0, None, None, None, None)
   torch.cuda.synchronize()
   assert int(bad.item()) == 0
   assert not torch.isnan(G[:, :n].float()).any()
@@ -216,6 +216,85 @@ def test_decoder_fwd_loss_and_finish(loss, rows, n, H):
   if loss == 'logloss':
     torch.testing.assert_close(Zs[:, :H].float(), (alpha[:, None] * Zf), rtol=1e-2, atol=1e-7)
     assert (Zs[:, H:] == 0).all()
+
+
+@pytest.mark.parametrize('gap', [0.0, 30.0, 100.0, 400.0])
+def test_nll_is_stable_for_any_logits(gap):
+  """F.log_softmax (recoder/losses.py:69) is finite for any logits.  The fused epilogue takes the largest TARGET logit
+  as softmax reference; rows in which a NON-target logit sits `gap` above every target (gap 100 and 400 overflow
+  exp() against that reference) must be flagged, redone on the device with their true maximum, and match."""
+  rows, n, H = 300, 1500, 64
+  gcpu = torch.Generator().manual_seed(3)
+  g = torch.Generator(device='cuda').manual_seed(4)
+  Zb, ldh = _bf16_mat(rows, H, g, 0.5)
+  Wg, _ = _bf16_mat(n, H, g, 0.3)
+  bias = torch.randn(n, generator=g, device='cuda') * 0.2
+  row_ptr, cols, vals = _sparse_targets(rows, n, 12, gcpu, ratings=False)
+  nnz = int(row_ptr[-1])
+  rix = torch.repeat_interleave(torch.arange(rows, device='cuda'), (row_ptr[1:] - row_ptr[:-1]).long())
+  T = torch.zeros(rows, n, device='cuda')
+  T[rix, cols.long()] = vals
+  # adversarial columns: items nobody in the slice interacted with get a huge decoder bias
+  free = (T.sum(0) == 0).nonzero().flatten()
+  assert free.numel() >= 3
+  if gap > 0:
+    bias[free[0]] += gap
+    bias[free[1]] += gap * 0.5
+  inv_b = 1.0 / rows
+  lid = _native.LOSS_IDS['logloss']
+  lib = _native.load()
+  O = Zb[:, :H].float() @ Wg[:, :H].float().t() + bias
+  ref_loss = (-T.double() * torch.log_softmax(O.double(), dim=1)).sum() * inv_b
+  ref_full = (torch.softmax(O.double(), dim=1) * T.sum(1, keepdim=True).double() - T.double()) * inv_b
+  assert torch.isfinite(ref_loss)
+  o_nnz = torch.empty(nnz, device='cuda'); corr = torch.empty(nnz, device='cuda')
+  row_ref = torch.empty(rows, device='cuda')
+  call('rcd_sddmm', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bias), H, ptr(row_ptr), ptr(cols), ptr(vals), 0, rows, lid, 0.0,
+       inv_b, ptr(o_nnz), ptr(corr), ptr(row_ref))
+  ldn = (n + 7) // 8 * 8
+  G = torch.zeros((rows, ldn), dtype=torch.bfloat16, device='cuda')
+  sc = lib.rcd_decoder_stat_cols(n)
+  stat = torch.zeros((rows, sc), device='cuda')
+  alpha = torch.empty(rows, device='cuda')
+  Zf = Zb[:, :H].float().contiguous()
+  acc = torch.zeros(1, dtype=torch.float64, device='cuda')
+  bad = torch.zeros(1, dtype=torch.int32, device='cuda')
+  flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+  row_redo = torch.zeros(rows, dtype=torch.int32, device='cuda')
+  nb = lib.rcd_loss_finish_blocks(rows)
+  blocks = torch.zeros(nb, dtype=torch.float64, device='cuda')
+  row_sum = T.sum(1).contiguous()
+
+  def fused(mode, cond):
+    call('rcd_decoder_fwd_loss', ptr(Zb), ldh, ptr(Wg), ldh, ptr(bias), rows, n, H, lid, inv_b, ptr(row_ref), ptr(G),
+         ldn, ptr(stat), sc, mode, ptr(cond))
+
+  def finish(rf, rr, cond):
+    call('rcd_loss_finish', ptr(stat), sc, sc, rows, lid, 0.0, inv_b, ptr(row_ref), ptr(row_sum), ptr(row_ptr),
+         ptr(vals), ptr(o_nnz), 0, ptr(alpha), ptr(Zf), H, None, ldh, None, ptr(bad), 0, ptr(blocks), ptr(rf), ptr(rr),
+         ptr(cond))
+
+  fused(_native.DEC_MODE_LOSS, None)
+  finish(flag, row_redo, None)
+  torch.cuda.synchronize()
+  flagged = int(flag.item())
+  assert flagged == (1 if gap >= 100 else 0)      # 2^64 = e^44: gaps of 0 and 30 stay below the clamp
+  assert torch.isfinite(G.float()).all()          # the clamp keeps the first pass finite whatever the logits are
+  fused(_native.DEC_MODE_ROWMAX, flag)
+  call('rcd_nll_ref_fix', ptr(stat), sc, sc, rows, ptr(row_redo), ptr(row_ref), ptr(flag))
+  fused(_native.DEC_MODE_LOSS, flag)
+  finish(None, None, flag)
+  call('rcd_loss_sum', ptr(blocks), nb, ptr(acc), ptr(flag))
+  torch.cuda.synchronize()
+  assert int(bad.item()) == 0 and int(flag.item()) == 0
+  if flagged:
+    assert int(row_redo.sum().item()) == rows
+    torch.testing.assert_close(row_ref, O.max(dim=1).values, rtol=1e-3, atol=1e-2)
+  assert float(acc.item()) == pytest.approx(float(ref_loss.item()), rel=2e-4)
+  full = G[:, :n].float() * alpha[:, None]
+  full[rix, cols.long()] += corr
+  err = (full.double() - ref_full).norm() / ref_full.norm()
+  assert err < 4e-3, err
 
 
 @pytest.mark.parametrize('rows,n,per_row', [(64, 50, 10), (2048, 300, 40), (500, 4000, 30)])
