@@ -374,13 +374,27 @@ def b200_arm(args, w):
   U, indptr, indices, data = make_matrix(w, args.users)
   I, H = w['items'], w['width']
   matrix = to_scipy(indptr, indices, data, I)
-  assert (K + W) * B * world <= U, 'not enough users for %d steps' % (K + W)
 
   def barrier():
     torch.cuda.synchronize()
     if world > 1:
       dist.barrier()
       torch.cuda.synchronize()
+
+  def collect_timings(trainer):
+    """{entry point: (total device ms, launches)} since the last call: CUDA-event pairs of the ctypes path
+    (`_native.TIMINGS`: collate, staging, Python-path steps) plus those the native step executor recorded itself."""
+    torch.cuda.synchronize()
+    out = {}
+    for name, evs in _native.TIMINGS.items():
+      out[name] = (sum(a.elapsed_time(b) for a, b in evs), len(evs))
+    _native.TIMINGS.clear()
+    nat = getattr(trainer.engine, '_native', None)
+    if nat is not None:
+      for name, (tot, cnt) in nat.read_profile().items():
+        t0, c0 = out.get(name, (0.0, 0))
+        out[name] = (t0 + tot, c0 + cnt)
+    return out
 
   def run(device_resident, sync_loss, profile, overlap=True, K=K):
     """One `Recoder.train()` call of W+K steps; returns (elapsed_ms max over ranks, stats)."""
@@ -409,18 +423,12 @@ def b200_arm(args, w):
       if step == W:
         torch.cuda.synchronize()
         if profile:
-          # per entry point: mean device time per step over the warm-up steps (first step excluded)
-          warm = {}
-          for name, evs in _native.TIMINGS.items():
-            per_step = len(evs) // W if W else 0
-            use = evs[per_step:] if per_step and len(evs) > per_step else evs
-            tot = sum(a.elapsed_time(b) for a, b in use)
-            warm[name] = tot / max(W - 1, 1)
+          # per entry point: mean device time per step over the warm-up steps
+          warm = {k: tot / max(W, 1) for k, (tot, cnt) in collect_timings(trainer).items()}
           st['warm'] = warm
           cand = {k: v for k, v in warm.items() if k not in ('rcd_collate', 'rcd_p2p_barrier')}
           st['dominant'] = max(cand, key=cand.get) if cand else None
           _native.PROFILE = {st['dominant']} if st['dominant'] else None
-          _native.TIMINGS.clear()
         barrier()
         sampler.start()
         st['launch0'] = lib.rcd_launch_count()
@@ -442,9 +450,16 @@ def b200_arm(args, w):
         st['clocks'] = sampler.stop()
         barrier()
 
-    trainer.train(ds, lr=LR, weight_decay=0, num_epochs=1, iters_per_epoch=W + K, batch_size=B,
-                  negative_sampling=True, user_order=lambda e: epoch_user_order(U, e), step_callback=cb,
-                  sync_loss_every_step=sync_loss)
+    # small matrices (C1: 39 full batches per pass) take several passes; every pass uses full batches only
+    per_pass = U // (B * world)
+    assert per_pass >= 1, 'batch larger than the matrix'
+    if W + K <= per_pass:
+      epochs, iters = 1, W + K
+    else:
+      epochs, iters = -(-(W + K) // per_pass), None
+    trainer.train(ds, lr=LR, weight_decay=0, num_epochs=epochs, iters_per_epoch=iters, batch_size=B,
+                  negative_sampling=True, user_order=lambda e: epoch_user_order(U, e)[:per_pass * B * world],
+                  step_callback=cb, sync_loss_every_step=sync_loss)
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     ht = getattr(trainer, '_host_timing', None)
@@ -468,10 +483,11 @@ def b200_arm(args, w):
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
       ms = float(t.item())
     st['dom_ms'] = None
-    if profile and st['dominant'] and _native.TIMINGS.get(st['dominant']):
-      evs = _native.TIMINGS[st['dominant']]
-      st['dom_ms'] = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
-      st['dom_launches_per_step'] = len(evs) / K
+    if profile and st['dominant']:
+      tot, cnt = collect_timings(trainer).get(st['dominant'], (0.0, 0))
+      if cnt:
+        st['dom_ms'] = tot / cnt
+        st['dom_launches_per_step'] = cnt / K
     _native.PROFILE = None
     _native.TIMINGS.clear()
     all_losses = trainer.engine.losses(W + K)

@@ -359,6 +359,112 @@ int rcd_sumsq(const float* x, long long rows, int cols, int ld, double* out_sq, 
 int rcd_gemm_bf16(int mode, const uint16_t* A, int lda, const uint16_t* B, int ldb, int M, int N, int K, float* C,
                   int ldc, int engine, void* stream);
 
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K12 native step executor — replaces the per-batch body of Recoder._train (recoder/model.py:383-404:
+ *     zero_grad -> __compute_loss -> backward -> optimizer.step) as ONE host call.  The Python engine issues the
+ *     same ~40 entry points of this header one ctypes call at a time (≈1 ms of host time per step: what bounds
+ *     the small configurations, where the GPU needs 0.1-0.3 ms); rcd_step_run issues them from C++ in the same
+ *     order on the same three streams, so both paths are bit-identical.
+ *     Covers single-hidden-layer autoencoders and matrix factorisation with a fused loss (MSE / NLL / logistic)
+ *     and a dense optimizer on one GPU, and the item-parallel autoencoder step of the multi-GPU mode (`ip`).
+ *     Streams: main (forward, GEMMs, encoder backward, input-table update), side (output-table update, as soon
+ *     as its gradient is complete), aux (column-major views of the slice).  overlap == 0: everything on main.
+ *     Workspace: ONE caller-provided device buffer, carved by CAPACITIES (cap_rows, cap_n, cap_nnz) so that the
+ *     layout is stable from step to step; rcd_step_workspace_bytes says how large it must be.  The caller grows
+ *     it (after a device synchronisation) when a step exceeds a capacity.
+ *     rcd_step_run fills `out_*` with BYTE OFFSETS into the workspace of the step's compact gradients.
+ *     rcd_step_join makes `stream` wait for the side-stream work of the last step.
+ *     rcd_step_profile(ctx, mode): 0 off, 1 CUDA events around every entry point, 2 around the entry point named
+ *     `name` only; rcd_step_profile_read sums the event pairs per entry point (synchronises) and clears them.
+ * ------------------------------------------------------------------------------------------------------- */
+#define RCD_STEP_ABI 2
+#define RCD_MODEL_AE 0
+#define RCD_MODEL_MF 1
+#define RCD_OPT_ADAM 0
+#define RCD_OPT_SGD 1
+#define RCD_OPT_ADAGRAD 2
+#define RCD_OPT_RMSPROP 3
+
+typedef struct rcd_param {
+  float* p;            /* parameter, [rows, cols] row-major */
+  float* s1;           /* Adam exp_avg | SGD momentum buffer | Adagrad sum | RMSprop square_avg */
+  float* s2;           /* Adam exp_avg_sq | RMSprop momentum buffer | unused */
+  long long rows;
+  int cols;
+  int pad_;
+  double weight_decay;
+  long long t;         /* 1-based step count of THIS step (Adam bias correction) */
+} rcd_param;
+
+typedef struct rcd_pool_view { /* outputs of rcd_collate for one pool (all device pointers) */
+  const int32_t* row_ptr;
+  const int32_t* raw_items;
+  const int32_t* cols;
+  const float* vals;
+  const float* row_inv_norm;
+  const float* row_sum;
+  const int32_t* pos;
+  const int64_t* items;   /* NULL without negative sampling (columns are raw item ids) */
+  const int64_t* users;
+  long long nnz_slice;    /* stored entries of the slice rows [row0, row0+rows) */
+  int n;                  /* number of columns (batch items) */
+  int pad_;
+} rcd_pool_view;
+
+typedef struct rcd_step_ip { /* item-parallel mode (world > 1): peer-mapped buffers of the four collectives */
+  int enabled, rank, world, use_nccl_;     /* use_nccl_ must be 0 */
+  void* const* flags_host;                 /* barrier flags, per-rank pointer table (HOST array) */
+  unsigned int* seq_host;                  /* HOST counter shared with the caller's other barriers */
+  double barrier_timeout_s;
+  float* shared_local;                     /* this rank's copy of the shared block */
+  float* const* shared_host;               /* per-rank pointer table of the shared block (HOST array) */
+  float* shared_mc;                        /* multicast address of the shared block or NULL */
+  long long off_z, off_dz, off_ref, off_sum;  /* FLOAT offsets inside the shared block: Zp [rows*H], dZ [rows*H + 4],
+                                                 row_ref [rows], row sums [rows] */
+} rcd_step_ip;
+
+typedef struct rcd_step_args {
+  int abi;               /* RCD_STEP_ABI */
+  int kind;              /* RCD_MODEL_AE | RCD_MODEL_MF */
+  int H, act, loss, optimizer, train, overlap;
+  float confidence, inv_b;
+  double lr;
+  rcd_param table_in;    /* AE: W_e [I,H]      MF: user table [U,D] */
+  rcd_param bias_in;     /* AE: b_e [H]        MF: unused (p == NULL) */
+  rcd_param table_out;   /* AE: W_d [I,H]      MF: item table [I,D] */
+  rcd_param bias_out;    /* AE: b_d [I]        MF: bias [I] */
+  rcd_pool_view in;      /* input pool */
+  rcd_pool_view tgt;     /* target pool (a copy of `in` when the input is its own target, recoder/model.py:473-476) */
+  int same_pool;
+  int row0, rows;
+  int cap_rows, cap_n, cap_n_in;
+  long long cap_nnz, cap_tnnz;
+  void* ws;
+  size_t ws_bytes;
+  double* loss_acc;
+  int32_t* bad_flag;
+  int32_t* redo_flag;
+  int32_t* user_pos;     /* MF: int32 [num_users], all -1 between steps */
+  void* stream_main;
+  void* stream_side;
+  void* stream_aux;
+  rcd_step_ip ip;
+  /* outputs: byte offsets into ws (-1: not produced) */
+  long long out_dW_in, out_db_in, out_dW_out, out_db_out;
+} rcd_step_args;
+
+size_t rcd_step_args_size(void); /* sizeof(rcd_step_args), checked by the binding */
+int rcd_step_create(void** ctx_out);
+int rcd_step_destroy(void* ctx);
+size_t rcd_step_workspace_bytes(const rcd_step_args* args);
+int rcd_step_run(void* ctx, rcd_step_args* args);
+int rcd_step_join(void* ctx, void* stream);
+int rcd_step_profile(void* ctx, int mode, const char* name);
+/* names_out: '\n'-separated entry-point names (names_cap bytes), ms_out / count_out: per name; returns the number of
+ * names or a negative RCD_ERR_* */
+int rcd_step_profile_read(void* ctx, char* names_out, int names_cap, float* ms_out, int* count_out, int max_names);
+
 #ifdef __cplusplus
 }
 #endif

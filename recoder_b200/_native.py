@@ -90,6 +90,53 @@ _SIGNATURES = {
   'rcd_gemm_bf16': (c_int, [c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
 }
 
+
+
+# ---- K12 native step executor: C structs of include/recoder_b200.h ("K12") ------------------------------------------
+class RcdParam(ctypes.Structure):
+  _fields_ = [('p', _P), ('s1', _P), ('s2', _P), ('rows', c_longlong), ('cols', c_int), ('pad_', c_int),
+              ('weight_decay', c_double), ('t', c_longlong)]
+
+
+class RcdPoolView(ctypes.Structure):
+  _fields_ = [('row_ptr', _P), ('raw_items', _P), ('cols', _P), ('vals', _P), ('row_inv_norm', _P), ('row_sum', _P),
+              ('pos', _P), ('items', _P), ('users', _P), ('nnz_slice', c_longlong), ('n', c_int), ('pad_', c_int)]
+
+
+class RcdStepIp(ctypes.Structure):
+  _fields_ = [('enabled', c_int), ('rank', c_int), ('world', c_int), ('use_nccl_', c_int), ('flags_host', _P),
+              ('seq_host', _P), ('barrier_timeout_s', c_double), ('shared_local', _P), ('shared_host', _P),
+              ('shared_mc', _P), ('off_z', c_longlong), ('off_dz', c_longlong), ('off_ref', c_longlong),
+              ('off_sum', c_longlong)]
+
+
+class RcdStepArgs(ctypes.Structure):
+  _fields_ = [('abi', c_int), ('kind', c_int), ('H', c_int), ('act', c_int), ('loss', c_int), ('optimizer', c_int),
+              ('train', c_int), ('overlap', c_int), ('confidence', c_float), ('inv_b', c_float), ('lr', c_double),
+              ('table_in', RcdParam), ('bias_in', RcdParam), ('table_out', RcdParam), ('bias_out', RcdParam),
+              ('pool_in', RcdPoolView), ('pool_tgt', RcdPoolView), ('same_pool', c_int), ('row0', c_int),
+              ('rows', c_int), ('cap_rows', c_int), ('cap_n', c_int), ('cap_n_in', c_int), ('cap_nnz', c_longlong),
+              ('cap_tnnz', c_longlong), ('ws', _P), ('ws_bytes', c_size_t), ('loss_acc', _P), ('bad_flag', _P),
+              ('redo_flag', _P), ('user_pos', _P), ('stream_main', _P), ('stream_side', _P), ('stream_aux', _P),
+              ('ip', RcdStepIp), ('out_dW_in', c_longlong), ('out_db_in', c_longlong), ('out_dW_out', c_longlong),
+              ('out_db_out', c_longlong)]
+
+
+STEP_ABI = 2
+MODEL_IDS = {'ae': 0, 'mf': 1}
+OPT_IDS = {'adam': 0, 'sgd': 1, 'adagrad': 2, 'rmsprop': 3}
+
+_SIGNATURES.update({
+  'rcd_step_args_size': (c_size_t, []),
+  'rcd_step_create': (c_int, [ctypes.POINTER(_P)]),
+  'rcd_step_destroy': (c_int, [_P]),
+  'rcd_step_workspace_bytes': (c_size_t, [ctypes.POINTER(RcdStepArgs)]),
+  'rcd_step_run': (c_int, [_P, ctypes.POINTER(RcdStepArgs)]),
+  'rcd_step_join': (c_int, [_P, _P]),
+  'rcd_step_profile': (c_int, [_P, c_int, ctypes.c_char_p]),
+  'rcd_step_profile_read': (c_int, [_P, ctypes.c_char_p, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_int), c_int]),
+})
+
 EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())
 
 _lib = None
@@ -110,6 +157,9 @@ def load():
     fn.argtypes = args
   if lib.rcd_abi_version() != 1:
     raise RuntimeError('recoder_b200: ABI version mismatch')
+  if lib.rcd_step_args_size() != ctypes.sizeof(RcdStepArgs):
+    raise RuntimeError('recoder_b200: rcd_step_args layout mismatch (%d vs %d bytes)' %
+                       (lib.rcd_step_args_size(), ctypes.sizeof(RcdStepArgs)))
   _lib = lib
   return lib
 

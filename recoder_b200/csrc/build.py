@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ['core.cu', 'collate.cu', 'embed.cu', 'loss.cu', 'optim.cu', 'gemm.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'decoder_tc.cu', 'sparse.cu', 'p2p.cu', 'dense.cu', 'eval.cu']
+SOURCES = ['core.cu', 'collate.cu', 'embed.cu', 'loss.cu', 'optim.cu', 'gemm.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'decoder_tc.cu', 'sparse.cu', 'p2p.cu', 'dense.cu', 'eval.cu', 'step.cu']
 HEADERS = ['common.cuh', 'scan.cuh', 'gemm_internal.cuh', 'tc_ptx.cuh', os.path.join(ROOT, 'include', 'recoder_b200.h')]
 LIB = os.path.join(HERE, 'librecoder_b200.so')
 OBJ_DIR = os.path.join(HERE, 'build')

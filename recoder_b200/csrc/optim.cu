@@ -4,6 +4,8 @@
 // SGD(momentum=0.9, dampening=0), SparseAdam (touched rows only, no weight decay).
 // Gradients arrive compact: row i of the table has gradient grad_rows[pos[i]] if pos[i] >= 0 else 0, so the
 // scatter of embedding_dense_backward is folded into the optimizer read.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rcd {
@@ -270,9 +272,22 @@ static __global__ void k_scatter_pos(const int64_t* __restrict__ ids, int n, int
   if (i < n) pos[ids[i]] = reset ? -1 : i;
 }
 
+// Resident CTAs per SM of the streaming optimizer kernels (grid-stride beyond that).  A full complement (8 x 256
+// threads) owns every thread slot of the GPU for the kernel's whole duration, so a GEMM enqueued on another stream
+// cannot start until the update has finished — the "overlap" of the update stream then buys nothing.  4 CTAs per SM
+// keep ~100 KB of loads in flight per SM (enough for the HBM latency-bandwidth product) and leave room for the
+// 320-thread tensor-core CTAs of the main stream.  RCD_STREAM_CTAS_PER_SM overrides (measurements in profiles/README.md).
+static inline int stream_ctas_per_sm() {
+  static int v = 0;
+  if (v > 0) return v;
+  const char* e = getenv("RCD_STREAM_CTAS_PER_SM");
+  int x = e ? atoi(e) : 4;
+  v = (x >= 1 && x <= 8) ? x : 4;
+  return v;
+}
 static inline int stream_grid(long long work_items) {
   long long b = (work_items + 255) / 256;
-  long long cap = (long long)rcd_num_sms() * 8;  // 8 x 256-thread CTAs per SM, grid-stride beyond that
+  long long cap = (long long)rcd_num_sms() * stream_ctas_per_sm();
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 

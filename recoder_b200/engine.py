@@ -19,6 +19,7 @@ Multi-GPU: rows of a global batch sharded over r
 axis sharded (`_ae_step_items`, itempar.py) with four small peer-memory collectives per step.
 """
 import math
+import os
 
 import torch
 
@@ -251,6 +252,212 @@ class Optimizer:
           self.sparse_lr = lr
 
 
+class NativeStep:
+  """Host side of the native step executor (`rcd_step_run`, include/recoder_b200.h "K12"): the launch sequence of
+  `TrainEngine._ae_step` / `_mf_step` / `_ae_step_items` issued from C++ in ONE call — same entry points, same order,
+  same streams, bit-identical results — instead of ~40 ctypes calls (about 1 ms of interpreter time per step, which
+  bounds the small configurations and lets one slow host stall every rank at the item-parallel barriers).  Owns one
+  grow-only workspace carved by capacities, so nothing is allocated once the shapes have been seen."""
+
+  GROW = 1.25
+
+  def __init__(self, engine):
+    import ctypes
+    self.ctypes = ctypes
+    self.eng = engine
+    self.lib = engine.lib
+    ctx = ctypes.c_void_p()
+    _native.check(self.lib.rcd_step_create(ctypes.byref(ctx)), 'rcd_step_create')
+    self.ctx = ctx
+    self.args = _native.RcdStepArgs()
+    self.ws = None
+    self.caps = {'rows': 0, 'n': 0, 'n_in': 0, 'nnz': 0, 'tnnz': 0}
+    self._static_done = False
+    self._prof_state = None
+    self._names = ctypes.create_string_buffer(4096)
+    self._ms = (ctypes.c_float * 64)()
+    self._cnt = (ctypes.c_int * 64)()
+
+  def close(self):
+    if self.ctx is not None:
+      self.lib.rcd_step_destroy(self.ctx)
+      self.ctx = None
+
+  def __del__(self):  # pragma: no cover
+    try:
+      self.close()
+    except Exception:
+      pass
+
+  @staticmethod
+  def _fill_param(dst, st, t):
+    rows, cols = st.view2d()
+    dst.p = st.p.data_ptr()
+    dst.s1 = st.m.data_ptr() if st.m is not None else None
+    dst.s2 = st.v.data_ptr() if st.v is not None else None
+    dst.rows, dst.cols = rows, cols
+    dst.weight_decay = float(st.weight_decay)
+    dst.t = t
+
+  @staticmethod
+  def _fill_pool(dst, pb, row0, rows):
+    dst.row_ptr = pb.row_ptr.data_ptr()
+    dst.raw_items = pb.raw_items.data_ptr()
+    dst.cols = pb.cols.data_ptr()
+    dst.vals = pb.vals.data_ptr()
+    dst.row_inv_norm = pb.row_inv_norm.data_ptr()
+    dst.row_sum = pb.row_sum.data_ptr()
+    dst.pos = pb.pos.data_ptr()
+    dst.items = pb.items_buf.data_ptr() if pb.negative_sampling else None
+    dst.users = pb.users.data_ptr()
+    dst.nnz_slice = int(pb.row_ptr_host[row0 + rows] - pb.row_ptr_host[row0])
+    dst.n = pb.n
+
+  def _static(self):
+    e, a = self.eng, self.args
+    a.abi = _native.STEP_ABI
+    a.kind = _native.MODEL_IDS[e.kind]
+    a.act = e.act
+    a.loss = e.loss_id
+    a.optimizer = _native.OPT_IDS[e.opt.type]
+    a.confidence = e.confidence
+    a.bad_flag = e.bad_flag.data_ptr()
+    a.redo_flag = e.redo_flag.data_ptr()
+    if e.kind == 'ae':
+      a.H = e.params['en_w'][1].shape[1]
+    else:
+      a.H = e.params['item_w'][1].shape[1]
+      U = e.params['user_w'][1]
+      self.user_pos = torch.full((U.shape[0],), -1, dtype=torch.int32, device=U.device)
+      a.user_pos = self.user_pos.data_ptr()
+    if e.ip is not None:
+      ctx = e.ip.p2p
+      a.ip.enabled, a.ip.rank, a.ip.world = 1, ctx.rank, ctx.world
+      a.ip.flags_host = self.ctypes.cast(ctx._flag_table, self.ctypes.c_void_p)
+      a.ip.seq_host = self.ctypes.cast(self.ctypes.pointer(ctx._seq), self.ctypes.c_void_p)
+      a.ip.barrier_timeout_s = float(ctx.barrier_timeout_s)
+    self._static_done = True
+
+  def _names_of(self):
+    e = self.eng
+    if e.kind == 'ae':
+      return e.params['en_w'][0], e.params['en_b'][0], e.params['de_w'][0], e.params['de_b'][0]
+    return e.params['user_w'][0], None, e.params['item_w'][0], e.params['bias'][0]
+
+  def _sync_profile(self):
+    """Mirrors `_native.PROFILE` (bench.py) into the executor's own CUDA-event timing."""
+    want = _native.PROFILE
+    key = None if want is None else ('all' if want == 'all' else tuple(sorted(want)))
+    if key == self._prof_state:
+      return
+    self._prof_state = key
+    if key is None:
+      self.lib.rcd_step_profile(self.ctx, 0, None)
+    elif key == 'all' or len(key) != 1:
+      self.lib.rcd_step_profile(self.ctx, 1, None)
+    else:
+      self.lib.rcd_step_profile(self.ctx, 2, key[0].encode())
+
+  def read_profile(self):
+    """{entry point: (total ms, launches)} recorded since the last read (synchronises on the recorded events)."""
+    k = self.lib.rcd_step_profile_read(self.ctx, self._names, 4096, self._ms, self._cnt, 64)
+    if k < 0:
+      _native.check(k, 'rcd_step_profile_read')
+    names = self._names.value.decode().split('\n') if k else []
+    return {names[i]: (float(self._ms[i]), int(self._cnt[i])) for i in range(k)}
+
+  def run(self, pool, tpool, row0, rows, inv_b, loss_slot, train):
+    e, a = self.eng, self.args
+    if not self._static_done:
+      self._static()
+    self._sync_profile()
+    same = tpool is pool
+    n_in_name, b_in_name, n_out_name, b_out_name = self._names_of()
+    opt = e.opt
+    states = [opt.states[n_in_name], opt.states[b_in_name] if b_in_name else None, opt.states[n_out_name],
+              opt.states[b_out_name]]
+    for st in states:
+      if st is not None:
+        opt._ensure(st)
+    for dst, st in zip((a.table_in, a.bias_in, a.table_out, a.bias_out), states):
+      if st is not None:
+        self._fill_param(dst, st, st.step + 1)
+    self._fill_pool(a.pool_in, pool, row0, rows)
+    self._fill_pool(a.pool_tgt, tpool, row0, rows)
+    a.same_pool = int(same)
+    a.row0, a.rows = int(row0), int(rows)
+    a.inv_b = inv_b
+    a.lr = float(opt.lr)
+    a.train = int(train)
+    a.overlap = int(e.overlap)
+    a.loss_acc = loss_slot.data_ptr()
+    # workspace capacities: grow-only with head-room; the layout is a function of the capacities alone
+    c = self.caps
+    need = {'rows': rows, 'n': tpool.n, 'n_in': pool.n, 'nnz': a.pool_in.nnz_slice, 'tnnz': a.pool_tgt.nnz_slice}
+    grow = self.ws is None or any(need[k] > c[k] for k in c)
+    if grow:
+      for k in c:
+        if need[k] > c[k]:
+          c[k] = int(need[k]) if k == 'rows' else int(need[k] * self.GROW) + 16
+      # a batch never holds more items than the table has rows
+      if tpool.negative_sampling:
+        c['n'] = max(min(c['n'], int(a.table_out.rows)), tpool.n)
+      if e.kind == 'ae' and pool.negative_sampling:
+        c['n_in'] = max(min(c['n_in'], int(a.table_in.rows)), pool.n)
+    a.cap_rows, a.cap_n, a.cap_n_in, a.cap_nnz, a.cap_tnnz = c['rows'], c['n'], c['n_in'], c['nnz'], c['tnnz']
+    if grow:
+      nbytes = int(self.lib.rcd_step_workspace_bytes(self.ctypes.byref(a)))
+      if nbytes == 0:
+        raise RuntimeError('recoder_b200: rcd_step_workspace_bytes rejected the step description')
+      if self.ws is None or self.ws.numel() < nbytes:
+        torch.cuda.synchronize()     # kernels of earlier steps may still use the old workspace on any stream
+        self.ws = None
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=e.device)
+    a.ws = self.ws.data_ptr()
+    a.ws_bytes = self.ws.numel()
+    # streams
+    if e.overlap:
+      if e._side is None:
+        e._side = torch.cuda.Stream(device=e.device)
+      if e._aux is None:
+        e._aux = torch.cuda.Stream(device=e.device)
+      a.stream_side = e._side.cuda_stream
+      a.stream_aux = e._aux.cuda_stream
+      e._keep_for_side(pool, None if same else tpool)
+    a.stream_main = _native.stream_ptr()
+    if e.ip is not None:
+      xb = e._ip_buffers(rows, a.H)
+      sh = xb['shared']
+      o_z, o_dz, o_ref, o_sum = xb['off']
+      a.ip.shared_local = sh.local_ptr
+      self._ip_table = sh.ptr_table()
+      a.ip.shared_host = self.ctypes.cast(self._ip_table, self.ctypes.c_void_p)
+      a.ip.shared_mc = sh.mc()
+      a.ip.off_z, a.ip.off_dz, a.ip.off_ref, a.ip.off_sum = o_z // 4, o_dz // 4, o_ref // 4, o_sum // 4
+    status = self.lib.rcd_step_run(self.ctx, self.ctypes.byref(a))
+    if status != 0:
+      _native.check(status, 'rcd_step_run')
+    if train:
+      for st in states:
+        if st is not None:
+          st.step += 1
+      H = a.H
+      f32 = self.ws.view(torch.float32)
+
+      def view(off, numel):
+        return f32[off // 4:off // 4 + numel]
+      if e.kind == 'ae':
+        e.last = {'n': tpool.n, 'n_in': pool.n, 'dWe': view(a.out_dW_in, pool.n * H).view(pool.n, H),
+                  'dWd': view(a.out_dW_out, tpool.n * H).view(tpool.n, H), 'dbd': view(a.out_db_out, tpool.n),
+                  'dbe': view(a.out_db_in, H), 'inner': f32[0:0], 'inner_layout': e._inner_layout()}
+      else:
+        e.last = {'n': tpool.n, 'dV': view(a.out_dW_out, tpool.n * H).view(tpool.n, H),
+                  'dbias': view(a.out_db_out, tpool.n), 'dU': view(a.out_dW_in, rows * H).view(rows, H)}
+
+  def join(self):
+    _native.check(self.lib.rcd_step_join(self.ctx, _native.stream_ptr()), 'rcd_step_join')
+
+
 class TrainEngine:
   """Executes training steps for a single-hidden-layer DynamicAutoencoder ('ae') or a MatrixFactorization ('mf')."""
 
@@ -275,7 +482,6 @@ class TrainEngine:
     self.ip = item_parallel       # itempar.ItemParallel: every rank sees all rows, the item axis is sharded
     self._ip_shared = None
     self._slab_shared = None
-    import os
     self.overlap = os.environ.get('RCD_OVERLAP', '1') != '0'
     self._side = None
     self._aux = None
@@ -299,6 +505,34 @@ class TrainEngine:
     self.bad_flag = torch.zeros(1, dtype=torch.int32, device=dev)   # set by rcd_loss_finish on non-finite rows
     self.redo_flag = torch.zeros(1, dtype=torch.int32, device=dev)  # NLL rows to redo with their true maximum
     self._loss_host = None
+    self._native = None            # NativeStep, created on first use
+    self.native_enabled = os.environ.get('RCD_NATIVE_STEP', '1') != '0'
+    self._used_python_path = False
+
+  def _native_ok(self, pool, tpool, train):
+    """True when the step can go through the native executor (`rcd_step_run`): single-hidden-layer autoencoder or
+    matrix factorisation, fused loss, dense optimizer, tcgen05 engine, one GPU or the item-parallel mode with
+    peer-memory collectives.  Everything else (inner layers, noise / dropout, tied weights, SparseAdam, custom loss
+    modules, row-parallel exchanges, the SIMT validation engine) keeps the Python launch sequence."""
+    if not self.native_enabled or self.loss_module is not None or self.gemm != _native.GEMM_TCGEN05:
+      return False
+    if self.enc_layers or self.dec_layers or self.tied:
+      return False
+    if train and (self.noise_prob > 0.0 or self.dropout_prob > 0.0):
+      return False
+    if any(st.sparse for st in self.opt.states.values()):
+      return False
+    if self.ip is not None:
+      return train and self.ip.p2p is not None
+    return self.pg is None
+
+  def _native_run(self, pool, tpool, row0, rows, inv_b, loss_slot, train):
+    if self._native is None:
+      self._native = NativeStep(self)
+    if self._used_python_path:     # order the executor after Python-path work still pending on the other streams
+      self.join()
+      self._used_python_path = False
+    self._native.run(pool, tpool, row0, rows, inv_b, loss_slot, train)
 
   # ------------------------------------------------------------------------------------------------------
   def _loss_slot(self):
@@ -371,6 +605,11 @@ class TrainEngine:
     inv_b = 1.0 / float(global_rows or rows)
     self._check_pool(pool, target_pool)
     loss_slot = self._loss_slot()
+    if self._native_ok(pool, target_pool or pool, True):
+      self._native_run(pool, target_pool or pool, row0, rows, inv_b, loss_slot, True)
+      self.steps_done += 1
+      return
+    self._python_path()
     if self.ip is not None:
       self._ae_step_items(pool, row0, rows, inv_b, loss_slot, train=True)
     elif self.kind == 'ae':
@@ -385,6 +624,10 @@ class TrainEngine:
     slot = self.buf.get('eval_loss', 1, torch.float64)
     self.join()
     slot.zero_()
+    if self._native_ok(pool, target_pool or pool, False):
+      self._native_run(pool, target_pool or pool, row0, rows, 1.0 / rows, slot, False)
+      return float(slot.item())
+    self._python_path()
     if self.ip is not None:
       self._ae_step_items(pool, row0, rows, 1.0 / rows, slot, train=False)
     elif self.kind == 'ae':
@@ -596,8 +839,16 @@ class TrainEngine:
     if ev is not None:
       torch.cuda.current_stream().wait_event(ev)
 
+  def _python_path(self):
+    """Called before a step takes the Python launch sequence: orders it after native-executor work in flight."""
+    if self._native is not None:
+      self._native.join()
+    self._used_python_path = True
+
   def join(self):
     """Makes the current stream wait for every update still running on the side stream."""
+    if self._native is not None:
+      self._native.join()
     for tag in list(self._ready):
       self._wait_ready(tag)
     if self.buf.retired:

@@ -143,7 +143,7 @@ class P2PContext:
         self.backend = 'ipc'
     self.flags = SharedBuffer(self, 4 * MAX_PEERS)
     self._flag_table = self.flags.ptr_table()
-    self.seq = 0
+    self._seq = ctypes.c_uint(0)    # shared with the native step executor (rcd_step_args.ip.seq_host)
     self.barrier_timeout_s = 60.0
 
   @staticmethod
@@ -182,9 +182,13 @@ class P2PContext:
 
   def barrier(self, bad_flag):
     """Stream-ordered barrier of all ranks (`rcd_p2p_barrier`)."""
-    self.seq += 1
-    _native.call('rcd_p2p_barrier', self._flag_table, self.rank, self.world, self.seq, _native.ptr(bad_flag),
+    self._seq.value += 1
+    _native.call('rcd_p2p_barrier', self._flag_table, self.rank, self.world, self._seq.value, _native.ptr(bad_flag),
                  float(self.barrier_timeout_s))
+
+  @property
+  def seq(self):
+    return self._seq.value
 
   def owned_rows(self, rows):
     """Contiguous row shard of this rank for a table of `rows` rows."""
