@@ -490,9 +490,10 @@ def b200_arm(args, w):
         st['dom_launches_per_step'] = cnt / K
     _native.PROFILE = None
     _native.TIMINGS.clear()
-    all_losses = trainer.engine.losses(W + K)
+    done = trainer.engine.steps_done      # (a run over several passes of a small matrix rounds up to whole passes)
+    all_losses = trainer.engine.losses(done)
     st['loss'] = float(all_losses[-1])
-    st['first_loss'] = float(all_losses[0]) if len(all_losses) == W + K else None
+    st['first_loss'] = float(all_losses[0]) if len(all_losses) == done else None
     st['params'] = sum(p.numel() for p in model.parameters())
     if world > 1 and not profile:
       # every rank must hold bit-identical parameters after the run (item-parallel: after gathering the shards)

@@ -272,17 +272,16 @@ static __global__ void k_scatter_pos(const int64_t* __restrict__ ids, int n, int
   if (i < n) pos[ids[i]] = reset ? -1 : i;
 }
 
-// Resident CTAs per SM of the streaming optimizer kernels (grid-stride beyond that).  A full complement (8 x 256
-// threads) owns every thread slot of the GPU for the kernel's whole duration, so a GEMM enqueued on another stream
-// cannot start until the update has finished — the "overlap" of the update stream then buys nothing.  4 CTAs per SM
-// keep ~100 KB of loads in flight per SM (enough for the HBM latency-bandwidth product) and leave room for the
-// 320-thread tensor-core CTAs of the main stream.  RCD_STREAM_CTAS_PER_SM overrides (measurements in profiles/README.md).
+// Resident CTAs per SM of the streaming optimizer kernels (grid-stride beyond that).  Measured on C3 (profiles/README.md
+// r02b): 8 x 256 threads per SM reach 6.2 TB/s alone; 4 per SM, which would leave thread slots for the tensor-core CTAs
+// of the main stream, reach 5.3 TB/s alone and do NOT shorten the step (2.50 vs 2.34 ms: the two streams compete for
+// HBM either way), 3 -> 2.35 ms, 2 -> 2.59 ms.  RCD_STREAM_CTAS_PER_SM overrides the default of 8.
 static inline int stream_ctas_per_sm() {
   static int v = 0;
   if (v > 0) return v;
   const char* e = getenv("RCD_STREAM_CTAS_PER_SM");
-  int x = e ? atoi(e) : 4;
-  v = (x >= 1 && x <= 8) ? x : 4;
+  int x = e ? atoi(e) : 8;
+  v = (x >= 1 && x <= 8) ? x : 8;
   return v;
 }
 static inline int stream_grid(long long work_items) {
