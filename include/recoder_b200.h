@@ -252,6 +252,23 @@ int rcd_adam_step(float* p, float* m, float* v, long long rows, int H, const flo
                   long long t, void* stream);
 int rcd_sgd_step(float* p, float* buf, long long rows, int H, const float* grad_rows, int ldg, const int32_t* pos,
                  double lr, double momentum, double weight_decay, void* stream);
+/* Deferred dense Adam — the SAME arithmetic and results as rcd_adam_step (bit-identical), with HBM traffic proportional
+ * to the rows a batch touches instead of the whole table.  Rows outside a batch have gradient wd*p whatever the batch
+ * is, so their updates are postponed: last int32[rows] holds the step up to which each row is current.
+ *   rcd_adam_lazy_catchup : replays the skipped steps last[r]+1 .. T (zero data gradient) for rows ids[0..n) (ids NULL:
+ *                           rows 0..n-1, i.e. a flush of the table) from the per-step scalars scal float[2*scal_len]
+ *                           = {lr_t/(1-beta1^t), 1/sqrt(1-beta2^t)} of steps scal_base .. scal_base+scal_len-1
+ *                           (rcd_adam_scalars); mark != 0: then sets last[r] = T.  Call it before anything reads the rows.
+ *   rcd_adam_lazy_update  : step t on rows ids[i] (current at t-1) with gradient row grad_rows[i,:]; last[ids[i]] = t.
+ *   rcd_adam_scalars      : HOST helper filling out_host[2*count] for steps t_first .. t_first+count-1 exactly as
+ *                           rcd_adam_step forms its scalars (double arithmetic, rounded to float). */
+int rcd_adam_lazy_catchup(float* p, float* m, float* v, int H, const int64_t* ids, long long n, int32_t* last,
+                          long long T, const float* scal, long long scal_base, long long scal_len, double beta1,
+                          double beta2, double eps, double weight_decay, int mark, void* stream);
+int rcd_adam_lazy_update(float* p, float* m, float* v, int H, const int64_t* ids, long long n, const float* grad_rows,
+                         int ldg, int32_t* last, double lr, double beta1, double beta2, double eps, double weight_decay,
+                         long long t, void* stream);
+int rcd_adam_scalars(double lr, double beta1, double beta2, long long t_first, int count, float* out_host);
 /* torch.optim.Adagrad(lr) and torch.optim.RMSprop(lr, momentum=0.9) with their defaults (lr_decay 0, eps 1e-10 /
  * alpha 0.99, eps 1e-8, not centered) — recoder/model.py:140-144, 150-154; dense semantics as above. */
 int rcd_adagrad_step(float* p, float* sum, long long rows, int H, const float* grad_rows, int ldg, const int32_t* pos,

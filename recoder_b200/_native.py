@@ -61,6 +61,11 @@ _SIGNATURES = {
   'rcd_adam_step': (c_int, [_P, _P, _P, c_longlong, c_int, _P, c_int, _P, c_double, c_double, c_double, c_double,
                             c_double, c_longlong, _P]),
   'rcd_sgd_step': (c_int, [_P, _P, c_longlong, c_int, _P, c_int, _P, c_double, c_double, c_double, _P]),
+  'rcd_adam_lazy_catchup': (c_int, [_P, _P, _P, c_int, _P, c_longlong, _P, c_longlong, _P, c_longlong, c_longlong,
+                                    c_double, c_double, c_double, c_double, c_int, _P]),
+  'rcd_adam_lazy_update': (c_int, [_P, _P, _P, c_int, _P, c_longlong, _P, c_int, _P, c_double, c_double, c_double,
+                                   c_double, c_double, c_longlong, _P]),
+  'rcd_adam_scalars': (c_int, [c_double, c_double, c_double, c_longlong, c_int, _P]),
   'rcd_sparse_adam_step': (c_int, [_P, _P, _P, c_int, _P, c_int, _P, c_int, c_double, c_double, c_double, c_double,
                                    c_longlong, _P]),
   'rcd_scatter_pos': (c_int, [_P, c_int, _P, c_int, _P]),

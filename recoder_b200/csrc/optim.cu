@@ -190,6 +190,106 @@ static __global__ void __launch_bounds__(256)
   }
 }
 
+
+// ---- deferred ("lazy") dense Adam -----------------------------------------------------------------------------------
+// torch.optim.Adam is dense: every row of an embedding table moves on every step, rows outside the batch with g = wd*p
+// (momentum, weight decay).  That is 24 B/param of HBM traffic per step over the WHOLE table (65 % of the step's bytes at
+// C3, 80 % at C5 / 512 users, the 1M-row user table of MF) for rows whose update does not depend on the batch at all.
+// Those updates are DEFERRED here, exactly: `last[r]` is the step up to which row r is current; before a step reads a
+// row (forward of a batch that contains it, evaluation, checkpoint) the skipped steps last[r]+1 .. T are replayed with
+// the very instruction sequence of k_adam (same fp32 operations in the same order, the per-step scalars lr/(1-b1^t) and
+// 1/sqrt(1-b2^t) from a device table the host fills in double precision like rcd_adam_step does) — the result is
+// bit-identical to the dense kernel's, the traffic is proportional to the rows the batch touches.
+//   k_adam_lazy_catchup : rows ids[0..n) (or all rows): replay steps last[r]+1 .. T with zero gradient
+//   k_adam_lazy_mark    : last[r] = T for the same rows (second launch: every thread of a row must have read last[r])
+//   k_adam_lazy_update  : rows ids[i] (current at T): the step T+1 with gradient row i; last[ids[i]] = T+1
+struct LazyConsts {
+  float beta2, eps, wd, omb1, omb2;
+};
+
+template <int VEC>
+static __global__ void __launch_bounds__(256)
+    k_adam_lazy_catchup(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, int H,
+                        const int64_t* __restrict__ ids, long long n, const int32_t* __restrict__ last, int T,
+                        const float2* __restrict__ scal, int scal_base, LazyConsts c) {
+  const int vpr = H / VEC;
+  const long long total = n * vpr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long k = i / vpr;
+    const long long r = ids ? ids[k] : k;
+    const int t0 = last[r];
+    if (t0 >= T) continue;
+    const int h = (int)(i - k * vpr) * VEC;
+    const size_t off = (size_t)r * H + h;
+    AdamScalars a;
+    a.beta2 = c.beta2; a.eps = c.eps; a.wd = c.wd; a.omb1 = c.omb1; a.omb2 = c.omb2;
+    if (VEC == 4) {
+      float4 pp = *reinterpret_cast<const float4*>(p + off);
+      float4 mm = *reinterpret_cast<const float4*>(m + off);
+      float4 vv = *reinterpret_cast<const float4*>(v + off);
+      for (int t = t0 + 1; t <= T; ++t) {
+        const float2 s = __ldg(scal + (t - scal_base));
+        a.step_size = s.x;
+        a.inv_bc2_sqrt = s.y;
+        adam_update(pp.x, mm.x, vv.x, 0.f, a);
+        adam_update(pp.y, mm.y, vv.y, 0.f, a);
+        adam_update(pp.z, mm.z, vv.z, 0.f, a);
+        adam_update(pp.w, mm.w, vv.w, 0.f, a);
+      }
+      *reinterpret_cast<float4*>(p + off) = pp;
+      *reinterpret_cast<float4*>(m + off) = mm;
+      *reinterpret_cast<float4*>(v + off) = vv;
+    } else {
+      float pp = p[off], mm = m[off], vv = v[off];
+      for (int t = t0 + 1; t <= T; ++t) {
+        const float2 s = __ldg(scal + (t - scal_base));
+        a.step_size = s.x;
+        a.inv_bc2_sqrt = s.y;
+        adam_update(pp, mm, vv, 0.f, a);
+      }
+      p[off] = pp;
+      m[off] = mm;
+      v[off] = vv;
+    }
+  }
+}
+
+static __global__ void k_adam_lazy_mark(const int64_t* __restrict__ ids, long long n, int32_t* __restrict__ last, int T) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) last[ids ? ids[i] : i] = T;
+}
+
+template <int VEC>
+static __global__ void __launch_bounds__(256)
+    k_adam_lazy_update(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, int H,
+                       const int64_t* __restrict__ ids, long long n, const float* __restrict__ grad_rows, int ldg,
+                       int32_t* __restrict__ last, int t_new, AdamScalars a) {
+  const int vpr = H / VEC;
+  const long long total = n * vpr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long k = i / vpr;
+    const long long r = ids ? ids[k] : k;
+    const int h = (int)(i - k * vpr) * VEC;
+    const size_t off = (size_t)r * H + h;
+    if (VEC == 4) {
+      float4 pp = __ldcs(reinterpret_cast<const float4*>(p + off));
+      float4 mm = __ldcs(reinterpret_cast<const float4*>(m + off));
+      float4 vv = __ldcs(reinterpret_cast<const float4*>(v + off));
+      const float4 g = __ldcs(reinterpret_cast<const float4*>(grad_rows + (size_t)k * ldg + h));
+      adam_vec4(p, m, v, off, g, a, pp, mm, vv);
+    } else {
+      float pp = p[off], mm = m[off], vv = v[off];
+      adam_update(pp, mm, vv, grad_rows[(size_t)k * ldg + h], a);
+      p[off] = pp;
+      m[off] = mm;
+      v[off] = vv;
+    }
+    if (h == 0) last[r] = t_new;
+  }
+}
+
 template <int VEC>
 static __global__ void __launch_bounds__(256)
     k_sgd(float* __restrict__ p, float* __restrict__ buf, long long rows, int H, const float* __restrict__ grad_rows,
@@ -316,6 +416,65 @@ RCD_EXPORT int rcd_adam_step(float* p, float* m, float* v, long long rows, int H
   else
     k_adam<1><<<stream_grid(rows * H), 256, 0, st>>>(p, m, v, rows, H, grad_rows, ldg, pos, a);
   RCD_LAUNCH_CHECK();
+  return RCD_OK;
+}
+
+
+RCD_EXPORT int rcd_adam_lazy_catchup(float* p, float* m, float* v, int H, const int64_t* ids, long long n,
+                                     int32_t* last, long long T, const float* scal, long long scal_base,
+                                     long long scal_len, double beta1, double beta2, double eps, double weight_decay,
+                                     int mark, void* stream) {
+  RCD_CHECK_ARG(p && m && v && last && scal && H > 0 && n >= 0, "bad arguments");
+  RCD_CHECK_ARG(T >= 0 && scal_base >= 0 && T - scal_base < scal_len, "step outside the scalar table");
+  if (n == 0) return RCD_OK;
+  LazyConsts c;
+  c.beta2 = (float)beta2; c.eps = (float)eps; c.wd = (float)weight_decay;
+  c.omb1 = (float)(1.0 - beta1); c.omb2 = (float)(1.0 - beta2);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (H % 4 == 0) && aligned16(p) && aligned16(m) && aligned16(v);
+  const float2* sc = reinterpret_cast<const float2*>(scal);
+  if (vec)
+    k_adam_lazy_catchup<4><<<stream_grid(n * (H / 4)), 256, 0, st>>>(p, m, v, H, ids, n, last, (int)T, sc, (int)scal_base, c);
+  else
+    k_adam_lazy_catchup<1><<<stream_grid(n * H), 256, 0, st>>>(p, m, v, H, ids, n, last, (int)T, sc, (int)scal_base, c);
+  RCD_LAUNCH_CHECK();
+  if (mark) {
+    k_adam_lazy_mark<<<rcd_div_up(n, 256), 256, 0, st>>>(ids, n, last, (int)T);
+    RCD_LAUNCH_CHECK();
+  }
+  return RCD_OK;
+}
+
+RCD_EXPORT int rcd_adam_lazy_update(float* p, float* m, float* v, int H, const int64_t* ids, long long n,
+                                    const float* grad_rows, int ldg, int32_t* last, double lr, double beta1,
+                                    double beta2, double eps, double weight_decay, long long t, void* stream) {
+  RCD_CHECK_ARG(p && m && v && last && grad_rows && H > 0 && n >= 0 && t >= 1 && ldg >= H, "bad arguments");
+  if (n == 0) return RCD_OK;
+  AdamScalars a;
+  a.beta2 = (float)beta2; a.eps = (float)eps; a.wd = (float)weight_decay;
+  a.omb1 = (float)(1.0 - beta1); a.omb2 = (float)(1.0 - beta2);
+  const double bc1 = 1.0 - pow(beta1, (double)t);
+  const double bc2 = 1.0 - pow(beta2, (double)t);
+  a.step_size = (float)(lr / bc1);
+  a.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (H % 4 == 0) && (ldg % 4 == 0) && aligned16(p) && aligned16(m) && aligned16(v) && aligned16(grad_rows);
+  if (vec)
+    k_adam_lazy_update<4><<<stream_grid(n * (H / 4)), 256, 0, st>>>(p, m, v, H, ids, n, grad_rows, ldg, last, (int)t, a);
+  else
+    k_adam_lazy_update<1><<<stream_grid(n * H), 256, 0, st>>>(p, m, v, H, ids, n, grad_rows, ldg, last, (int)t, a);
+  RCD_LAUNCH_CHECK();
+  return RCD_OK;
+}
+
+/* host helper: the per-step scalars of torch.optim.Adam exactly as rcd_adam_step forms them (double -> float) */
+RCD_EXPORT int rcd_adam_scalars(double lr, double beta1, double beta2, long long t_first, int count, float* out_host) {
+  RCD_CHECK_ARG(out_host && count > 0 && t_first >= 1, "bad arguments");
+  for (int i = 0; i < count; ++i) {
+    const double t = (double)(t_first + i);
+    out_host[2 * i] = (float)(lr / (1.0 - pow(beta1, t)));
+    out_host[2 * i + 1] = (float)(1.0 / sqrt(1.0 - pow(beta2, t)));
+  }
   return RCD_OK;
 }
 

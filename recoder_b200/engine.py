@@ -108,6 +108,8 @@ class ParamState:
     self.m = None   # Adam exp_avg / SGD momentum buffer
     self.v = None   # Adam exp_avg_sq
     self.shared = None  # p2p.SharedBuffer holding `p` when the table lives in peer-mapped memory
+    self.lazy = False   # deferred dense Adam (rcd_adam_lazy_*): `last[r]` = step up to which row r is current
+    self.last = None
 
   def view2d(self):
     t = self.p
@@ -135,6 +137,89 @@ class Optimizer:
         raise ValueError('Sparse gradients optimization not supported with %s' % optimizer_type)  # model.py:142-152
       self.states[name] = ParamState(name, p, wd, sp)
 
+  # --- deferred dense Adam (include/recoder_b200.h, rcd_adam_lazy_*) ---------------------------------------------------
+  SCAL_CHUNK = 4096       # per-step scalars are computed on the host this many steps ahead
+  FLUSH_EVERY = 16384     # every table is brought up to date at least this often (bounds the scalar table)
+
+  def enable_lazy(self, names):
+    """Defers the dense-Adam update of rows outside the batch for the given embedding tables (bit-identical results;
+    HBM traffic per step proportional to the batch's rows instead of the whole table)."""
+    if self.type != 'adam':
+      return
+    for n in names:
+      st = self.states[n]
+      if st.sparse or st.shared is not None or st.p.dim() != 2:
+        continue
+      self._ensure(st)
+      st.lazy = True
+      st.last = torch.full((st.p.shape[0],), st.step, dtype=torch.int32, device=st.p.device)
+    if any(s.lazy for s in self.states.values()) and getattr(self, '_scal', None) is None:
+      dev = next(s.p.device for s in self.states.values() if s.lazy)
+      self._scal_cap = self.FLUSH_EVERY + 2 * self.SCAL_CHUNK
+      self._scal = torch.zeros(self._scal_cap, 2, dtype=torch.float32, device=dev)
+      self._scal_pin = torch.zeros(self.SCAL_CHUNK, 2, dtype=torch.float32).pin_memory()
+      self._scal_base = 0        # step number of table entry 0
+      self._scal_upto = 0        # entries for steps <= _scal_upto are final (steps already taken)
+      self._scal_filled = 0      # entries for steps <= _scal_filled hold values for `_scal_lr`
+      self._scal_lr = None
+      self._scal_event = None
+
+  def lazy_names(self):
+    return [n for n, s in self.states.items() if s.lazy]
+
+  def _lazy_T(self):
+    """Steps taken so far by the lazy tables (they are stepped together)."""
+    steps = {s.step for s in self.states.values() if s.lazy}
+    assert len(steps) <= 1, 'deferred Adam tables must be stepped together'
+    return steps.pop() if steps else 0
+
+  def _ensure_scal(self, t):
+    """Makes the scalar-table entry of step `t` (the step about to be taken) valid for the current learning rate."""
+    if t - self._scal_base >= self._scal_cap - 1:
+      self.flush()     # rebase: everything current, history before `t` no longer needed
+      self._scal_base = t - 1
+      self._scal_filled = 0
+    if self._scal_lr != self.lr or t > self._scal_filled:
+      # (re)compute the entries of steps t .. t+CHUNK-1 with the current lr; entries of earlier steps are history
+      count = min(self.SCAL_CHUNK, self._scal_cap - (t - self._scal_base))
+      if self._scal_event is not None:
+        self._scal_event.synchronize()      # the previous upload has left the pinned buffer
+      lib = _native.load()
+      _native.check(lib.rcd_adam_scalars(float(self.lr), ADAM_BETAS[0], ADAM_BETAS[1], int(t), int(count),
+                                         self._scal_pin.data_ptr()), 'rcd_adam_scalars')
+      lo = t - self._scal_base
+      self._scal[lo:lo + count].copy_(self._scal_pin[:count], non_blocking=True)
+      self._scal_event = torch.cuda.Event()
+      self._scal_event.record()
+      self._scal_lr = self.lr
+      self._scal_filled = t + count - 1
+
+  def begin_step(self):
+    """Called on the main stream before a training step forks work to other streams: publishes the per-step scalars of
+    the step about to be taken (deferred tables replay them later)."""
+    if getattr(self, '_scal', None) is not None:
+      self._ensure_scal(self._lazy_T() + 1)
+
+  def catch_up(self, name, ids, n):
+    """Brings rows `ids[0:n]` (int64, device) of a lazy table up to date before they are read."""
+    st = self.states[name]
+    if not st.lazy or st.step == 0:
+      return
+    _, H = st.view2d()
+    call('rcd_adam_lazy_catchup', ptr(st.p), ptr(st.m), ptr(st.v), H, ptr(ids), int(n), ptr(st.last), st.step,
+         ptr(self._scal), self._scal_base, self._scal_cap, ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS,
+         float(st.weight_decay), 1)
+
+  def flush(self):
+    """Brings every row of every lazy table up to date (before evaluation, checkpoints, or anything else that reads
+    whole tables)."""
+    for st in self.states.values():
+      if st.lazy and st.step > 0:
+        rows, H = st.view2d()
+        call('rcd_adam_lazy_catchup', ptr(st.p), ptr(st.m), ptr(st.v), H, None, int(rows), ptr(st.last), st.step,
+             ptr(self._scal), self._scal_base, self._scal_cap, ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS,
+             float(st.weight_decay), 1)
+
   def _ensure(self, st):
     if st.m is None:
       st.m = torch.zeros_like(st.p)     # adam exp_avg | sgd momentum buffer | adagrad sum | rmsprop square_avg
@@ -152,6 +237,11 @@ class Optimizer:
       if st.sparse:
         call('rcd_sparse_adam_step', ptr(st.p), ptr(st.m), ptr(st.v), H, ptr(grad), ldg, ptr(ids), int(n_ids),
              float(self.sparse_lr), ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS, st.step)
+      elif st.lazy:
+        # rows of the batch only (they were caught up before the forward); the rest is replayed when next touched
+        assert self._scal_filled >= st.step and self._scal_lr == self.lr, 'Optimizer.begin_step() was not called'
+        call('rcd_adam_lazy_update', ptr(st.p), ptr(st.m), ptr(st.v), H, ptr(ids), int(n_ids), ptr(grad), ldg,
+             ptr(st.last), float(self.lr), ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS, float(st.weight_decay), st.step)
       else:
         call('rcd_adam_step', ptr(st.p), ptr(st.m), ptr(st.v), rows, H, ptr(grad), ldg, ptr(pos), float(self.lr),
              ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS, float(st.weight_decay), st.step)
@@ -195,6 +285,7 @@ class Optimizer:
 
   # --- torch.optim-compatible state_dict (param index = position in named_parameters(), model.py:208-215) ----
   def state_dict(self, dense=True):
+    self.flush()
     names = [n for n, s in self.states.items() if s.sparse != dense]
     state, groups = {}, []
     for i, n in enumerate(names):
@@ -464,8 +555,12 @@ class TrainEngine:
   LOSS_RING = 4096
 
   def __init__(self, kind, params, loss, confidence, activation, optimizer: Optimizer, gemm_engine=None,
-               process_group=None, tied=False, p2p=None, item_parallel=None, loss_module=None):
+               process_group=None, tied=False, p2p=None, item_parallel=None, loss_module=None, lazy_adam=False):
     _native.require_cuda()
+    # deferred dense Adam for the embedding tables: False (default for directly constructed engines: parameters are
+    # always current), True, or 'auto' = per table when the batches touch a small enough share of its rows
+    self.lazy_adam = lazy_adam
+    self._lazy_decided = False
     self.kind = kind
     self.params = params          # dict of role -> (name, tensor)
     self.loss_module = loss_module   # kind 'custom': any nn.Module with sum reduction (recoder/model.py:88-89)
@@ -508,6 +603,29 @@ class TrainEngine:
     self._native = None            # NativeStep, created on first use
     self.native_enabled = os.environ.get('RCD_NATIVE_STEP', '1') != '0'
     self._used_python_path = False
+
+  LAZY_GAIN = 0.9   # 'auto': defer when the estimated traffic is below this share of the dense update's
+
+  def _decide_lazy(self, pool, tpool, rows):
+    """Enables the deferred dense Adam (Optimizer.enable_lazy) per table on the first training step.  Estimate of the
+    traffic per parameter: dense 24 B over all T rows + 4 B over the n gradient rows; deferred 28 B over the n batch rows
+    + 24 B over the batch rows that were not in the previous batch (about n * (1 - n/T) of them)."""
+    self._lazy_decided = True
+    if not self.lazy_adam or self.opt.type != 'adam' or self.tied or self.p2p is not None:
+      return
+    if self.pg is not None and self.ip is None:
+      return
+    if self.kind == 'ae':
+      cand = [(self.params['en_w'][0], pool.n), (self.params['de_w'][0], tpool.n)]
+    else:
+      cand = [(self.params['user_w'][0], rows), (self.params['item_w'][0], tpool.n)]
+    names = []
+    for name, n in cand:
+      T = self.opt.states[name].p.shape[0]
+      est = (28.0 * n + 24.0 * n * (1.0 - n / T)) / (24.0 * T + 4.0 * n)
+      if self.lazy_adam is True or est < self.LAZY_GAIN:
+        names.append(name)
+    self.opt.enable_lazy(names)
 
   def _native_ok(self, pool, tpool, train):
     """True when the step can go through the native executor (`rcd_step_run`): single-hidden-layer autoencoder or
@@ -604,6 +722,9 @@ class TrainEngine:
     is averaged over (model.py:483-484); defaults to `rows`."""
     inv_b = 1.0 / float(global_rows or rows)
     self._check_pool(pool, target_pool)
+    if not self._lazy_decided:
+      self._decide_lazy(pool, target_pool or pool, rows)
+    self.opt.begin_step()
     loss_slot = self._loss_slot()
     if self._native_ok(pool, target_pool or pool, True):
       self._native_run(pool, target_pool or pool, row0, rows, inv_b, loss_slot, True)
@@ -1060,6 +1181,7 @@ class TrainEngine:
     Wg = b.get('Wg', n * ldh, torch.bfloat16)
     bg = b.get('bias_g', n, torch.float32)
     self._wait_ready('de')   # the previous step's W_d / b_d update (side stream; peers' pushes) has landed
+    self.opt.catch_up(de_name, t_items, n)      # deferred dense Adam: the batch's rows are brought up to date
     call('rcd_gather_rows', ptr(Wd), H, ptr(t_items), n, 0, ptr(Wg), ldh, None)
     call('rcd_gather_vec', ptr(bd), ptr(t_items), n, ptr(bg))
 
@@ -1076,6 +1198,7 @@ class TrainEngine:
     Z = b.get('Z', rows * H, torch.float32)
     Zb = b.get('Zb', rows * ldh, torch.bfloat16)
     self._wait_ready('en')
+    self.opt.catch_up(en_name, pool.items if pool.negative_sampling else None, n_in)
     call('rcd_ae_encoder_fwd', ptr(We), H, ptr(be), ptr(pool.row_ptr), ptr(pool.raw_items), ptr(in_vals),
          ptr(pool.row_inv_norm), row0, rows, self.act, ptr(Z), None if general else ptr(Zb), ldh)
     mid = None
@@ -1344,11 +1467,13 @@ class TrainEngine:
     Vg = b.get('Wg', n * ldd, torch.bfloat16)
     bg = b.get('bias_g', n, torch.float32)
     self._wait_ready('item')
+    self.opt.catch_up(v_name, t_items, n)
     call('rcd_gather_rows', ptr(V), D, ptr(t_items), n, 0, ptr(Vg), ldd, None)
     call('rcd_gather_vec', ptr(bias), ptr(t_items), n, ptr(bg))
     Ue = b.get('Z', rows * D, torch.float32)
     Ub = b.get('Zb', rows * ldd, torch.bfloat16)
     self._wait_ready('user')
+    self.opt.catch_up(u_name, users, rows)
     call('rcd_gather_rows', ptr(U), D, ptr(users), rows, self.act, ptr(Ub), ldd, ptr(Ue))
     drop = train and self.dropout_prob > 0.0
     Y = Ue
