@@ -20,7 +20,8 @@ A step = GPU collate of one batch of users + forward + loss + backward + optimiz
             `e2e` are timed with no per-kernel events), host enqueue vs wait time, per-rank times for N>1
 N>1: `--parallel rows` splits the users of the global batch (gradient exchange per `--dp-exchange`: the fused
 peer-memory reduce-scatter/Adam/all-gather kernel or one NCCL all-reduce); `--parallel items` splits the item axis
-(recoder_b200/itempar.py); `auto` picks the faster one as measured (profiles/README.md r01d).
+(recoder_b200/itempar.py); `auto` = items for the autoencoder configs (the faster mode at every N measured,
+profiles/README.md r02c/r02d), rows for matrix factorisation.
 `--impl reference` times that CPU arm alone, on the same config (global batch = per-GPU batch x N; steps of more
 than --cpu-max-batch users are sampled at that many users, stated in `cpu_baseline.sample`).
 Under torchrun (N>1) one process per GPU, NCCL; timing = CUDA events, max over ranks, barrier + synchronize on
@@ -328,6 +329,7 @@ def parity_check(w, U, indptr, indices, data, global_batch, gpu_first_loss):
   from recoder_b200.synth import epoch_user_order
   if gpu_first_loss is None:
     return {'error': 'first-step loss not recorded'}
+  torch.set_num_threads(cpu_threads())     # (torchrun exports OMP_NUM_THREADS=1 to every rank)
   I, H = w['items'], w['width']
   torch.manual_seed(0)
   if w['model'] == 'ae':
@@ -612,7 +614,15 @@ def b200_arm(args, w):
   # ---- parity of the benchmarked run: loss of its FIRST step against the CPU oracle with batch_size = global batch
   # (the reference's step on the same users, forward only, evaluated over row chunks), replicas bit-identical ---------
   parity = None
-  if not args.no_parity_check:
+  # the oracle forward costs 4*B*n*H flops on the host cores while every GPU of the box sits idle: beyond
+  # --parity-max-tflop it is skipped (and said so) unless --parity-check full
+  est_tflop = 4.0 * users_per_step * (np.mean(s_dev['n']) * (world if args.parallel == 'items' and world > 1 else 1)
+                                      if s_dev['n'] else 0.0) * H / 1e12
+  if not args.no_parity_check and args.parity_check != 'full' and est_tflop > args.parity_max_tflop:
+    parity = {'skipped': 'oracle forward of %.1f TFLOP on the host exceeds --parity-max-tflop %.1f (run with '
+                         '--parity-check full)' % (est_tflop, args.parity_max_tflop),
+              'replicas_identical': s_dev.get('replicas_identical')}
+  elif not args.no_parity_check:
     try:
       parity = parity_check(w, U, indptr, indices, data, users_per_step, s_dev.get('first_loss'))
       if world > 1:
@@ -667,8 +677,7 @@ def main():
                   help='N>1: fused peer-memory reduce-scatter/Adam/all-gather kernel (p2p) or NCCL all-reduce + full Adam')
   ap.add_argument('--parallel', default='auto', choices=['auto', 'rows', 'items'],
                   help='N>1: split the users of the global batch (data parallel, gradient exchange per --dp-exchange) '
-                       'or the item axis (itempar.py); auto = items for the autoencoder configs at 2-4 GPUs, rows '
-                       'otherwise (the faster of the two as measured, profiles/README.md)')
+                       'or the item axis (itempar.py); auto = items for the autoencoder configs, rows for matrix factorisation')
   ap.add_argument('--per-rank-kernels', action='store_true',
                   help='N>1 diagnostic: gather every rank\'s per-entry-point warm-up timings into the JSON line')
   ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -679,15 +688,17 @@ def main():
   ap.add_argument('--cpu-kind', default='auto', choices=['auto', 'reference', 'port'],
                   help='CPU arm: the unmodified reference (needs baseline/_ref or /root/reference) or the oracle port')
   ap.add_argument('--no-parity-check', action='store_true', help='skip the first-step loss check against the oracle')
+  ap.add_argument('--parity-check', default='auto', choices=['auto', 'full'],
+                  help='auto: skip the oracle forward when it exceeds --parity-max-tflop; full: always run it')
+  ap.add_argument('--parity-max-tflop', type=float, default=12.0)
   args = ap.parse_args()
   w = WORKLOADS[args.config]
   if args.parallel == 'auto':
-    # measured on C3 (profiles/README.md r01d): item-parallel wins at 2 and 4 GPUs (1.80 M / 2.85 M users/s against
-    # 1.46 M / 2.42 M for row-parallel + fused peer-memory exchange); at 8 GPUs the row-parallel exchange (NVLS
-    # multicast) measured 4.66 M against 2.5-3.3 M for the item-parallel mode, whose four NCCL collectives per step
-    # absorb the skew between eight ranks
-    world_env = int(os.environ.get('WORLD_SIZE', '1'))
-    args.parallel = 'items' if (w['model'] == 'ae' and 1 < world_env <= 4) else 'rows'
+    # measured on C3 (profiles/README.md r02c / r02d): with the native step executor the item-parallel mode runs at
+    # 1.69 M users/s on 2 GPUs and 6.71 M on 8 (one GPU: 0.85-0.88 M) against 1.35 M / 4.34 M for row-parallel + fused
+    # peer-memory exchange, so it is the autoencoder default at every N; matrix factorisation has no item-parallel
+    # mode (its user table is indexed by row) and uses the row-parallel exchange
+    args.parallel = 'items' if w['model'] == 'ae' else 'rows'
   if args.impl == 'reference':
     reference_arm(args, w)
   else:

@@ -36,6 +36,14 @@ extern "C" {
 #define RCD_ACT_TANH 1
 #define RCD_ACT_SIGMOID 2
 #define RCD_ACT_RELU 3
+/* further `torch.<name>` unary functions whose derivative is a function of the OUTPUT (what the backward kernels keep) */
+#define RCD_ACT_SELU 4
+#define RCD_ACT_CELU 5       /* alpha = 1 (torch.celu default) */
+#define RCD_ACT_HARDSHRINK 6 /* lambda = 0.5 */
+#define RCD_ACT_ATAN 7
+#define RCD_ACT_SINH 8
+#define RCD_ACT_ASINH 9
+#define RCD_ACT_EXPM1 10
 
 /* loss ids — recoder/model.py:87-99 `__init_loss_module` */
 #define RCD_LOSS_MSE 0      /* recoder/losses.py:16-47  MSELoss(confidence, 'sum') */
@@ -395,7 +403,7 @@ int rcd_gemm_bf16(int mode, const uint16_t* A, int lda, const uint16_t* B, int l
  *     rcd_step_profile(ctx, mode): 0 off, 1 CUDA events around every entry point, 2 around the entry point named
  *     `name` only; rcd_step_profile_read sums the event pairs per entry point (synchronises) and clears them.
  * ------------------------------------------------------------------------------------------------------- */
-#define RCD_STEP_ABI 2
+#define RCD_STEP_ABI 3
 #define RCD_MODEL_AE 0
 #define RCD_MODEL_MF 1
 #define RCD_OPT_ADAM 0
@@ -412,6 +420,7 @@ typedef struct rcd_param {
   int pad_;
   double weight_decay;
   long long t;         /* 1-based step count of THIS step (Adam bias correction) */
+  int32_t* last;       /* deferred dense Adam (rcd_adam_lazy_*): per-row step counters, or NULL = dense update */
 } rcd_param;
 
 typedef struct rcd_pool_view { /* outputs of rcd_collate for one pool (all device pointers) */
@@ -463,6 +472,8 @@ typedef struct rcd_step_args {
   int32_t* bad_flag;
   int32_t* redo_flag;
   int32_t* user_pos;     /* MF: int32 [num_users], all -1 between steps */
+  const float* scal;     /* deferred dense Adam: per-step scalars (rcd_adam_lazy_catchup), steps scal_base .. +scal_len-1 */
+  long long scal_base, scal_len;
   void* stream_main;
   void* stream_side;
   void* stream_aux;

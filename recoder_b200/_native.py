@@ -13,7 +13,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'csrc', 'librecoder_b200.so')
 
-ACT_IDS = {'none': 0, 'tanh': 1, 'sigmoid': 2, 'relu': 3}
+ACT_IDS = {'none': 0, 'tanh': 1, 'sigmoid': 2, 'relu': 3, 'selu': 4, 'celu': 5, 'hardshrink': 6, 'atan': 7, 'sinh': 8,
+           'asinh': 9, 'expm1': 10}
 LOSS_IDS = {'mse': 0, 'logloss': 1, 'logistic': 2}
 GEMM_TCGEN05, GEMM_SIMT = 0, 1
 DEC_MODE_LOSS, DEC_MODE_ROWMAX = 0, 1
@@ -100,7 +101,7 @@ _SIGNATURES = {
 # ---- K12 native step executor: C structs of include/recoder_b200.h ("K12") ------------------------------------------
 class RcdParam(ctypes.Structure):
   _fields_ = [('p', _P), ('s1', _P), ('s2', _P), ('rows', c_longlong), ('cols', c_int), ('pad_', c_int),
-              ('weight_decay', c_double), ('t', c_longlong)]
+              ('weight_decay', c_double), ('t', c_longlong), ('last', _P)]
 
 
 class RcdPoolView(ctypes.Structure):
@@ -122,12 +123,13 @@ class RcdStepArgs(ctypes.Structure):
               ('pool_in', RcdPoolView), ('pool_tgt', RcdPoolView), ('same_pool', c_int), ('row0', c_int),
               ('rows', c_int), ('cap_rows', c_int), ('cap_n', c_int), ('cap_n_in', c_int), ('cap_nnz', c_longlong),
               ('cap_tnnz', c_longlong), ('ws', _P), ('ws_bytes', c_size_t), ('loss_acc', _P), ('bad_flag', _P),
-              ('redo_flag', _P), ('user_pos', _P), ('stream_main', _P), ('stream_side', _P), ('stream_aux', _P),
+              ('redo_flag', _P), ('user_pos', _P), ('scal', _P), ('scal_base', c_longlong), ('scal_len', c_longlong),
+              ('stream_main', _P), ('stream_side', _P), ('stream_aux', _P),
               ('ip', RcdStepIp), ('out_dW_in', c_longlong), ('out_db_in', c_longlong), ('out_dW_out', c_longlong),
               ('out_db_out', c_longlong)]
 
 
-STEP_ABI = 2
+STEP_ABI = 3
 MODEL_IDS = {'ae': 0, 'mf': 1}
 OPT_IDS = {'adam': 0, 'sgd': 1, 'adagrad': 2, 'rmsprop': 3}
 

@@ -69,13 +69,23 @@ __device__ __forceinline__ int warp_sum_i(int v) {
   return v;
 }
 
-// Activation ids shared by host and device (recoder/nn.py:6-9 allows any torch.<name>; these are the ones
-// the reference's scripts, docs and tests use).
+// Activation ids shared by host and device.  recoder/nn.py:6-9 accepts any `torch.<name>`; the backward kernels keep the
+// activation OUTPUT only, so the supported set is the unary torch functions whose derivative is a function of the output:
+// the ones the reference's scripts, docs and tests use (tanh, sigmoid, relu) plus selu, celu, hardshrink, atan, sinh,
+// asinh, expm1.  (abs, square, sin, erf, ... need the pre-activation and raise NotImplementedError in nn.py.)
 __device__ __forceinline__ float act_apply(float x, int act) {
   switch (act) {
     case RCD_ACT_TANH: return tanhf(x);
     case RCD_ACT_SIGMOID: return 1.0f / (1.0f + expf(-x));
     case RCD_ACT_RELU: return fmaxf(x, 0.0f);
+    case RCD_ACT_SELU: return 1.0507009873554804934193349852946f *
+                              (x > 0.f ? x : 1.6732632423543772848170429916717f * expm1f(x));
+    case RCD_ACT_CELU: return x > 0.f ? x : expm1f(x);
+    case RCD_ACT_HARDSHRINK: return fabsf(x) > 0.5f ? x : 0.f;
+    case RCD_ACT_ATAN: return atanf(x);
+    case RCD_ACT_SINH: return sinhf(x);
+    case RCD_ACT_ASINH: return asinhf(x);
+    case RCD_ACT_EXPM1: return expm1f(x);
     default: return x;
   }
 }
@@ -85,6 +95,15 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act) {
     case RCD_ACT_TANH: return 1.0f - y * y;
     case RCD_ACT_SIGMOID: return y * (1.0f - y);
     case RCD_ACT_RELU: return y > 0.0f ? 1.0f : 0.0f;
+    // selu: scale for x > 0, scale*alpha*e^x = y + scale*alpha otherwise
+    case RCD_ACT_SELU: return y > 0.0f ? 1.0507009873554804934193349852946f
+                                       : y + 1.0507009873554804934193349852946f * 1.6732632423543772848170429916717f;
+    case RCD_ACT_CELU: return y > 0.0f ? 1.0f : y + 1.0f;          // e^x = y + 1
+    case RCD_ACT_HARDSHRINK: return y != 0.0f ? 1.0f : 0.0f;
+    case RCD_ACT_ATAN: { const float c = cosf(y); return c * c; }  // 1/(1+x^2) = cos^2(atan x)
+    case RCD_ACT_SINH: return sqrtf(fmaf(y, y, 1.0f));             // cosh x
+    case RCD_ACT_ASINH: return 1.0f / coshf(y);                    // 1/sqrt(1+x^2)
+    case RCD_ACT_EXPM1: return y + 1.0f;
     default: return 1.0f;
   }
 }

@@ -150,9 +150,16 @@ static cudaEvent_t prof_event(StepCtx* c) {
   } while (0)
 
 static int opt_step(StepCtx* c, const rcd_step_args& a, const rcd_param& p, const float* grad, int ldg, const int32_t* pos,
-                    void* st) {
+                    void* st, const int64_t* ids = nullptr, long long n_ids = 0) {
   const long long rows = p.rows;
   const int H = p.cols;
+  if (p.last) {  // deferred dense Adam: the batch's rows only (ids NULL: the identity, i.e. every row)
+    RCD_CHECK_ARG(a.optimizer == RCD_OPT_ADAM, "deferred updates are an Adam mode");
+    STEP_CALL("rcd_adam_lazy_update", st,
+              rcd_adam_lazy_update(p.p, p.s1, p.s2, H, ids, n_ids, grad, ldg, p.last, a.lr, 0.9, 0.999, 1e-8,
+                                   p.weight_decay, p.t, st));
+    return RCD_OK;
+  }
   switch (a.optimizer) {
     case RCD_OPT_ADAM:
       STEP_CALL("rcd_adam_step", st,
@@ -173,6 +180,16 @@ static int opt_step(StepCtx* c, const rcd_step_args& a, const rcd_param& p, cons
       rcd_set_error("rcd_step_run: unknown optimizer %d", a.optimizer);
       return RCD_ERR_INVALID;
   }
+  return RCD_OK;
+}
+
+// deferred dense Adam: rows ids[0..n) of table `p` are brought up to date (steps <= p.t - 1) before they are read
+static int catch_up(StepCtx* c, const rcd_step_args& a, const rcd_param& p, const int64_t* ids, long long n, void* st) {
+  if (!p.last || p.t <= 1) return RCD_OK;
+  RCD_CHECK_ARG(a.scal, "deferred Adam needs the scalar table");
+  STEP_CALL("rcd_adam_lazy_catchup", st,
+            rcd_adam_lazy_catchup(p.p, p.s1, p.s2, p.cols, ids, n, p.last, p.t - 1, a.scal, a.scal_base, a.scal_len, 0.9,
+                                  0.999, 1e-8, p.weight_decay, 1, st));
   return RCD_OK;
 }
 
@@ -435,6 +452,13 @@ RCD_EXPORT int rcd_step_run(void* ctx, rcd_step_args* args) {
     if (ss != sm) RCD_CUDA(cudaStreamWaitEvent(sm, c->ev_out, 0));
     c->out_pending = false;
   }
+  {
+    int rc = catch_up(c, a, a.table_out, a.tgt.items, a.tgt.items ? n : a.table_out.rows, st);
+    if (rc != RCD_OK) return rc;
+    if (ae) rc = catch_up(c, a, a.table_in, a.in.items, a.in.items ? n_in : a.table_in.rows, st);
+    else rc = catch_up(c, a, a.table_in, a.in.users + row0, rows, st);
+    if (rc != RCD_OK) return rc;
+  }
   STEP_CALL("rcd_gather_rows", st, rcd_gather_rows(a.table_out.p, H, a.tgt.items, n, 0, Wg, ldh, nullptr, st));
   STEP_CALL("rcd_gather_vec", st, rcd_gather_vec(a.bias_out.p, a.tgt.items, n, bg, st));
   float* row_ref_ip = nullptr;
@@ -532,7 +556,8 @@ RCD_EXPORT int rcd_step_run(void* ctx, rcd_step_args* args) {
     RCD_CUDA(cudaStreamWaitEvent(ss, c->ev_fork, 0));
   }
   {
-    int rc = opt_step(c, a, a.table_out, dW_out, H, a.tgt.pos, (void*)ss);
+    int rc = opt_step(c, a, a.table_out, dW_out, H, a.tgt.pos, (void*)ss, a.tgt.items,
+                      a.tgt.items ? n : a.table_out.rows);
     if (rc != RCD_OK) return rc;
     rc = opt_step(c, a, a.bias_out, db_out, 1, a.tgt.pos, (void*)ss);
     if (rc != RCD_OK) return rc;
@@ -582,7 +607,7 @@ RCD_EXPORT int rcd_step_run(void* ctx, rcd_step_args* args) {
                                    reinterpret_cast<int32_t*>(ws + L.csc_row[k]),
                                    reinterpret_cast<float*>(ws + L.csc_val[k]), a.in.row_inv_norm, row0, n_in, dW_in,
                                    nullptr, nullptr, heavy, hb, innz, st));
-    int rc = opt_step(c, a, a.table_in, dW_in, H, a.in.pos, st);
+    int rc = opt_step(c, a, a.table_in, dW_in, H, a.in.pos, st, a.in.items, a.in.items ? n_in : a.table_in.rows);
     if (rc != RCD_OK) return rc;
     rc = opt_step(c, a, a.bias_in, db_in, 1, nullptr, st);
     if (rc != RCD_OK) return rc;
@@ -590,7 +615,7 @@ RCD_EXPORT int rcd_step_run(void* ctx, rcd_step_args* args) {
     RCD_CHECK_ARG(a.user_pos, "MF needs user_pos");
     const int64_t* users = a.in.users + row0;
     STEP_CALL("rcd_scatter_pos", st, rcd_scatter_pos(users, rows, a.user_pos, 0, st));
-    int rc = opt_step(c, a, a.table_in, dW_in, H, a.user_pos, st);
+    int rc = opt_step(c, a, a.table_in, dW_in, H, a.user_pos, st, users, rows);
     if (rc != RCD_OK) return rc;
     STEP_CALL("rcd_scatter_pos", st, rcd_scatter_pos(users, rows, a.user_pos, 1, st));
   }

@@ -389,6 +389,7 @@ class NativeStep:
     dst.rows, dst.cols = rows, cols
     dst.weight_decay = float(st.weight_decay)
     dst.t = t
+    dst.last = st.last.data_ptr() if st.lazy else None
 
   @staticmethod
   def _fill_pool(dst, pb, row0, rows):
@@ -482,6 +483,8 @@ class NativeStep:
     a.train = int(train)
     a.overlap = int(e.overlap)
     a.loss_acc = loss_slot.data_ptr()
+    if getattr(opt, '_scal', None) is not None:
+      a.scal, a.scal_base, a.scal_len = opt._scal.data_ptr(), opt._scal_base, opt._scal_cap
     # workspace capacities: grow-only with head-room; the layout is a function of the capacities alone
     c = self.caps
     need = {'rows': rows, 'n': tpool.n, 'n_in': pool.n, 'nnz': a.pool_in.nnz_slice, 'tnnz': a.pool_tgt.nnz_slice}
@@ -1355,6 +1358,7 @@ class TrainEngine:
     Wg = b.get('Wg', n * ldh, torch.bfloat16)
     bg = b.get('bias_g', n, torch.float32)
     self._wait_ready('de')
+    self.opt.catch_up(de_name, pool.items, n)
     call('rcd_gather_rows', ptr(Wd), H, ptr(pool.items), n, 0, ptr(Wg), ldh, None)
     call('rcd_gather_vec', ptr(bd), ptr(pool.items), n, ptr(bg))
 
@@ -1367,6 +1371,7 @@ class TrainEngine:
       zero_bias.zero_()
       self._zero_bias_init = True
     self._wait_ready('en')
+    self.opt.catch_up(en_name, pool.items, n)
     call('rcd_ae_encoder_fwd', ptr(We), H, ptr(zero_bias), ptr(pool.row_ptr), ptr(pool.raw_items), ptr(pool.vals),
          ptr(pool.row_inv_norm), row0, rows, none, ptr(Zp), None, ldh)
     self._ip_allreduce('allreduce_Z', Zp, sh, o_z)

@@ -79,7 +79,7 @@ class Recoder(object):
                optimizer_type='sgd', loss='mse',
                loss_params=None, use_cuda=False,
                user_based=True, item_based=True,
-               process_group=None, gemm_engine=None, dp_exchange='auto', parallel='rows'):
+               process_group=None, gemm_engine=None, dp_exchange='auto', parallel='rows', lazy_adam='auto'):
 
     self.model = model
     self.num_items = num_items
@@ -98,6 +98,12 @@ class Recoder(object):
     if parallel not in ('rows', 'items'):
       raise ValueError("parallel must be 'rows' or 'items'")
     self.parallel = parallel
+    # deferred dense Adam (engine.Optimizer.enable_lazy): 'auto' (per table, when the batches touch a small enough
+    # share of its rows), True or False; RCD_LAZY_ADAM=0|1|auto overrides.  Results are bit-identical either way.
+    env = os.environ.get('RCD_LAZY_ADAM')
+    if env is not None:
+      lazy_adam = {'0': False, '1': True}.get(env, 'auto')
+    self.lazy_adam = lazy_adam
     self._p2p = None
     self._ip = None
 
@@ -266,9 +272,16 @@ class Recoder(object):
             entry[k] = self._ip.gather_full(v.to(self.device), full_rows[name]).cpu()
     return sd
 
+  def flush_parameters(self):
+    """Deferred dense Adam: brings every table row up to date (a no-op when nothing is deferred).  Called before
+    anything reads whole tables: evaluation, recommendations, checkpoints, the end of `train()`."""
+    if self.optimizer is not None:
+      self.optimizer.flush()
+
   def sync_parameters(self):
     """Item-parallel mode: gathers the item shards back into the model's (full-size) parameters — called before
     evaluation and checkpoints; collective.  A no-op otherwise."""
+    self.flush_parameters()
     if self._ip is not None:
       if self.engine is not None:
         self.engine.join()
@@ -288,7 +301,10 @@ class Recoder(object):
       self.optimizer.states[name].shared = buf
     self.engine = TrainEngine(kind, roles, loss_kind, confidence, activation, self.optimizer,
                               gemm_engine=self.gemm_engine, process_group=pg, tied=tied, p2p=self._p2p,
-                              item_parallel=self._ip, loss_module=loss_module)
+                              item_parallel=self._ip, loss_module=loss_module, lazy_adam=self.lazy_adam)
+    if not getattr(self, '_flush_hook', None):
+      # anything that serialises the model sees current rows
+      self._flush_hook = self.model.register_state_dict_pre_hook(lambda *a, **k: self.flush_parameters())
 
   def init_from_model_file(self, model_file):
     """
@@ -592,6 +608,7 @@ class Recoder(object):
 
       if self._sync_loss_every_step:
         self.engine.drain_deferred_loss()
+      self.flush_parameters()     # the model's parameters are current at every epoch boundary
       if self._ip is not None and ((eval_freq > 0 and epoch % eval_freq == 0) or epoch == num_epochs or
                                    (checkpoint_freq > 0 and epoch % checkpoint_freq == 0)):
         self.sync_parameters()
@@ -648,6 +665,7 @@ class Recoder(object):
     if self.model is None:
       raise Exception('Model not initialized.')
     self.__require_cuda()
+    self.flush_parameters()
     self.model.eval()
     batch_collator = BatchCollator(batch_size=len(users_interactions.users), negative_sampling=False)
     batch = batch_collator.collate(users_interactions)[0]
@@ -680,6 +698,7 @@ class Recoder(object):
     self.__require_cuda()
     if self.engine is not None:
       self.engine.join()
+    self.flush_parameters()
     self.model.eval()
     # the pool is collated on the GPU (no negative sampling: columns are raw item ids) and goes through the encoder as
     # CSR; the dense [B, I] input and the boolean mask pass of the reference (model.py:502-510, 541) never exist

@@ -25,7 +25,9 @@ SUPPORTED_ACTIVATIONS = tuple(_native.ACT_IDS.keys())
 
 def _check_activation(act):
   if act not in _native.ACT_IDS:
-    raise NotImplementedError("activation '%s' has no B200 kernel; supported: %s" % (act, SUPPORTED_ACTIVATIONS))
+    raise NotImplementedError("activation '%s' has no B200 kernel: the backward kernels keep the activation output "
+                              "only, so torch.<name> functions whose derivative needs the pre-activation are not "
+                              "covered; supported: %s" % (act, SUPPORTED_ACTIVATIONS))
 
 
 def _xavier_uniform_(t):

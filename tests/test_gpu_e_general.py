@@ -221,3 +221,54 @@ def test_custom_loss_module_step_matches_oracle(kind, loss_module):
     assert np.linalg.norm(got) == pytest.approx(np.linalg.norm(w), rel=5e-3), key
     assert rel_err(got, w) < 3e-2, key
   assert abs(eng.eval_loss(pool, 0, B) - float(tr.compute_loss(ob).item())) < 2e-3 * abs(oloss) + 1e-2
+
+
+ACTS = ['tanh', 'sigmoid', 'relu', 'selu', 'celu', 'hardshrink', 'atan', 'sinh', 'asinh', 'expm1']
+
+
+@pytest.mark.parametrize('act', ACTS)
+def test_activation_forward_and_derivative_match_torch(act):
+  """recoder/nn.py:6-9 applies `torch.<activation_type>`: the kernels' forward (rcd_bias_act) and their derivative
+  expressed through the OUTPUT (rcd_act_grad) against torch and torch autograd."""
+  rows, H = 257, 72
+  g = torch.Generator(device='cuda').manual_seed(3)
+  x = (torch.randn(rows, H, device='cuda', generator=g) * 1.5)
+  bias = torch.randn(H, device='cuda', generator=g) * 0.1
+  Z = torch.empty(rows, H, device='cuda')
+  call('rcd_bias_act', ptr(x), ptr(bias), rows, H, _native.ACT_IDS[act], ptr(Z), None, H)
+  pre = (x + bias).double().requires_grad_(True)
+  want = getattr(torch, act)(pre)
+  torch.testing.assert_close(Z.double(), want.detach(), rtol=2e-6, atol=2e-6)
+  dy = torch.randn(rows, H, device='cuda', generator=g)
+  want.backward(dy.double())
+  dpre = torch.empty(rows, H, device='cuda')
+  call('rcd_act_grad', ptr(dy), ptr(Z), rows * H, _native.ACT_IDS[act], ptr(dpre))
+  torch.testing.assert_close(dpre.double(), pre.grad, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('act', ['selu', 'celu', 'atan'])
+def test_step_with_other_torch_activations_matches_oracle(act):
+  U, I, H, B = 2000, 6000, 96, 256
+  indptr, indices, data = synthetic_csr(U, I, 40, seed=13)
+  params = O.init_ae_params(I, [H], seed=3)
+  tr = O.OracleTrainer('ae', params, loss='logloss', optimizer='adam', lr=1e-3, activation=act)
+  model = make_model('ae', I, U, [H], act, {k: v.numpy() for k, v in params.items()})
+  eng = make_engine(model, 'logloss', 0.0, 'adam', 1e-3, 0.0, _native.GEMM_TCGEN05)
+  ds = device_dataset(indptr, indices, data, I)
+  users = np.arange(B)
+  pool = collate_pool(ds.device_csr(), users, True)
+  ob = O.collate(indptr, indices, data, I, users, B, True)[0]
+  oloss, ograds = tr.step(ob)
+  eng.train_step(pool, 0, B)
+  assert float(eng.losses(1)[0]) == pytest.approx(oloss, rel=1e-3)
+  for key, name in (('dWe', O.AE_EN_W), ('dWd', O.AE_DE_W)):
+    want = ograds[name].numpy()[ob.items]
+    got = eng.last[key].detach().cpu().numpy()
+    assert np.linalg.norm(got) == pytest.approx(np.linalg.norm(want), rel=1e-3), key
+    assert rel_err(got, want) < 2e-2, key
+
+
+def test_unsupported_activation_is_refused_loudly():
+  from recoder_b200.nn import DynamicAutoencoder
+  with pytest.raises(NotImplementedError, match='pre-activation'):
+    DynamicAutoencoder(hidden_layers=[8], activation_type='sin').init_model(num_items=10)
