@@ -73,7 +73,9 @@ def load_peaks():
     return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source='fallback')
 
 
-NCU_KERNEL_OF = {'rcd_adam_step': 'k_adam<4>', 'rcd_decoder_fwd_loss': 'k_decoder_fused', 'rcd_adam_step_p2p': 'k_adam_p2p'}
+NCU_KERNEL_OF = {'rcd_adam_step': 'k_adam<4>', 'rcd_decoder_fwd_loss': 'k_decoder_fused', 'rcd_adam_step_p2p': 'k_adam_p2p',
+                 'rcd_adam_lazy_update': 'k_adam_lazy_update<4>', 'rcd_adam_lazy_catchup': 'k_adam_lazy_catchup<4>',
+                 'rcd_decoder_wgrad': 'k_gemm_tc<2>', 'rcd_decoder_dgrad': 'k_gemm_tc<2>'}
 
 
 def ncu_traffic(entry_point):
@@ -297,6 +299,10 @@ def kernel_work(name, w, rows, n, n_in, nnz_rows, tables):
   if name == 'rcd_adam_step':
     params, grads = tables[0], tables[1]
     return 'hbm', 24.0 * params + 4.0 * grads
+  if name == 'rcd_adam_lazy_update':
+    # deferred dense Adam: the batch's rows only — read p, m, v + the gradient row, write p, m, v = 28 B/param
+    grads = tables[1]
+    return 'hbm', 28.0 * grads
   if name == 'rcd_adam_step_p2p':
     # per rank: NVLink ingress = the other ranks' gradient rows of the owned shard + the other ranks' pushed rows
     params, grads, world = tables if len(tables) == 3 else (tables[0], tables[1], 1)

@@ -90,6 +90,75 @@ class HostStagedCSR:
       slot['event'].synchronize()  # the previous H2D copy out of this slot has finished
     return slot
 
+  def stage_sharded(self, users: np.ndarray, rank: int, world: int, pg):
+    """Data-parallel staging: every rank needs the WHOLE pool on its device (the item set of a step is that of the
+    global batch) but copies only ITS block of rows over PCIe; the blocks are then exchanged device to
+    device (one NCCL all-gather over NVLink).  Layout of the result: block q occupies [q*M, q*M + nnz_q) of the index /
+    value arrays (M = the largest block), and the pool-local indptr carries one dummy row per block that covers the
+    padding, so the rows the collate gathers are contiguous as usual.  Returns (mini CSR, positions int64[P] of the pool
+    rows inside it)."""
+    import torch.distributed as dist
+    lib = _native.load()
+    P = int(users.size)
+    per = P // world
+    assert per * world == P
+    lens = self.indptr_host[users + 1] - self.indptr_host[users]
+    block_nnz = lens.reshape(world, per).sum(axis=1)
+    M = int(max(int(block_nnz.max()), 1))
+    mine = users[rank * per:(rank + 1) * per]
+    slot = self._slot(per, M)
+    got = lib.rcd_host_stage_rows(self.indptr_host.ctypes.data, self.indices_host.ctypes.data,
+                                  self.data_host.ctypes.data, mine.ctypes.data, per, int(self.shape[0]),
+                                  int(slot['idx'].numel()), slot['ptr'].data_ptr(), slot['idx'].data_ptr(),
+                                  slot['val'].data_ptr())
+    if got < 0:
+      _native.check(int(got), 'rcd_host_stage_rows')
+    sh = slot.get('shard')
+    if sh is None or sh['idx'].numel() < world * M or sh['ptr'].numel() < P + world + 1:
+      cap_m, cap_p = int(M * 1.25) + 16, P + world + 1
+      sh = {'cap_m': cap_m,
+            'send': torch.empty(2 * cap_m, dtype=torch.int32, device=self.device),
+            'recv': torch.empty(2 * cap_m * world, dtype=torch.int32, device=self.device),
+            'idx': torch.empty(cap_m * world, dtype=torch.int32, device=self.device),
+            'val': torch.empty(cap_m * world, dtype=torch.float32, device=self.device),
+            'ptr': torch.empty(cap_p, dtype=torch.int64, device=self.device),
+            'ptr_pin': torch.empty(cap_p, dtype=torch.int64).pin_memory()}
+      slot['shard'] = sh
+    # own block -> device (indices and value bit patterns packed into one buffer), then one all-gather
+    nnz_r = int(block_nnz[rank])
+    send = sh['send'][:2 * M]
+    send[:nnz_r].copy_(slot['idx'][:nnz_r], non_blocking=True)
+    send[M:M + nnz_r].copy_(slot['val'][:nnz_r].view(torch.int32), non_blocking=True)
+    recv = sh['recv'][:2 * M * world]
+    dist.all_gather_into_tensor(recv, send, group=pg)
+    rv = recv.view(world, 2, M)
+    idx, val = sh['idx'][:world * M], sh['val'][:world * M]
+    idx.view(world, M).copy_(rv[:, 0, :])
+    val.view(world, M).copy_(rv[:, 1, :].view(torch.float32))
+    # pool-local indptr with one dummy row per block (covers the padding up to the next block)
+    ptr = np.empty(P + world + 1, dtype=np.int64)
+    starts = np.zeros((world, per + 1), dtype=np.int64)
+    np.cumsum(lens.reshape(world, per), axis=1, out=starts[:, 1:])
+    starts += (np.arange(world, dtype=np.int64) * M)[:, None]
+    ptr[:-1] = starts.reshape(-1)
+    ptr[-1] = world * M
+    sh['ptr_pin'][:P + world + 1].copy_(torch.from_numpy(ptr))
+    d_ptr = sh['ptr'][:P + world + 1]
+    d_ptr.copy_(sh['ptr_pin'][:P + world + 1], non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    slot['event'] = ev
+    mini = DeviceCSR.__new__(DeviceCSR)
+    mini.device = self.device
+    mini.shape = (P + world, self.shape[1])
+    mini.indptr_host = ptr
+    mini.indptr = d_ptr
+    mini.indices = idx
+    mini.data = val
+    TRANSFER_BYTES['h2d'] += 2 * max(nnz_r, 1) * 4 + (P + world + 1) * 8
+    positions = np.arange(P, dtype=np.int64) + np.arange(P, dtype=np.int64) // per
+    return mini, positions
+
   def stage(self, users: np.ndarray):
     lib = _native.load()
     P = int(users.size)
@@ -305,7 +374,7 @@ class PoolRing:
 
 
 def collate_pool_launch(csr, users, negative_sampling: bool, stream=None, after=(), ring=None,
-                        row_constants=None, table_rows=None) -> PoolBatch:
+                        row_constants=None, table_rows=None, stage_shard=None) -> PoolBatch:
   """Enqueues K1 on the rows `users` of `csr` (DeviceCSR, or HostStagedCSR: staged over PCIe first) and an
   asynchronous read-back of the two counts (n, nnz) every downstream shape depends on.  The returned PoolBatch is
   usable after `collate_pool_finish`.  Launching the collate of pool i+1 before the training step of pool i is
@@ -322,7 +391,10 @@ def collate_pool_launch(csr, users, negative_sampling: bool, stream=None, after=
   `table_rows`: rows of the embedding tables the pool will train (the model's `num_items`).  The reference allows a
   model wider than the matrix (`assert num_items >= max item id + 1`, recoder/model.py:241): the item -> column map
   `pos`, which the optimizer kernels read for EVERY table row, is then `table_rows` long with -1 beyond the matrix
-  width.  A matrix wider than the model is an error (the reference fails inside its embedding lookup)."""
+  width.  A matrix wider than the model is an error (the reference fails inside its embedding lookup).
+
+  `stage_shard` = (rank, world, process group): data-parallel runs on a host-resident matrix — every rank stages only
+  its own block of the pool's rows and the blocks are all-gathered device to device (HostStagedCSR.stage_sharded)."""
   users = np.ascontiguousarray(np.asarray(users).reshape(-1), dtype=np.int64)
   assert users.size > 0
   assert users.min() >= 0 and users.max() < csr.shape[0], 'user index out of range'
@@ -365,9 +437,13 @@ def collate_pool_launch(csr, users, negative_sampling: bool, stream=None, after=
     TRANSFER_BYTES['h2d'] += P * 8
     rows_dev = users_dev
     if isinstance(csr, HostStagedCSR):
-      csr = csr.stage(users)
-      users = np.arange(P, dtype=np.int64)
-      rows_dev = _arange_cached(P, dev)
+      if stage_shard is not None and stage_shard[1] > 1 and P % stage_shard[1] == 0:
+        csr, users = csr.stage_sharded(users, *stage_shard)
+        rows_dev = _positions_cached(P, stage_shard[1], dev)
+      else:
+        csr = csr.stage(users)
+        users = np.arange(P, dtype=np.int64)
+        rows_dev = _arange_cached(P, dev)
   lens = csr.indptr_host[users + 1] - csr.indptr_host[users]
   nnz = int(lens.sum())
   assert nnz < 2 ** 31, 'pool too large'
@@ -422,6 +498,20 @@ def _arange_cached(n, dev):
     t = torch.arange(int(n * 1.25) + 16, dtype=torch.int64, device=dev)
     _ARANGE_CACHE[dev] = t
   return t[:n]
+
+
+_POSITIONS_CACHE = {}
+
+
+def _positions_cached(P, world, dev):
+  """Positions of the pool rows inside a sharded staging layout (one dummy row after every block)."""
+  key = (P, world, dev)
+  t = _POSITIONS_CACHE.get(key)
+  if t is None:
+    per = P // world
+    t = (torch.arange(P, dtype=torch.int64) + torch.arange(P, dtype=torch.int64) // per).to(dev)
+    _POSITIONS_CACHE[key] = t
+  return t
 
 
 _COUNTS_RING = []

@@ -516,11 +516,15 @@ class Recoder(object):
     table_rows = self.num_items if (self._ip is None or self.num_items is None) else \
       self._ip.local_rows(self.num_items)
 
+    # row-parallel runs on a host-resident matrix: every rank stages its own block of the pool, NVLink does the rest
+    shard = (rank, world, self.engine.pg) if (world > 1 and self._ip is None) else None
+
     def launch(index):
       after = (self.engine._side,) if self.engine is not None else ()
-      pool = collate_pool_launch(csr, index, ns, stream=aux, after=after, ring=ring, table_rows=table_rows)
-      tpool = collate_pool_launch(tcsr, index, ns, stream=aux, after=after, ring=tring, table_rows=table_rows) \
-        if tcsr is not None else None
+      pool = collate_pool_launch(csr, index, ns, stream=aux, after=after, ring=ring, table_rows=table_rows,
+                                 stage_shard=shard)
+      tpool = collate_pool_launch(tcsr, index, ns, stream=aux, after=after, ring=tring, table_rows=table_rows,
+                                  stage_shard=shard) if tcsr is not None else None
       return pool, tpool
 
     # One-pool-ahead software pipeline: the collate of pool i+1 is enqueued BEFORE the training steps of pool i, so

@@ -17,7 +17,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 
-def run(kind, loss, mode, pg, batch, steps, matrix, U, I, H, seed_params):
+def run(kind, loss, mode, pg, batch, steps, matrix, U, I, H, seed_params, resident=True):
   from recoder_b200.data import RecommendationDataset
   from recoder_b200.model import Recoder
   from recoder_b200.nn import DynamicAutoencoder, MatrixFactorization
@@ -42,7 +42,7 @@ def run(kind, loss, mode, pg, batch, steps, matrix, U, I, H, seed_params):
     mode, parallel = 'nccl', 'items'
   tr = Recoder(model=model, use_cuda=True, optimizer_type='adam', loss=loss, process_group=pg,
                dp_exchange=mode if mode != 'single' else 'nccl', parallel=parallel)
-  ds = RecommendationDataset(matrix)
+  ds = RecommendationDataset(matrix, device_resident=resident)
   order = np.random.default_rng(5).permutation(U)
   tr.train(ds, lr=1e-2, weight_decay=1e-4, num_epochs=1, iters_per_epoch=steps, batch_size=batch,
            negative_sampling=True, user_order=lambda e: order)
@@ -86,6 +86,9 @@ def main():
     assert p2p[3] and p2p_mc[3], 'peer-memory exchange was not used'
     assert not nccl[3]
     variants = [('nccl', nccl), ('p2p-ipc', p2p), ('p2p-auto', p2p_mc)]
+    # host-resident matrix: every rank stages its own block of the pool, the blocks are all-gathered on the devices
+    staged = run(kind, loss, 'p2p:auto', None, B, steps, matrix, U, I, H, 3, resident=False)
+    variants.append(('p2p-host-staged', staged))
     if kind == 'ae':
       for tag in ('items', 'items-mc', 'items-nccl'):
         got = run(kind, loss, tag, None, B, steps, matrix, U, I, H, 3)
