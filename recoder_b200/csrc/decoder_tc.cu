@@ -26,6 +26,7 @@
 // tcgen05.ld 32x32b (lane = row) -> math -> bf16 -> 128B-swizzled smem box [32 rows x 64 cols] -> TMA store
 // (full 128-byte lines to HBM instead of row-per-thread 16-byte stores), double-buffered per warp.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "gemm_internal.cuh"
 #include "tc_ptx.cuh"
@@ -282,9 +283,221 @@ static __global__ void __launch_bounds__(kDecThreads, 1)
   }
 }
 
+// ---- CTA-pair variant (cta_group::2) ------------------------------------------------------------------------------------
+// Two CTAs on the two SMs of a TPC compute a 256-row x 256-item tile with ONE M=256 MMA per k-step: each CTA stages its
+// own 128 rows of Zb and only HALF of the Wg tile (128 items); the tensor cores read the other half from the partner's
+// shared memory.  Per 128x256x64 MMA a CTA therefore loads 32 KB instead of 48 KB — the single-CTA kernel runs at the
+// L2->SM return bandwidth (2.80 GB per launch for a 0.24 GB operand set, tensor pipe 44 % active: profiles r02e), not at
+// the tensor pipe.  Accumulators stay double-buffered in each CTA's TMEM (its 128 lanes x 2 x 256 columns), so the loss
+// epilogue of tile i still overlaps the MMAs of tile i+1.  Protocol: both producers' TMA loads complete on the LEADER's
+// full barrier (expect_tx = both CTAs' bytes); the leader's MMA lane issues tcgen05.mma.cta_group::2 and releases stages
+// / publishes accumulators with multicast commits that arrive in BOTH CTAs; both CTAs' epilogue warps arrive on the
+// leader's accumulator-empty barrier.  4-stage ring of 32 KB.
+constexpr int kPairStages = 4;
+constexpr int kPairAStage = kTileM * kTileK * 2;            // 16 KB: this CTA's 128 rows
+constexpr int kPairBStage = (kDecTileN / 2) * kTileK * 2;   // 16 KB: this CTA's 128 items
+constexpr int kPairStage = kPairAStage + kPairBStage;
+constexpr int kPairSmem = kPairStages * kPairStage + kDecStaging + kDecBiasBytes + 256 + 1024;
+
+template <int LOSS, bool MAXMODE>
+static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDecThreads, 1)
+    k_decoder_fused_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmG, DecFusedParams p, int m_tiles, int n_tiles, int kblocks,
+                    uint32_t idesc) {
+  if (p.cond != nullptr && __ldg(p.cond) == 0) return;  // uniform over the grid: nobody has touched a barrier yet
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t tiles = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (tiles - raw_addr);
+  const uint32_t staging = tiles + kPairStages * kPairStage;
+  float* bias_s = reinterpret_cast<float*>(smem + kPairStages * kPairStage + kDecStaging);
+  const uint32_t bars = staging + kDecStaging + kDecBiasBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kPairStages + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * kPairStages + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * kPairStages + 2 + a); };
+  uint32_t* tmem_slot =
+      reinterpret_cast<uint32_t*>(smem + kPairStages * kPairStage + kDecStaging + kDecBiasBytes + 8 * (2 * kPairStages + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();   // 0 = leader: owns the operand-ready barriers and issues the MMAs
+  const bool leader = cta_rank == 0;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmG);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kPairStages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), 2 * kDecEpiWarps);   // the epilogue warps of BOTH CTAs release the leader's accumulator
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();   // both CTAs' barriers are initialised and TMEM is allocated before anyone signals across
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int units = m_tiles * n_tiles;           // m_tiles counts 256-row PAIR tiles
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int unit = pair_id; unit < units; unit += num_pairs) {
+        const int mt = unit % m_tiles, nt = unit / m_tiles;  // m fastest: concurrent pairs share the Wg tile in L2
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, 10);
+          // each CTA loads ITS 128 rows of A and ITS half (128 items) of B; all four boxes count on the leader's barrier
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * (uint32_t)kPairStage);
+          const uint32_t lead_bar = mapa_shared(full_bar(stage), 0);
+          const uint32_t a_dst = tiles + stage * kPairStage;
+          tma_load_2d_pair(a_dst, &tmA, lead_bar, kb * kTileK, mt * 2 * kTileM + (int)cta_rank * kTileM);
+          tma_load_2d_pair(a_dst + kPairAStage, &tmB, lead_bar, kb * kTileK,
+                           nt * kDecTileN + (int)cta_rank * (kDecTileN / 2));
+          if (++stage == kPairStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int unit = pair_id; unit < units; unit += num_pairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 11);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kDecTileN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase, 12);
+          tc_fence_after();
+          const uint32_t a_addr = tiles + stage * kPairStage, b_addr = a_addr + kPairAStage;
+#pragma unroll
+          for (int k = 0; k < kTileK / 16; ++k)
+            tc_mma_bf16_pair(tmem_d, make_smem_desc(a_addr + k * 32, 16, 1024),
+                             make_smem_desc(b_addr + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit_pair(empty_bar(stage));   // the slot is free in BOTH CTAs once these MMAs retire
+          if (++stage == kPairStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit_pair(tfull_bar(acc));   // both CTAs' epilogues read their own 128 lanes
+      }
+    }
+  } else {
+    // ---------------- epilogue warps 2..9 ----------------
+    const int e = warp - 2;
+    const int q = warp & 3;   // TMEM lane quarter this warp may read
+    const int half = e >> 2;  // column half of the tile
+    const uint32_t my_staging = staging + (uint32_t)(e * 2 * kDecBoxBytes);
+    const int et = threadIdx.x - 64;  // 0..255
+    const float scale = (LOSS == RCD_LOSS_MSE) ? 2.0f * p.inv_b : p.inv_b;
+    int sbuf = 0;
+    int it = 0;
+    const uint32_t lead_tempty[2] = {mapa_shared(tempty_bar(0), 0), mapa_shared(tempty_bar(1), 0)};
+    for (int unit = pair_id; unit < units; unit += num_pairs, ++it) {
+      const int mt = unit % m_tiles, nt = unit / m_tiles;
+      const int row_base = mt * 2 * kTileM + (int)cta_rank * kTileM;   // this CTA's 128 rows of the pair tile
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int n0 = nt * kDecTileN;
+      {
+        const int c = n0 + et;
+        float b = (c < p.N) ? __ldg(p.bias + c) : 0.f;
+        if (LOSS == RCD_LOSS_NLL) b *= kLog2e;
+        bias_s[acc * kDecTileN + et] = b;
+      }
+      named_bar_sync(1, kDecEpiWarps * 32);
+      const int row = row_base + q * 32 + lane;
+      float m2 = 0.f;
+      if (LOSS == RCD_LOSS_NLL && p.row_ref && row < p.M) m2 = __ldg(p.row_ref + row) * kLog2e;
+      mbar_wait(tfull_bar(acc), acc_phase, 13);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kDecTileN + half * 128);
+      float racc = MAXMODE ? -INFINITY : 0.f;
+#pragma unroll 1
+      for (int box = 0; box < 2; ++box) {
+        const int col0 = n0 + half * 128 + box * 64;
+        if (col0 >= p.N) break;  // warp-uniform
+        const uint32_t sdst = my_staging + (uint32_t)(sbuf * kDecBoxBytes);
+        if (!MAXMODE) {
+          if (lane == 0) tma_store_wait_read<1>();  // the store that last used this buffer has read it
+          __syncwarp();
+        }
+#pragma unroll
+        for (int c32 = 0; c32 < 2; ++c32) {
+          float v[32];
+          tc_ld_32x32(taddr + (uint32_t)(box * 64 + c32 * 32), v);
+          uint32_t packed[16];
+          const float* bs = bias_s + acc * kDecTileN + half * 128 + box * 64 + c32 * 32;
+          const int n_valid = p.N - (col0 + c32 * 32);
+          if (n_valid >= 32) dec_chunk32<LOSS, false, MAXMODE>(v, bs, m2, scale, 32, packed, racc);
+          else dec_chunk32<LOSS, true, MAXMODE>(v, bs, m2, scale, n_valid, packed, racc);
+          if (MAXMODE) continue;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t chunk = (uint32_t)(c32 * 4 + j);
+            const uint32_t addr = sdst + (uint32_t)lane * 128u + ((chunk ^ ((uint32_t)lane & 7u)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[j * 4]),
+                         "r"(packed[j * 4 + 1]), "r"(packed[j * 4 + 2]), "r"(packed[j * 4 + 3])
+                         : "memory");
+          }
+        }
+        if (MAXMODE) continue;
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmG, sdst, col0, row_base + q * 32);
+          tma_store_commit();
+        }
+        sbuf ^= 1;
+      }
+      if (row < p.M) p.stat[(size_t)row * p.stat_ld + nt * 2 + half] = racc;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lead_tempty[acc]);
+    }
+    if (!MAXMODE && lane == 0) tma_store_wait_all<0>();
+  }
+
+  // neither CTA may leave (or free TMEM) while the other still reads its shared memory / signals its barriers
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 }  // namespace rcd
 
 using namespace rcd;
+
+// RCD_GEMM_PAIR=0|1: CTA-pair (cta_group::2) kernels off / on
+static bool decoder_pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RCD_GEMM_PAIR");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 
 RCD_EXPORT int rcd_decoder_stat_cols(int n) { return 2 * rcd_div_up(n > 0 ? n : 1, kDecTileN); }
 
@@ -310,10 +523,57 @@ RCD_EXPORT int rcd_decoder_fwd_loss(const uint16_t* Zb, int ldzb, const uint16_t
   DecFusedParams p{};
   p.M = rows; p.N = n; p.inv_b = inv_b; p.bias = bias; p.row_ref = row_ref; p.stat = stat; p.stat_ld = stat_ld;
   p.cond = cond;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (decoder_pair_enabled() && rows > kTileM) {
+    // CTA pairs: 256-row tiles, each CTA of a pair stages half of the Wg tile
+    CUtensorMap tmBh;
+    rc = encode_map(&tmBh, Wg, H, n, ldw, kTileK, kDecTileN / 2);
+    if (rc != RCD_OK) return rc;
+    const int m_tiles2 = rcd_div_up(rows, 2 * kTileM);
+    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kDecTileN >> 3) << 17) |
+                            ((uint32_t)((2 * kTileM) >> 4) << 24);
+    const int units2 = m_tiles2 * n_tiles;
+    static int max_pairs = 0;
+    static bool pair_attr[4] = {false, false, false, false};
+#define RCD_DEC_PAIR_LAUNCH(L, MAXM, SLOT)                                                                          \
+  do {                                                                                                              \
+    if (!pair_attr[SLOT]) {                                                                                         \
+      RCD_CUDA(cudaFuncSetAttribute(k_decoder_fused_pair<L, MAXM>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                    kPairSmem));                                                                    \
+      pair_attr[SLOT] = true;                                                                                       \
+    }                                                                                                               \
+    if (max_pairs == 0) {                                                                                           \
+      cudaLaunchConfig_t cfg = {};                                                                                  \
+      cfg.gridDim = dim3(rcd_num_sms() & ~1);                                                                       \
+      cfg.blockDim = dim3(kDecThreads);                                                                             \
+      cfg.dynamicSmemBytes = kPairSmem;                                                                             \
+      int nc = 0;                                                                                                   \
+      if (cudaOccupancyMaxActiveClusters(&nc, k_decoder_fused_pair<L, MAXM>, &cfg) != cudaSuccess || nc <= 0)       \
+        nc = (rcd_num_sms() / 2) - 2;                                                                               \
+      max_pairs = nc;                                                                                               \
+    }                                                                                                               \
+    const int pairs = units2 < max_pairs ? units2 : max_pairs;                                                      \
+    k_decoder_fused_pair<L, MAXM><<<2 * pairs, kDecThreads, kPairSmem, st>>>(tmA, tmBh, tmG, p, m_tiles2, n_tiles,  \
+                                                                            kblocks, idesc2);                       \
+  } while (0)
+    switch (loss) {
+      case RCD_LOSS_MSE: RCD_DEC_PAIR_LAUNCH(RCD_LOSS_MSE, false, 0); break;
+      case RCD_LOSS_NLL:
+        if (mode == RCD_DEC_MODE_ROWMAX) RCD_DEC_PAIR_LAUNCH(RCD_LOSS_NLL, true, 3);
+        else RCD_DEC_PAIR_LAUNCH(RCD_LOSS_NLL, false, 1);
+        break;
+      case RCD_LOSS_LOGISTIC: RCD_DEC_PAIR_LAUNCH(RCD_LOSS_LOGISTIC, false, 2); break;
+      default:
+        rcd_set_error("rcd_decoder_fwd_loss: unknown loss id %d", loss);
+        return RCD_ERR_INVALID;
+    }
+#undef RCD_DEC_PAIR_LAUNCH
+    RCD_LAUNCH_CHECK();
+    return RCD_OK;
+  }
   const int units = m_tiles * n_tiles;
   const int sms = rcd_num_sms();
   const int grid = units < sms ? units : sms;
-  cudaStream_t st = (cudaStream_t)stream;
   static bool attr_set[4] = {false, false, false, false};
 #define RCD_DEC_LAUNCH(L, MAXM, SLOT)                                                                             \
   do {                                                                                                            \
