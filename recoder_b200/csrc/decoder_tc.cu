@@ -4,7 +4,7 @@
 //   G[r,c]   = NLL      exp(o - ref[r])          (unnormalised softmax numerator; dL/dO = alpha[r]*G - t/B)
 //              MSE      2*o/B                     (dense, target-free part of dL/dO)
 //              LOGISTIC sigmoid(o)/B
-//   stat[r, 2*n_tile+half] = row partial of       NLL: sum G   MSE: sum o^2   LOGISTIC: sum softplus(o)
+//   stat[r, 4*n_tile+group] = row partial of      NLL: sum G   MSE: sum o^2   LOGISTIC: sum softplus(o)
 //
 // The logits never go to memory: this replaces F.linear (recoder/nn.py:280, :361), the loss modules
 // (recoder/losses.py:43-47, 68-71; BCEWithLogitsLoss, recoder/model.py:91) and the first node of their backward.
@@ -19,12 +19,12 @@
 // is every step of a sane model: F.log_softmax's unconditional stability (recoder/losses.py:69) for a few
 // microseconds of empty launches.
 //
-// One persistent CTA per SM, 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer (tcgen05.mma cta_group::1,
-// M=128, N=256, K=16) + TMEM allocator, warps 2-9 = epilogue.  Tile 128 rows x 256 items, K = H in 64-wide blocks
+// One persistent CTA per SM, 576 threads: warp 0 = TMA producer, warp 1 = MMA issuer (tcgen05.mma cta_group::1,
+// M=128, N=256, K=16) + TMEM allocator, warps 2-17 = epilogue.  Tile 128 rows x 256 items, K = H in 64-wide blocks
 // through a 3-stage smem ring; accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i
-// overlaps the MMAs of tile i+1.  Epilogue warp (q = warp%4 -> TMEM lanes 32q.., half = columns 128*half..):
+// overlaps the MMAs of tile i+1.  Epilogue warp (q = warp%4 -> TMEM lanes 32q.., group = (warp-2)/4 -> columns 64*group..):
 // tcgen05.ld 32x32b (lane = row) -> math -> bf16 -> 128B-swizzled smem box [32 rows x 64 cols] -> TMA store
-// (full 128-byte lines to HBM instead of row-per-thread 16-byte stores), double-buffered per warp.
+// (full 128-byte lines to HBM instead of row-per-thread 16-byte stores).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -34,14 +34,20 @@
 namespace rcd {
 
 constexpr int kDecStages = 3;
-constexpr int kDecEpiWarps = 8;
-constexpr int kDecThreads = 64 + 32 * kDecEpiWarps;  // 320
+// 16 epilogue warps (4 per scheduler): with 8 the kernel was LATENCY-bound in the epilogue — issue slots 26 % busy, tensor
+// pipe 44 % (profiles r02e), and the CTA-pair variant, which loads a third fewer operand bytes, was no faster (r02f)
+constexpr int kDecEpiWarps = 16;
+constexpr int kDecColGroups = kDecEpiWarps / 4;             // column groups of a tile: warp e -> lanes 32*(warp%4), group e/4
+constexpr int kDecThreads = 64 + 32 * kDecEpiWarps;         // 576
 constexpr int kDecTileN = 256;
 constexpr int kDecAStage = kTileM * kTileK * 2;       // 16 KB
 constexpr int kDecBStage = kDecTileN * kTileK * 2;    // 32 KB
 constexpr int kDecStage = kDecAStage + kDecBStage;
 constexpr int kDecBoxBytes = 32 * 64 * 2;             // staging box: 32 rows x 64 bf16 columns
-constexpr int kDecStaging = kDecEpiWarps * 2 * kDecBoxBytes;
+constexpr int kDecColsPerWarp = 256 / kDecColGroups;         // 64
+constexpr int kDecBoxes = kDecColsPerWarp / 64;             // staging boxes per warp and tile
+constexpr int kDecStageBufs = (kDecBoxes > 1) ? 2 : 1;      // one box per tile: its store finished a whole tile ago
+constexpr int kDecStaging = kDecEpiWarps * kDecStageBufs * kDecBoxBytes;
 constexpr int kDecBiasBytes = 2 * kDecTileN * 4;
 constexpr int kDecSmem = kDecStages * kDecStage + kDecStaging + kDecBiasBytes + 256 + 1024;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -205,9 +211,9 @@ static __global__ void __launch_bounds__(kDecThreads, 1)
     // ---------------- epilogue warps 2..9 ----------------
     const int e = warp - 2;
     const int q = warp & 3;   // TMEM lane quarter this warp may read
-    const int half = e >> 2;  // column half of the tile
-    const uint32_t my_staging = staging + (uint32_t)(e * 2 * kDecBoxBytes);
-    const int et = threadIdx.x - 64;  // 0..255
+    const int colg = e >> 2;  // column group of the tile
+    const uint32_t my_staging = staging + (uint32_t)(e * kDecStageBufs * kDecBoxBytes);
+    const int et = threadIdx.x - 64;  // 0..32*kDecEpiWarps-1
     const float scale = (LOSS == RCD_LOSS_MSE) ? 2.0f * p.inv_b : p.inv_b;
     int sbuf = 0;
     int it = 0;
@@ -216,7 +222,7 @@ static __global__ void __launch_bounds__(kDecThreads, 1)
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int n0 = nt * kDecTileN;
-      {
+      if (et < kDecTileN) {
         const int c = n0 + et;
         float b = (c < p.N) ? __ldg(p.bias + c) : 0.f;
         if (LOSS == RCD_LOSS_NLL) b *= kLog2e;
@@ -228,15 +234,15 @@ static __global__ void __launch_bounds__(kDecThreads, 1)
       if (LOSS == RCD_LOSS_NLL && p.row_ref && row < p.M) m2 = __ldg(p.row_ref + row) * kLog2e;
       mbar_wait(tfull_bar(acc), acc_phase, 13);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kDecTileN + half * 128);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kDecTileN + colg * kDecColsPerWarp);
       float racc = MAXMODE ? -INFINITY : 0.f;
 #pragma unroll 1
-      for (int box = 0; box < 2; ++box) {
-        const int col0 = n0 + half * 128 + box * 64;
+      for (int box = 0; box < kDecBoxes; ++box) {
+        const int col0 = n0 + colg * kDecColsPerWarp + box * 64;
         if (col0 >= p.N) break;  // warp-uniform
         const uint32_t sdst = my_staging + (uint32_t)(sbuf * kDecBoxBytes);
         if (!MAXMODE) {
-          if (lane == 0) tma_store_wait_read<1>();  // the store that last used this buffer has read it
+          if (lane == 0) tma_store_wait_read<kDecStageBufs - 1>();  // the store that last used this buffer has read it
           __syncwarp();
         }
 #pragma unroll
@@ -244,7 +250,7 @@ static __global__ void __launch_bounds__(kDecThreads, 1)
           float v[32];
           tc_ld_32x32(taddr + (uint32_t)(box * 64 + c32 * 32), v);
           uint32_t packed[16];
-          const float* bs = bias_s + acc * kDecTileN + half * 128 + box * 64 + c32 * 32;
+          const float* bs = bias_s + acc * kDecTileN + colg * kDecColsPerWarp + box * 64 + c32 * 32;
           const int n_valid = p.N - (col0 + c32 * 32);
           if (n_valid >= 32) dec_chunk32<LOSS, false, MAXMODE>(v, bs, m2, scale, 32, packed, racc);
           else dec_chunk32<LOSS, true, MAXMODE>(v, bs, m2, scale, n_valid, packed, racc);
@@ -265,9 +271,9 @@ static __global__ void __launch_bounds__(kDecThreads, 1)
           tma_store_2d(&tmG, sdst, col0, mt * kTileM + q * 32);
           tma_store_commit();
         }
-        sbuf ^= 1;
+        if (kDecStageBufs > 1) sbuf ^= 1;
       }
-      if (row < p.M) p.stat[(size_t)row * p.stat_ld + nt * 2 + half] = racc;
+      if (row < p.M) p.stat[(size_t)row * p.stat_ld + nt * kDecColGroups + colg] = racc;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -404,9 +410,9 @@ static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDecThreads, 
     // ---------------- epilogue warps 2..9 ----------------
     const int e = warp - 2;
     const int q = warp & 3;   // TMEM lane quarter this warp may read
-    const int half = e >> 2;  // column half of the tile
-    const uint32_t my_staging = staging + (uint32_t)(e * 2 * kDecBoxBytes);
-    const int et = threadIdx.x - 64;  // 0..255
+    const int colg = e >> 2;  // column group of the tile
+    const uint32_t my_staging = staging + (uint32_t)(e * kDecStageBufs * kDecBoxBytes);
+    const int et = threadIdx.x - 64;  // 0..32*kDecEpiWarps-1
     const float scale = (LOSS == RCD_LOSS_MSE) ? 2.0f * p.inv_b : p.inv_b;
     int sbuf = 0;
     int it = 0;
@@ -417,7 +423,7 @@ static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDecThreads, 
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int n0 = nt * kDecTileN;
-      {
+      if (et < kDecTileN) {
         const int c = n0 + et;
         float b = (c < p.N) ? __ldg(p.bias + c) : 0.f;
         if (LOSS == RCD_LOSS_NLL) b *= kLog2e;
@@ -429,15 +435,15 @@ static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDecThreads, 
       if (LOSS == RCD_LOSS_NLL && p.row_ref && row < p.M) m2 = __ldg(p.row_ref + row) * kLog2e;
       mbar_wait(tfull_bar(acc), acc_phase, 13);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kDecTileN + half * 128);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kDecTileN + colg * kDecColsPerWarp);
       float racc = MAXMODE ? -INFINITY : 0.f;
 #pragma unroll 1
-      for (int box = 0; box < 2; ++box) {
-        const int col0 = n0 + half * 128 + box * 64;
+      for (int box = 0; box < kDecBoxes; ++box) {
+        const int col0 = n0 + colg * kDecColsPerWarp + box * 64;
         if (col0 >= p.N) break;  // warp-uniform
         const uint32_t sdst = my_staging + (uint32_t)(sbuf * kDecBoxBytes);
         if (!MAXMODE) {
-          if (lane == 0) tma_store_wait_read<1>();  // the store that last used this buffer has read it
+          if (lane == 0) tma_store_wait_read<kDecStageBufs - 1>();  // the store that last used this buffer has read it
           __syncwarp();
         }
 #pragma unroll
@@ -445,7 +451,7 @@ static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDecThreads, 
           float v[32];
           tc_ld_32x32(taddr + (uint32_t)(box * 64 + c32 * 32), v);
           uint32_t packed[16];
-          const float* bs = bias_s + acc * kDecTileN + half * 128 + box * 64 + c32 * 32;
+          const float* bs = bias_s + acc * kDecTileN + colg * kDecColsPerWarp + box * 64 + c32 * 32;
           const int n_valid = p.N - (col0 + c32 * 32);
           if (n_valid >= 32) dec_chunk32<LOSS, false, MAXMODE>(v, bs, m2, scale, 32, packed, racc);
           else dec_chunk32<LOSS, true, MAXMODE>(v, bs, m2, scale, n_valid, packed, racc);
@@ -466,9 +472,9 @@ static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDecThreads, 
           tma_store_2d(&tmG, sdst, col0, row_base + q * 32);
           tma_store_commit();
         }
-        sbuf ^= 1;
+        if (kDecStageBufs > 1) sbuf ^= 1;
       }
-      if (row < p.M) p.stat[(size_t)row * p.stat_ld + nt * 2 + half] = racc;
+      if (row < p.M) p.stat[(size_t)row * p.stat_ld + nt * kDecColGroups + colg] = racc;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(lead_tempty[acc]);
@@ -499,7 +505,7 @@ static bool decoder_pair_enabled() {
   return v == 1;
 }
 
-RCD_EXPORT int rcd_decoder_stat_cols(int n) { return 2 * rcd_div_up(n > 0 ? n : 1, kDecTileN); }
+RCD_EXPORT int rcd_decoder_stat_cols(int n) { return kDecColGroups * rcd_div_up(n > 0 ? n : 1, kDecTileN); }
 
 RCD_EXPORT int rcd_decoder_fwd_loss(const uint16_t* Zb, int ldzb, const uint16_t* Wg, int ldw, const float* bias,
                                     int rows, int n, int H, int loss, float inv_b, const float* row_ref, uint16_t* G,

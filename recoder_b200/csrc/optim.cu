@@ -207,6 +207,19 @@ struct LazyConsts {
   float beta2, eps, wd, omb1, omb2;
 };
 
+__device__ __forceinline__ void lazy_replay4(float4& pp, float4& mm, float4& vv, int t0, int T,
+                                             const float2* __restrict__ scal, int scal_base, AdamScalars& a) {
+  for (int t = t0 + 1; t <= T; ++t) {
+    const float2 s = __ldg(scal + (t - scal_base));
+    a.step_size = s.x;
+    a.inv_bc2_sqrt = s.y;
+    adam_update(pp.x, mm.x, vv.x, 0.f, a);
+    adam_update(pp.y, mm.y, vv.y, 0.f, a);
+    adam_update(pp.z, mm.z, vv.z, 0.f, a);
+    adam_update(pp.w, mm.w, vv.w, 0.f, a);
+  }
+}
+
 template <int VEC>
 static __global__ void __launch_bounds__(256)
     k_adam_lazy_catchup(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, int H,
@@ -214,33 +227,54 @@ static __global__ void __launch_bounds__(256)
                         const float2* __restrict__ scal, int scal_base, LazyConsts c) {
   const int vpr = H / VEC;
   const long long total = n * vpr;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long k = i / vpr;
-    const long long r = ids ? ids[k] : k;
-    const int t0 = last[r];
-    if (t0 >= T) continue;
-    const int h = (int)(i - k * vpr) * VEC;
-    const size_t off = (size_t)r * H + h;
-    AdamScalars a;
-    a.beta2 = c.beta2; a.eps = c.eps; a.wd = c.wd; a.omb1 = c.omb1; a.omb2 = c.omb2;
-    if (VEC == 4) {
-      float4 pp = *reinterpret_cast<const float4*>(p + off);
-      float4 mm = *reinterpret_cast<const float4*>(m + off);
-      float4 vv = *reinterpret_cast<const float4*>(v + off);
-      for (int t = t0 + 1; t <= T; ++t) {
-        const float2 s = __ldg(scal + (t - scal_base));
-        a.step_size = s.x;
-        a.inv_bc2_sqrt = s.y;
-        adam_update(pp.x, mm.x, vv.x, 0.f, a);
-        adam_update(pp.y, mm.y, vv.y, 0.f, a);
-        adam_update(pp.z, mm.z, vv.z, 0.f, a);
-        adam_update(pp.w, mm.w, vv.w, 0.f, a);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  AdamScalars a;
+  a.beta2 = c.beta2; a.eps = c.eps; a.wd = c.wd; a.omb1 = c.omb1; a.omb2 = c.omb2;
+  if (VEC == 4) {
+    // two items per iteration: the id -> last[] -> p/m/v chain of dependent loads is latency-bound, and only the stale
+    // rows (a fraction of the batch) carry any payload — the second item's loads are in flight while the first replays
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * stride) {
+      const long long i1 = i + stride;
+      const bool has1 = i1 < total;
+      const long long k0 = i / vpr, k1 = has1 ? i1 / vpr : 0;
+      const long long r0 = ids ? ids[k0] : k0;
+      const long long r1 = has1 ? (ids ? ids[k1] : k1) : 0;
+      const int t00 = last[r0];
+      const int t01 = has1 ? last[r1] : T;
+      const bool do0 = t00 < T, do1 = t01 < T;
+      const size_t off0 = (size_t)r0 * H + (size_t)(i - k0 * vpr) * 4;
+      const size_t off1 = (size_t)r1 * H + (size_t)(i1 - k1 * vpr) * 4;
+      float4 p0, m0, v0, p1, m1, v1;
+      if (do0) {
+        p0 = *reinterpret_cast<const float4*>(p + off0);
+        m0 = *reinterpret_cast<const float4*>(m + off0);
+        v0 = *reinterpret_cast<const float4*>(v + off0);
       }
-      *reinterpret_cast<float4*>(p + off) = pp;
-      *reinterpret_cast<float4*>(m + off) = mm;
-      *reinterpret_cast<float4*>(v + off) = vv;
-    } else {
+      if (do1) {
+        p1 = *reinterpret_cast<const float4*>(p + off1);
+        m1 = *reinterpret_cast<const float4*>(m + off1);
+        v1 = *reinterpret_cast<const float4*>(v + off1);
+      }
+      if (do0) {
+        lazy_replay4(p0, m0, v0, t00, T, scal, scal_base, a);
+        *reinterpret_cast<float4*>(p + off0) = p0;
+        *reinterpret_cast<float4*>(m + off0) = m0;
+        *reinterpret_cast<float4*>(v + off0) = v0;
+      }
+      if (do1) {
+        lazy_replay4(p1, m1, v1, t01, T, scal, scal_base, a);
+        *reinterpret_cast<float4*>(p + off1) = p1;
+        *reinterpret_cast<float4*>(m + off1) = m1;
+        *reinterpret_cast<float4*>(v + off1) = v1;
+      }
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+      const long long k = i / vpr;
+      const long long r = ids ? ids[k] : k;
+      const int t0 = last[r];
+      if (t0 >= T) continue;
+      const size_t off = (size_t)r * H + (size_t)(i - k * vpr);
       float pp = p[off], mm = m[off], vv = v[off];
       for (int t = t0 + 1; t <= T; ++t) {
         const float2 s = __ldg(scal + (t - scal_base));
