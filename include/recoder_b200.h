@@ -148,7 +148,7 @@ int rcd_ae_encoder_fwd(const float* We, int H, const float* be, const int32_t* r
  *        MSE      G = 2*o/B                      dL/dO = G + sparse
  *        LOGISTIC G = sigmoid(o)/B               dL/dO = G + sparse
  *        NLL      G = exp(o - row_ref[r])        dL/dO = alpha[r]*G + sparse,  alpha[r] = S_r/(B*sum_c G[r,c])
- *     and per-row partials stat fp32 [rows, stat_ld] (rcd_decoder_stat_cols(n) of them: 4 per 256-column tile): sum G
+ *     and per-row partials stat fp32 [rows, stat_ld] (rcd_decoder_stat_cols(n) of them: 2 per 256-column tile): sum G
  *     (NLL), sum o^2 (MSE),
  *     sum softplus(o) (LOGISTIC).  The SPARSE part at the stored targets (fp32, never quantised to bf16) comes
  *     from rcd_sddmm:  MSE 2*((w-1)*o - w*t)/B with w = 1+conf*[t>0];  NLL / LOGISTIC -t/B.

@@ -11,7 +11,8 @@ from ctypes import c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'librecoder_b200.so')
+# RCD_LIB: an alternative build of the same library (kernel experiments: tools/gpu_*.sh)
+LIB_PATH = os.environ.get('RCD_LIB') or os.path.join(_HERE, 'csrc', 'librecoder_b200.so')
 
 ACT_IDS = {'none': 0, 'tanh': 1, 'sigmoid': 2, 'relu': 3, 'selu': 4, 'celu': 5, 'hardshrink': 6, 'atan': 7, 'sinh': 8,
            'asinh': 9, 'expm1': 10}

@@ -4,7 +4,7 @@
 //   G[r,c]   = NLL      exp(o - ref[r])          (unnormalised softmax numerator; dL/dO = alpha[r]*G - t/B)
 //              MSE      2*o/B                     (dense, target-free part of dL/dO)
 //              LOGISTIC sigmoid(o)/B
-//   stat[r, 4*n_tile+group] = row partial of      NLL: sum G   MSE: sum o^2   LOGISTIC: sum softplus(o)
+//   stat[r, 2*n_tile+group] = row partial of      NLL: sum G   MSE: sum o^2   LOGISTIC: sum softplus(o)
 //
 // The logits never go to memory: this replaces F.linear (recoder/nn.py:280, :361), the loss modules
 // (recoder/losses.py:43-47, 68-71; BCEWithLogitsLoss, recoder/model.py:91) and the first node of their backward.
@@ -19,10 +19,11 @@
 // is every step of a sane model: F.log_softmax's unconditional stability (recoder/losses.py:69) for a few
 // microseconds of empty launches.
 //
-// One persistent CTA per SM, 576 threads: warp 0 = TMA producer, warp 1 = MMA issuer (tcgen05.mma cta_group::1,
-// M=128, N=256, K=16) + TMEM allocator, warps 2-17 = epilogue.  Tile 128 rows x 256 items, K = H in 64-wide blocks
-// through a 3-stage smem ring; accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i
-// overlaps the MMAs of tile i+1.  Epilogue warp (q = warp%4 -> TMEM lanes 32q.., group = (warp-2)/4 -> columns 64*group..):
+// One persistent CTA per SM, 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer (tcgen05.mma cta_group::1,
+// M=128, N=256, K=16) + TMEM allocator, warps 2-9 = epilogue.  Tile 128 rows x 256 items, K = H in 64-wide blocks
+// through a 4-stage smem ring (192 KB of operands in flight: the MMAs wait for operand latency, not for the tensor pipe —
+// 3 stages measured 0.268 ms for the C3 forward, 4 stages 0.231 ms); accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i
+// overlaps the MMAs of tile i+1.  Epilogue warp (q = warp%4 -> TMEM lanes 32q.., group = (warp-2)/4 -> columns 128*group..):
 // tcgen05.ld 32x32b (lane = row) -> math -> bf16 -> 128B-swizzled smem box [32 rows x 64 cols] -> TMA store
 // (full 128-byte lines to HBM instead of row-per-thread 16-byte stores).
 #include <cuda.h>
@@ -31,25 +32,29 @@
 #include "gemm_internal.cuh"
 #include "tc_ptx.cuh"
 
+#ifndef RCD_DEC_STAGES
+#define RCD_DEC_STAGES 4
+#endif
+
 namespace rcd {
 
-constexpr int kDecStages = 3;
-// 16 epilogue warps (4 per scheduler): with 8 the kernel was LATENCY-bound in the epilogue — issue slots 26 % busy, tensor
-// pipe 44 % (profiles r02e), and the CTA-pair variant, which loads a third fewer operand bytes, was no faster (r02f)
-constexpr int kDecEpiWarps = 16;
+constexpr int kDecStages = RCD_DEC_STAGES;   // 3 (double-buffered staging boxes) or 4 (single: +48 KB of operands in flight)
+// 8 epilogue warps.  Measured (profiles/README.md r02g): 16 warps (4 per scheduler, 64 columns each) are SLOWER — fused
+// forward 0.291 ms against 0.268 at C3 — so the epilogue is not what the MMAs wait for; bytes in flight per SM are.
+constexpr int kDecEpiWarps = 8;
 constexpr int kDecColGroups = kDecEpiWarps / 4;             // column groups of a tile: warp e -> lanes 32*(warp%4), group e/4
-constexpr int kDecThreads = 64 + 32 * kDecEpiWarps;         // 576
+constexpr int kDecThreads = 64 + 32 * kDecEpiWarps;         // 320
 constexpr int kDecTileN = 256;
 constexpr int kDecAStage = kTileM * kTileK * 2;       // 16 KB
 constexpr int kDecBStage = kDecTileN * kTileK * 2;    // 32 KB
 constexpr int kDecStage = kDecAStage + kDecBStage;
 constexpr int kDecBoxBytes = 32 * 64 * 2;             // staging box: 32 rows x 64 bf16 columns
-constexpr int kDecColsPerWarp = 256 / kDecColGroups;         // 64
+constexpr int kDecColsPerWarp = 256 / kDecColGroups;         // 128
 constexpr int kDecBoxes = kDecColsPerWarp / 64;             // staging boxes per warp and tile
-constexpr int kDecStageBufs = (kDecBoxes > 1) ? 2 : 1;      // one box per tile: its store finished a whole tile ago
+constexpr int kDecStageBufs = (RCD_DEC_STAGES >= 4) ? 1 : 2;
 constexpr int kDecStaging = kDecEpiWarps * kDecStageBufs * kDecBoxBytes;
 constexpr int kDecBiasBytes = 2 * kDecTileN * 4;
-constexpr int kDecSmem = kDecStages * kDecStage + kDecStaging + kDecBiasBytes + 256 + 1024;
+constexpr int kDecSmem = kDecStages * kDecStage + kDecStaging + kDecBiasBytes + 256;   // aligned below: no slack
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kNllClampLog2 = 64.0f;   // == RCD_NLL_CLAMP_LOG2 (rcd_loss_finish redoes rows with sum >= 2^64)
@@ -118,10 +123,14 @@ static __global__ void __launch_bounds__(kDecThreads, 1)
                     const __grid_constant__ CUtensorMap tmG, DecFusedParams p, int m_tiles, int n_tiles, int kblocks,
                     uint32_t idesc) {
   if (p.cond != nullptr && __ldg(p.cond) == 0) return;  // uniform over the grid: nobody has touched a barrier yet
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t tiles = (raw_addr + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (tiles - raw_addr);
+  extern __shared__ __align__(1024) uint8_t smem_pair_raw[];
+  const uint32_t raw_addr = smem_u32(smem_pair_raw);
+  if ((raw_addr & 1023u) != 0) {   // 128B-swizzle atoms need 1024 B alignment; the budget has no room for slack
+    if (threadIdx.x == 0) printf("recoder_b200: dynamic shared memory is not 1024-byte aligned (0x%x)\n", raw_addr);
+    __trap();
+  }
+  const uint32_t tiles = raw_addr;
+  uint8_t* smem = smem_pair_raw;
   const uint32_t staging = tiles + kDecStages * kDecStage;
   float* bias_s = reinterpret_cast<float*>(smem + kDecStages * kDecStage + kDecStaging);
   const uint32_t bars = staging + kDecStaging + kDecBiasBytes;
@@ -298,12 +307,14 @@ static __global__ void __launch_bounds__(kDecThreads, 1)
 // epilogue of tile i still overlaps the MMAs of tile i+1.  Protocol: both producers' TMA loads complete on the LEADER's
 // full barrier (expect_tx = both CTAs' bytes); the leader's MMA lane issues tcgen05.mma.cta_group::2 and releases stages
 // / publishes accumulators with multicast commits that arrive in BOTH CTAs; both CTAs' epilogue warps arrive on the
-// leader's accumulator-empty barrier.  4-stage ring of 32 KB.
-constexpr int kPairStages = 4;
+// leader's accumulator-empty barrier.  5-stage ring of 32 KB: 160 KB in flight per SM for two thirds of the bytes per MMA
+// (single-CTA kernel: 144 KB) — the fused forward is bound by operand bytes in flight, not by the tensor pipe or the
+// epilogue (r02f / r02g).
+constexpr int kPairStages = (RCD_DEC_STAGES >= 4) ? 6 : 5;
 constexpr int kPairAStage = kTileM * kTileK * 2;            // 16 KB: this CTA's 128 rows
 constexpr int kPairBStage = (kDecTileN / 2) * kTileK * 2;   // 16 KB: this CTA's 128 items
 constexpr int kPairStage = kPairAStage + kPairBStage;
-constexpr int kPairSmem = kPairStages * kPairStage + kDecStaging + kDecBiasBytes + 256 + 1024;
+constexpr int kPairSmem = kPairStages * kPairStage + kDecStaging + kDecBiasBytes + 256;  // no slack: aligned below
 
 template <int LOSS, bool MAXMODE>
 static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDecThreads, 1)
@@ -311,10 +322,14 @@ static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDecThreads, 
                     const __grid_constant__ CUtensorMap tmG, DecFusedParams p, int m_tiles, int n_tiles, int kblocks,
                     uint32_t idesc) {
   if (p.cond != nullptr && __ldg(p.cond) == 0) return;  // uniform over the grid: nobody has touched a barrier yet
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t tiles = (raw_addr + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (tiles - raw_addr);
+  extern __shared__ __align__(1024) uint8_t smem_pair_raw[];
+  const uint32_t raw_addr = smem_u32(smem_pair_raw);
+  if ((raw_addr & 1023u) != 0) {   // 128B-swizzle atoms need 1024 B alignment; the budget has no room for slack
+    if (threadIdx.x == 0) printf("recoder_b200: dynamic shared memory is not 1024-byte aligned (0x%x)\n", raw_addr);
+    __trap();
+  }
+  const uint32_t tiles = raw_addr;
+  uint8_t* smem = smem_pair_raw;
   const uint32_t staging = tiles + kPairStages * kPairStage;
   float* bias_s = reinterpret_cast<float*>(smem + kPairStages * kPairStage + kDecStaging);
   const uint32_t bars = staging + kDecStaging + kDecBiasBytes;
