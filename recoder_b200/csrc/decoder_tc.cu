@@ -510,12 +510,13 @@ static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDecThreads, 
 
 using namespace rcd;
 
-// RCD_GEMM_PAIR=0|1: CTA-pair (cta_group::2) kernels off / on
+// CTA-pair (cta_group::2) variant of the fused kernel for slices of more than 128 rows; RCD_GEMM_PAIR=0 switches it off.
+// Measured (profiles/README.md r02k): C3 forward 0.225 ms against 0.232 ms single-CTA, C5 / 8192 users 4.28 against 4.57 ms.
 static bool decoder_pair_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("RCD_GEMM_PAIR");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
 }

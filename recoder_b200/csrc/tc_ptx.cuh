@@ -101,8 +101,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// (default .release.cta semantics: a .release.cluster arrive compiles to MEMBAR.ALL.CTA + ERRBAR, which drained every
+// outstanding store of the epilogue warp once per tile — 32 % of the pair kernel's warp samples in r02j.  What the
+// arrive orders here are tcgen05.ld reads, covered by tcgen05.fence::before_thread_sync.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load of this CTA's share of a pair's operand tile; the bytes are counted on the LEADER CTA's mbarrier
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
