@@ -268,12 +268,17 @@ int rcd_sgd_step(float* p, float* buf, long long rows, int H, const float* grad_
  *                           rows 0..n-1, i.e. a flush of the table) from the per-step scalars scal float[2*scal_len]
  *                           = {lr_t/(1-beta1^t), 1/sqrt(1-beta2^t)} of steps scal_base .. scal_base+scal_len-1
  *                           (rcd_adam_scalars); mark != 0: then sets last[r] = T.  Call it before anything reads the rows.
+ *                           n_dev (optional): device int32 holding the row count (n is then an upper bound: the
+ *                           collate of the NEXT pool has not been read back when its rows are caught up ahead of
+ *                           time); exclude_pos (optional): rows r with exclude_pos[r] >= 0 are skipped — the rows of
+ *                           the batch in flight, whose step is still being applied.
  *   rcd_adam_lazy_update  : step t on rows ids[i] (current at t-1) with gradient row grad_rows[i,:]; last[ids[i]] = t.
  *   rcd_adam_scalars      : HOST helper filling out_host[2*count] for steps t_first .. t_first+count-1 exactly as
  *                           rcd_adam_step forms its scalars (double arithmetic, rounded to float). */
 int rcd_adam_lazy_catchup(float* p, float* m, float* v, int H, const int64_t* ids, long long n, int32_t* last,
                           long long T, const float* scal, long long scal_base, long long scal_len, double beta1,
-                          double beta2, double eps, double weight_decay, int mark, void* stream);
+                          double beta2, double eps, double weight_decay, int mark, const int32_t* n_dev,
+                          const int32_t* exclude_pos, void* stream);
 int rcd_adam_lazy_update(float* p, float* m, float* v, int H, const int64_t* ids, long long n, const float* grad_rows,
                          int ldg, int32_t* last, double lr, double beta1, double beta2, double eps, double weight_decay,
                          long long t, void* stream);
@@ -404,7 +409,7 @@ int rcd_gemm_bf16(int mode, const uint16_t* A, int lda, const uint16_t* B, int l
  *     rcd_step_profile(ctx, mode): 0 off, 1 CUDA events around every entry point, 2 around the entry point named
  *     `name` only; rcd_step_profile_read sums the event pairs per entry point (synchronises) and clears them.
  * ------------------------------------------------------------------------------------------------------- */
-#define RCD_STEP_ABI 3
+#define RCD_STEP_ABI 4
 #define RCD_MODEL_AE 0
 #define RCD_MODEL_MF 1
 #define RCD_OPT_ADAM 0
@@ -475,6 +480,16 @@ typedef struct rcd_step_args {
   int32_t* user_pos;     /* MF: int32 [num_users], all -1 between steps */
   const float* scal;     /* deferred dense Adam: per-step scalars (rcd_adam_lazy_catchup), steps scal_base .. +scal_len-1 */
   long long scal_base, scal_len;
+  /* deferred Adam, optional: the rows of the NEXT pool that are not in this batch are caught up ahead of time on the side
+   * stream (underneath the dgrad GEMM and the encoder backward) instead of at the start of the next step.  items: the next
+   * pool's sorted item ids (device), n: its item count ON THE DEVICE (not read back yet), cap: an upper bound of it.  The
+   * caller has made the side stream wait for the next pool's collate. */
+  const int64_t* next_items_in;
+  const int32_t* next_n_in;
+  long long next_cap_in;
+  const int64_t* next_items_out;
+  const int32_t* next_n_out;
+  long long next_cap_out;
   void* stream_main;
   void* stream_side;
   void* stream_aux;

@@ -64,7 +64,7 @@ _SIGNATURES = {
                             c_double, c_longlong, _P]),
   'rcd_sgd_step': (c_int, [_P, _P, c_longlong, c_int, _P, c_int, _P, c_double, c_double, c_double, _P]),
   'rcd_adam_lazy_catchup': (c_int, [_P, _P, _P, c_int, _P, c_longlong, _P, c_longlong, _P, c_longlong, c_longlong,
-                                    c_double, c_double, c_double, c_double, c_int, _P]),
+                                    c_double, c_double, c_double, c_double, c_int, _P, _P, _P]),
   'rcd_adam_lazy_update': (c_int, [_P, _P, _P, c_int, _P, c_longlong, _P, c_int, _P, c_double, c_double, c_double,
                                    c_double, c_double, c_longlong, _P]),
   'rcd_adam_scalars': (c_int, [c_double, c_double, c_double, c_longlong, c_int, _P]),
@@ -125,12 +125,13 @@ class RcdStepArgs(ctypes.Structure):
               ('rows', c_int), ('cap_rows', c_int), ('cap_n', c_int), ('cap_n_in', c_int), ('cap_nnz', c_longlong),
               ('cap_tnnz', c_longlong), ('ws', _P), ('ws_bytes', c_size_t), ('loss_acc', _P), ('bad_flag', _P),
               ('redo_flag', _P), ('user_pos', _P), ('scal', _P), ('scal_base', c_longlong), ('scal_len', c_longlong),
-              ('stream_main', _P), ('stream_side', _P), ('stream_aux', _P),
+              ('next_items_in', _P), ('next_n_in', _P), ('next_cap_in', c_longlong), ('next_items_out', _P),
+              ('next_n_out', _P), ('next_cap_out', c_longlong), ('stream_main', _P), ('stream_side', _P), ('stream_aux', _P),
               ('ip', RcdStepIp), ('out_dW_in', c_longlong), ('out_db_in', c_longlong), ('out_dW_out', c_longlong),
               ('out_db_out', c_longlong)]
 
 
-STEP_ABI = 3
+STEP_ABI = 4
 MODEL_IDS = {'ae': 0, 'mf': 1}
 OPT_IDS = {'adam': 0, 'sgd': 1, 'adagrad': 2, 'rmsprop': 3}
 

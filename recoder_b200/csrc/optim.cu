@@ -224,8 +224,13 @@ template <int VEC>
 static __global__ void __launch_bounds__(256)
     k_adam_lazy_catchup(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, int H,
                         const int64_t* __restrict__ ids, long long n, const int32_t* __restrict__ last, int T,
-                        const float2* __restrict__ scal, int scal_base, LazyConsts c) {
+                        const float2* __restrict__ scal, int scal_base, LazyConsts c, const int32_t* __restrict__ n_dev,
+                        const int32_t* __restrict__ exclude) {
   const int vpr = H / VEC;
+  if (n_dev) {  // row count known on the device only (the collate of the NEXT pool has not been read back yet)
+    const long long nd = (long long)__ldg(n_dev);
+    n = nd < n ? nd : n;
+  }
   const long long total = n * vpr;
   const long long stride = (long long)gridDim.x * blockDim.x;
   AdamScalars a;
@@ -239,8 +244,8 @@ static __global__ void __launch_bounds__(256)
       const long long k0 = i / vpr, k1 = has1 ? i1 / vpr : 0;
       const long long r0 = ids ? ids[k0] : k0;
       const long long r1 = has1 ? (ids ? ids[k1] : k1) : 0;
-      const int t00 = last[r0];
-      const int t01 = has1 ? last[r1] : T;
+      const int t00 = (exclude && exclude[r0] >= 0) ? T : last[r0];
+      const int t01 = (has1 && !(exclude && exclude[r1] >= 0)) ? last[r1] : T;
       const bool do0 = t00 < T, do1 = t01 < T;
       const size_t off0 = (size_t)r0 * H + (size_t)(i - k0 * vpr) * 4;
       const size_t off1 = (size_t)r1 * H + (size_t)(i1 - k1 * vpr) * 4;
@@ -272,6 +277,7 @@ static __global__ void __launch_bounds__(256)
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
       const long long k = i / vpr;
       const long long r = ids ? ids[k] : k;
+      if (exclude && exclude[r] >= 0) continue;
       const int t0 = last[r];
       if (t0 >= T) continue;
       const size_t off = (size_t)r * H + (size_t)(i - k * vpr);
@@ -289,9 +295,17 @@ static __global__ void __launch_bounds__(256)
   }
 }
 
-static __global__ void k_adam_lazy_mark(const int64_t* __restrict__ ids, long long n, int32_t* __restrict__ last, int T) {
+static __global__ void k_adam_lazy_mark(const int64_t* __restrict__ ids, long long n, int32_t* __restrict__ last, int T,
+                                        const int32_t* __restrict__ n_dev, const int32_t* __restrict__ exclude) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) last[ids ? ids[i] : i] = T;
+  if (n_dev) {
+    const long long nd = (long long)__ldg(n_dev);
+    n = nd < n ? nd : n;
+  }
+  if (i >= n) return;
+  const long long r = ids ? ids[i] : i;
+  if (exclude && exclude[r] >= 0) return;
+  last[r] = T;
 }
 
 template <int VEC>
@@ -457,7 +471,7 @@ RCD_EXPORT int rcd_adam_step(float* p, float* m, float* v, long long rows, int H
 RCD_EXPORT int rcd_adam_lazy_catchup(float* p, float* m, float* v, int H, const int64_t* ids, long long n,
                                      int32_t* last, long long T, const float* scal, long long scal_base,
                                      long long scal_len, double beta1, double beta2, double eps, double weight_decay,
-                                     int mark, void* stream) {
+                                     int mark, const int32_t* n_dev, const int32_t* exclude_pos, void* stream) {
   RCD_CHECK_ARG(p && m && v && last && scal && H > 0 && n >= 0, "bad arguments");
   RCD_CHECK_ARG(T >= 0 && scal_base >= 0 && T - scal_base < scal_len, "step outside the scalar table");
   if (n == 0) return RCD_OK;
@@ -468,12 +482,14 @@ RCD_EXPORT int rcd_adam_lazy_catchup(float* p, float* m, float* v, int H, const 
   const bool vec = (H % 4 == 0) && aligned16(p) && aligned16(m) && aligned16(v);
   const float2* sc = reinterpret_cast<const float2*>(scal);
   if (vec)
-    k_adam_lazy_catchup<4><<<stream_grid(n * (H / 4)), 256, 0, st>>>(p, m, v, H, ids, n, last, (int)T, sc, (int)scal_base, c);
+    k_adam_lazy_catchup<4><<<stream_grid(n * (H / 4)), 256, 0, st>>>(p, m, v, H, ids, n, last, (int)T, sc, (int)scal_base, c,
+                                                                     n_dev, exclude_pos);
   else
-    k_adam_lazy_catchup<1><<<stream_grid(n * H), 256, 0, st>>>(p, m, v, H, ids, n, last, (int)T, sc, (int)scal_base, c);
+    k_adam_lazy_catchup<1><<<stream_grid(n * H), 256, 0, st>>>(p, m, v, H, ids, n, last, (int)T, sc, (int)scal_base, c, n_dev,
+                                                               exclude_pos);
   RCD_LAUNCH_CHECK();
   if (mark) {
-    k_adam_lazy_mark<<<rcd_div_up(n, 256), 256, 0, st>>>(ids, n, last, (int)T);
+    k_adam_lazy_mark<<<rcd_div_up(n, 256), 256, 0, st>>>(ids, n, last, (int)T, n_dev, exclude_pos);
     RCD_LAUNCH_CHECK();
   }
   return RCD_OK;

@@ -189,7 +189,7 @@ static int catch_up(StepCtx* c, const rcd_step_args& a, const rcd_param& p, cons
   RCD_CHECK_ARG(a.scal, "deferred Adam needs the scalar table");
   STEP_CALL("rcd_adam_lazy_catchup", st,
             rcd_adam_lazy_catchup(p.p, p.s1, p.s2, p.cols, ids, n, p.last, p.t - 1, a.scal, a.scal_base, a.scal_len, 0.9,
-                                  0.999, 1e-8, p.weight_decay, 1, st));
+                                  0.999, 1e-8, p.weight_decay, 1, nullptr, nullptr, st));
   return RCD_OK;
 }
 
@@ -561,6 +561,20 @@ RCD_EXPORT int rcd_step_run(void* ctx, rcd_step_args* args) {
     if (rc != RCD_OK) return rc;
     rc = opt_step(c, a, a.bias_out, db_out, 1, a.tgt.pos, (void*)ss);
     if (rc != RCD_OK) return rc;
+  }
+  // deferred Adam: rows of the NEXT pool that are not in this batch are replayed up to THIS step now, on the side
+  // stream, underneath the dgrad GEMM / encoder backward (they are disjoint from the rows this step updates)
+  if (a.next_items_out && a.table_out.last && a.scal) {
+    STEP_CALL("rcd_adam_lazy_catchup", (void*)ss,
+              rcd_adam_lazy_catchup(a.table_out.p, a.table_out.s1, a.table_out.s2, a.table_out.cols, a.next_items_out,
+                                    a.next_cap_out, a.table_out.last, a.table_out.t, a.scal, a.scal_base, a.scal_len, 0.9,
+                                    0.999, 1e-8, a.table_out.weight_decay, 1, a.next_n_out, a.tgt.pos, (void*)ss));
+  }
+  if (ae && a.next_items_in && a.table_in.last && a.scal) {
+    STEP_CALL("rcd_adam_lazy_catchup", (void*)ss,
+              rcd_adam_lazy_catchup(a.table_in.p, a.table_in.s1, a.table_in.s2, a.table_in.cols, a.next_items_in,
+                                    a.next_cap_in, a.table_in.last, a.table_in.t, a.scal, a.scal_base, a.scal_len, 0.9,
+                                    0.999, 1e-8, a.table_in.weight_decay, 1, a.next_n_in, a.in.pos, (void*)ss));
   }
   if (ss != sm) {
     RCD_CUDA(cudaEventRecord(c->ev_out, ss));

@@ -343,6 +343,8 @@ class PoolBatch:
     self.max_user = -1
     self.row_ptr_host = None
     self._pending = None
+    self.next_hint = None          # (next PoolBatch, next target PoolBatch) while that pool is being collated
+    self.last_slice_row0 = -1
 
   @property
   def items(self):

@@ -208,7 +208,7 @@ class Optimizer:
     _, H = st.view2d()
     call('rcd_adam_lazy_catchup', ptr(st.p), ptr(st.m), ptr(st.v), H, ptr(ids), int(n), ptr(st.last), st.step,
          ptr(self._scal), self._scal_base, self._scal_cap, ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS,
-         float(st.weight_decay), 1)
+         float(st.weight_decay), 1, None, None)
 
   def flush(self):
     """Brings every row of every lazy table up to date (before evaluation, checkpoints, or anything else that reads
@@ -218,7 +218,7 @@ class Optimizer:
         rows, H = st.view2d()
         call('rcd_adam_lazy_catchup', ptr(st.p), ptr(st.m), ptr(st.v), H, None, int(rows), ptr(st.last), st.step,
              ptr(self._scal), self._scal_base, self._scal_cap, ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS,
-             float(st.weight_decay), 1)
+             float(st.weight_decay), 1, None, None)
 
   def _ensure(self, st):
     if st.m is None:
@@ -519,6 +519,27 @@ class NativeStep:
       a.stream_aux = e._aux.cuda_stream
       e._keep_for_side(pool, None if same else tpool)
     a.stream_main = _native.stream_ptr()
+    # deferred Adam: catch the next pool's rows up ahead of time (last slice of this pool only; see rcd_step_args)
+    a.next_items_in = a.next_items_out = None
+    nxt = getattr(pool, 'next_hint', None)
+    if (train and e.overlap and nxt is not None and row0 == getattr(pool, 'last_slice_row0', -1)
+        and os.environ.get('RCD_LAZY_PREFETCH', '1') != '0'):
+      npool, ntpool = nxt
+      ntpool = ntpool or npool
+      lazy_in = e.kind == 'ae' and opt.states[n_in_name].lazy
+      lazy_out = opt.states[n_out_name].lazy
+      if (lazy_in or lazy_out) and npool.negative_sampling and npool._pending is not None:
+        e._side.wait_event(npool._pending[1])         # the next pool's collate (trainer's auxiliary stream)
+        if ntpool is not npool and ntpool._pending is not None:
+          e._side.wait_event(ntpool._pending[1])
+        if lazy_out:
+          a.next_items_out = ntpool.items_buf.data_ptr()
+          a.next_n_out = ntpool.counts.data_ptr()
+          a.next_cap_out = ntpool.items_buf.numel()
+        if lazy_in:
+          a.next_items_in = npool.items_buf.data_ptr()
+          a.next_n_in = npool.counts.data_ptr()
+          a.next_cap_in = npool.items_buf.numel()
     if e.ip is not None:
       xb = e._ip_buffers(rows, a.H)
       sh = xb['shared']

@@ -547,11 +547,16 @@ class Recoder(object):
       ht['wait'] += t1 - t0                      # blocked on the GPU (counts of the collated pool)
       ht['launch'] += _time.perf_counter() - t1  # host time to enqueue the next pool's collate
       if self._ip is not None:   # every rank takes all rows of the global slice; the item axis is what is split
-        for goff in range(0, pool.num_rows, gstep):
-          grows = min(gstep, pool.num_rows - goff)
-          yield pool, None, goff, grows, grows
-        continue
-      for row0, rows, global_rows in shard_rows(pool.num_rows, gstep, world, rank):
+        slices = [(goff, min(gstep, pool.num_rows - goff), min(gstep, pool.num_rows - goff))
+                  for goff in range(0, pool.num_rows, gstep)]
+        tpool = None
+      else:
+        slices = list(shard_rows(pool.num_rows, gstep, world, rank))
+      if slices:
+        # the engine may bring the NEXT pool's table rows up to date underneath the last step of this pool
+        pool.next_hint = nxt
+        pool.last_slice_row0 = slices[-1][0]
+      for row0, rows, global_rows in slices:
         yield pool, tpool, row0, rows, global_rows
 
   def _train(self, train_dataloader, val_dataloader,

@@ -64,7 +64,7 @@ def test_lazy_kernels_replay_the_dense_kernel_bit_for_bit(wd, H):
     _native.check(lib.rcd_adam_scalars(lr, ADAM_BETAS[0], ADAM_BETAS[1], t, 1, scal_host[t:t + 1].data_ptr()), 'scalars')
     scal[t].copy_(scal_host[t])
     call('rcd_adam_lazy_catchup', ptr(lazy[0]), ptr(lazy[1]), ptr(lazy[2]), H, ptr(ids), n, ptr(last), t - 1, ptr(scal),
-         0, cap, ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS, wd, 1)
+         0, cap, ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS, wd, 1, None, None)
     assert bool((last[ids] == t - 1).all())
     call('rcd_adam_lazy_update', ptr(lazy[0]), ptr(lazy[1]), ptr(lazy[2]), H, ptr(ids), n, ptr(grad), H, ptr(last), lr,
          ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS, wd, t)
@@ -76,7 +76,7 @@ def test_lazy_kernels_replay_the_dense_kernel_bit_for_bit(wd, H):
   stale = int((last < steps).sum())
   assert stale > I // 4, 'the test must leave a good share of rows deferred'
   call('rcd_adam_lazy_catchup', ptr(lazy[0]), ptr(lazy[1]), ptr(lazy[2]), H, None, I, ptr(last), steps, ptr(scal), 0, cap,
-       ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS, wd, 1)
+       ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS, wd, 1, None, None)
   torch.cuda.synchronize()
   assert bool((last == steps).all())
   for name, a, b in zip(('p', 'exp_avg', 'exp_avg_sq'), dense, lazy):
