@@ -141,14 +141,14 @@ class Optimizer:
   SCAL_CHUNK = 4096       # per-step scalars are computed on the host this many steps ahead
   FLUSH_EVERY = 16384     # every table is brought up to date at least this often (bounds the scalar table)
 
-  def enable_lazy(self, names):
+  def enable_lazy(self, names, allow_shared=False):
     """Defers the dense-Adam update of rows outside the batch for the given embedding tables (bit-identical results;
     HBM traffic per step proportional to the batch's rows instead of the whole table)."""
     if self.type != 'adam':
       return
     for n in names:
       st = self.states[n]
-      if st.sparse or st.shared is not None or st.p.dim() != 2:
+      if st.sparse or (st.shared is not None and not allow_shared) or st.p.dim() != 2:
         continue
       self._ensure(st)
       st.lazy = True
@@ -273,7 +273,7 @@ class Optimizer:
     """Completes the row-sharded Adam state (m, v) of peer-memory tables on every rank (before a checkpoint)."""
     import torch.distributed as dist
     for st in self.states.values():
-      if st.shared is None or st.m is None:
+      if st.shared is None or st.m is None or st.lazy:   # (deferred tables keep complete state on every replica)
         continue
       rows, _ = st.view2d()
       per = (rows + ctx.world - 1) // ctx.world
@@ -519,11 +519,14 @@ class NativeStep:
       a.stream_aux = e._aux.cuda_stream
       e._keep_for_side(pool, None if same else tpool)
     a.stream_main = _native.stream_ptr()
-    # deferred Adam: catch the next pool's rows up ahead of time (last slice of this pool only; see rcd_step_args)
+    # deferred Adam, opt-in (RCD_LAZY_PREFETCH=1): catch the next pool's rows up ahead of time on the side stream (last
+    # slice of this pool only; see rcd_step_args).  Measured a LOSS (profiles/README.md r02m: C3 2.15 -> 2.28 ms, C5/512
+    # 2.67 -> 2.84 ms): the SIMT catch-up CTAs share the SMs' issue slots with the single MMA / TMA threads of the
+    # tensor-core kernels they overlap, which slows those down by more than the catch-up saves at the start of a step.
     a.next_items_in = a.next_items_out = None
     nxt = getattr(pool, 'next_hint', None)
     if (train and e.overlap and nxt is not None and row0 == getattr(pool, 'last_slice_row0', -1)
-        and os.environ.get('RCD_LAZY_PREFETCH', '1') != '0'):
+        and os.environ.get('RCD_LAZY_PREFETCH', '0') == '1'):
       npool, ntpool = nxt
       ntpool = ntpool or npool
       lazy_in = e.kind == 'ae' and opt.states[n_in_name].lazy
@@ -635,14 +638,26 @@ class TrainEngine:
     traffic per parameter: dense 24 B over all T rows + 4 B over the n gradient rows; deferred 28 B over the n batch rows
     + 24 B over the batch rows that were not in the previous batch (about n * (1 - n/T) of them)."""
     self._lazy_decided = True
-    if not self.lazy_adam or self.opt.type != 'adam' or self.tied or self.p2p is not None:
+    if not self.lazy_adam or self.opt.type != 'adam' or self.tied:
       return
-    if self.pg is not None and self.ip is None:
+    if self.p2p is not None:
+      # the fused peer-memory exchange updates row SHARDS densely and pushes them to every replica — except for the MF
+      # user table, whose gradient rows belong to the B_global users of the step: deferred, every replica applies the
+      # same B_global row updates itself and the table (1M x 256 at C4) never crosses NVLink
+      if self.kind == 'mf':
+        name = self.params['user_w'][0]
+        T = self.opt.states[name].p.shape[0]
+        n = rows * self._world()[0]
+        if self.lazy_adam is True or (28.0 * n + 24.0 * n) / (24.0 * T + 4.0 * n) < self.LAZY_GAIN:
+          self.opt.enable_lazy([name], allow_shared=True)
       return
+    # row-parallel runs with the NCCL exchange qualify: every rank applies the same catch-ups and the same row updates
+    # from the same all-reduced gradients, so the replicas stay bit-identical
+    world = self._world()[0] if self.ip is None else 1
     if self.kind == 'ae':
       cand = [(self.params['en_w'][0], pool.n), (self.params['de_w'][0], tpool.n)]
     else:
-      cand = [(self.params['user_w'][0], rows), (self.params['item_w'][0], tpool.n)]
+      cand = [(self.params['user_w'][0], rows * world), (self.params['item_w'][0], tpool.n)]
     names = []
     for name, n in cand:
       T = self.opt.states[name].p.shape[0]
@@ -1486,8 +1501,9 @@ class TrainEngine:
     slab = self._slab(o_u + all_rows * D + 4, V.shape[0] * D + _round_up(V.shape[0], 4) + all_rows * D + 4)
     dV, dbias = slab[0:o_b], slab[o_b:o_b + n]
     dU_all = slab[o_u:o_u + all_rows * D]
-    if world > 1 and self.p2p is None:
-      dU_all.zero_()
+    lazy_users = self.opt.states[u_name].lazy
+    if world > 1 and (self.p2p is None or lazy_users):
+      dU_all.zero_()       # the other ranks' blocks: the exchange sums the slabs, which then is a gather
     dU = dU_all[rank * rows * D:(rank + 1) * rows * D]
 
     Vg = b.get('Wg', n * ldd, torch.bfloat16)
@@ -1499,7 +1515,8 @@ class TrainEngine:
     Ue = b.get('Z', rows * D, torch.float32)
     Ub = b.get('Zb', rows * ldd, torch.bfloat16)
     self._wait_ready('user')
-    self.opt.catch_up(u_name, users, rows)
+    # (data parallel: the user rows of ALL ranks' blocks are updated on every replica, so all of them are caught up)
+    self.opt.catch_up(u_name, pool.users[row0 - rank * rows:row0 - rank * rows + all_rows], all_rows)
     call('rcd_gather_rows', ptr(U), D, ptr(users), rows, self.act, ptr(Ub), ldd, ptr(Ue))
     drop = train and self.dropout_prob > 0.0
     Y = Ue
@@ -1555,9 +1572,16 @@ class TrainEngine:
       with self._update_stream():
         self.p2p.barrier(self.bad_flag)            # dU / loss complete everywhere; V pushes have landed
         self._mark_ready('item')
-        call('rcd_scatter_pos', ptr(all_users), all_rows, ptr(upos), 0)
-        self.opt.step_param_p2p(u_name, self.p2p, self._slab_shared.ptr_table(4 * o_u), D, upos, grad_block_rows=rows)
-        call('rcd_scatter_pos', ptr(all_users), all_rows, ptr(upos), 1)
+        if lazy_users:
+          # deferred user table: gather the B_global gradient rows (block q is non-zero in rank q's slab only, so the
+          # rank-ordered sum IS the gather) and update those rows on this replica; nothing else of the table moves
+          dU_g = self._p2p_reduce('dU_gathered', o_u, all_rows * D)
+          self.opt.step_param(u_name, dU_g, D, ids=all_users, n_ids=all_rows)
+        else:
+          call('rcd_scatter_pos', ptr(all_users), all_rows, ptr(upos), 0)
+          self.opt.step_param_p2p(u_name, self.p2p, self._slab_shared.ptr_table(4 * o_u), D, upos,
+                                  grad_block_rows=rows)
+          call('rcd_scatter_pos', ptr(all_users), all_rows, ptr(upos), 1)
         lsum = self._p2p_reduce('tail_en', slab.numel() - 2, 2)
         loss_slot.copy_(lsum[0:1].to(torch.float64) + lsum[1:2].to(torch.float64))
         self.p2p.barrier(self.bad_flag)            # user-row pushes have landed; the slabs may be overwritten

@@ -17,7 +17,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 
-def run(kind, loss, mode, pg, batch, steps, matrix, U, I, H, seed_params, resident=True):
+def run(kind, loss, mode, pg, batch, steps, matrix, U, I, H, seed_params, resident=True, lazy='auto'):
   from recoder_b200.data import RecommendationDataset
   from recoder_b200.model import Recoder
   from recoder_b200.nn import DynamicAutoencoder, MatrixFactorization
@@ -41,7 +41,7 @@ def run(kind, loss, mode, pg, batch, steps, matrix, U, I, H, seed_params, reside
       os.environ['RCD_P2P_MULTICAST'] = '1'
     mode, parallel = 'nccl', 'items'
   tr = Recoder(model=model, use_cuda=True, optimizer_type='adam', loss=loss, process_group=pg,
-               dp_exchange=mode if mode != 'single' else 'nccl', parallel=parallel)
+               dp_exchange=mode if mode != 'single' else 'nccl', parallel=parallel, lazy_adam=lazy)
   ds = RecommendationDataset(matrix, device_resident=resident)
   order = np.random.default_rng(5).permutation(U)
   tr.train(ds, lr=1e-2, weight_decay=1e-4, num_epochs=1, iters_per_epoch=steps, batch_size=batch,
@@ -89,6 +89,10 @@ def main():
     # host-resident matrix: every rank stages its own block of the pool, the blocks are all-gathered on the devices
     staged = run(kind, loss, 'p2p:auto', None, B, steps, matrix, U, I, H, 3, resident=False)
     variants.append(('p2p-host-staged', staged))
+    # NCCL exchange with the deferred dense Adam forced on: every replica replays / updates the same rows
+    lazy = run(kind, loss, 'nccl', None, B, steps, matrix, U, I, H, 3, lazy=True)
+    assert not lazy[3]
+    variants.append(('nccl-deferred-adam', lazy))
     if kind == 'ae':
       for tag in ('items', 'items-mc', 'items-nccl'):
         got = run(kind, loss, tag, None, B, steps, matrix, U, I, H, 3)
