@@ -212,7 +212,13 @@ class Optimizer:
 
   def flush(self):
     """Brings every row of every lazy table up to date (before evaluation, checkpoints, or anything else that reads
-    whole tables)."""
+    whole tables).  Ordered after the updates still running on the engine's other streams (`_join`, set by the
+    engine): a flush that overtakes the last row update would replay rows whose step is still in flight."""
+    if not any(st.lazy for st in self.states.values()):
+      return
+    join = getattr(self, '_join', None)
+    if join is not None:
+      join()
     for st in self.states.values():
       if st.lazy and st.step > 0:
         rows, H = st.view2d()
@@ -627,6 +633,7 @@ class TrainEngine:
     self.bad_flag = torch.zeros(1, dtype=torch.int32, device=dev)   # set by rcd_loss_finish on non-finite rows
     self.redo_flag = torch.zeros(1, dtype=torch.int32, device=dev)  # NLL rows to redo with their true maximum
     self._loss_host = None
+    self.opt._join = self.join     # Optimizer.flush orders itself after the update / side streams
     self._native = None            # NativeStep, created on first use
     self.native_enabled = os.environ.get('RCD_NATIVE_STEP', '1') != '0'
     self._used_python_path = False
@@ -1502,8 +1509,8 @@ class TrainEngine:
     dV, dbias = slab[0:o_b], slab[o_b:o_b + n]
     dU_all = slab[o_u:o_u + all_rows * D]
     lazy_users = self.opt.states[u_name].lazy
-    if world > 1 and (self.p2p is None or lazy_users):
-      dU_all.zero_()       # the other ranks' blocks: the exchange sums the slabs, which then is a gather
+    if world > 1 and self.p2p is None:
+      dU_all.zero_()       # the other ranks' blocks: the all-reduce of the slab then is a gather
     dU = dU_all[rank * rows * D:(rank + 1) * rows * D]
 
     Vg = b.get('Wg', n * ldd, torch.bfloat16)
@@ -1517,6 +1524,11 @@ class TrainEngine:
     self._wait_ready('user')
     # (data parallel: the user rows of ALL ranks' blocks are updated on every replica, so all of them are caught up)
     self.opt.catch_up(u_name, pool.users[row0 - rank * rows:row0 - rank * rows + all_rows], all_rows)
+    if world > 1 and self.p2p is not None and lazy_users:
+      # peer-memory exchange with the deferred user table: the peers SUM the slabs' user blocks (a gather, since block q
+      # is non-zero in rank q's slab only).  Zeroed here, after the waits above: the peers have finished reading the
+      # previous step's slab (barrier at the end of its exchange)
+      dU_all.zero_()
     call('rcd_gather_rows', ptr(U), D, ptr(users), rows, self.act, ptr(Ub), ldd, ptr(Ue))
     drop = train and self.dropout_prob > 0.0
     Y = Ue

@@ -113,7 +113,6 @@ def _train(kind, U, I, nnz, H, B, loss, neg, native, lazy, steps=50):
     eng.train_step(collate_pool(ds.device_csr(), users, neg), 0, B)
   deferred = {n: int((st.last < st.step).sum()) for n, st in eng.opt.states.items() if st.lazy}
   eng.opt.flush()
-  eng.join()
   torch.cuda.synchronize()
   state = {n: p.detach().clone() for n, p in model.named_parameters()}
   ostate = {n: (st.m.clone(), st.v.clone()) for n, st in eng.opt.states.items()}
