@@ -128,6 +128,8 @@ class Optimizer:
       raise Exception('Unknown optimizer kind')                       # model.py:156
     self.type = optimizer_type
     self.lr = lr            # dense optimizer lr (MultiStepLR acts on it, model.py:327-332)
+    self.base_lr = lr       # MultiStepLR's `initial_lr`: the schedule's base, restored from a checkpoint on resume
+    self.resumed = False    # True once a state dict has been loaded: its lr / initial_lr win over train(lr=...)
     self.sparse_lr = lr     # SparseAdam lr never decays (reference quirk)
     self.states = {}
     for name, p in named_params:
@@ -308,6 +310,8 @@ class Optimizer:
         else:
           state[i] = {'momentum_buffer': s.m.detach().cpu().clone()}
       g = {'params': [i], 'lr': self.lr if dense else self.sparse_lr, 'weight_decay': s.weight_decay}
+      if dense:
+        g['initial_lr'] = self.base_lr    # what torch's MultiStepLR adds to every group it schedules
       if self.type == 'adam':
         g.update({'betas': ADAM_BETAS, 'eps': ADAM_EPS})
       elif self.type == 'adagrad':
@@ -344,7 +348,11 @@ class Optimizer:
       lr = sd['param_groups'][0].get('lr')
       if lr is not None:
         if dense:
+          # torch's optimizer.load_state_dict restores the groups' lr (and MultiStepLR's initial_lr): on resume the
+          # reference trains on with the CHECKPOINT's rates, whatever lr is passed to train() (model.py:158-164, 327-332)
           self.lr = lr
+          self.base_lr = sd['param_groups'][0].get('initial_lr', lr)
+          self.resumed = True
         else:
           self.sparse_lr = lr
 
@@ -621,7 +629,18 @@ class TrainEngine:
     self.dec_layers = params.get('dec_layers', [])   # 'w' is None for tied layers (weight = enc layer^T)
     self.noise_prob = float(params.get('noise_prob', 0.0))
     self.dropout_prob = float(params.get('dropout_prob', 0.0))
-    self.rng_seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+    # Philox key of the dropout / noise masks: drawn from torch's global generator when the engine is built (like
+    # RandomSampler seeds itself, data.py), so successive train() calls and different models get fresh mask streams
+    # while torch.manual_seed() still makes a run reproducible; data-parallel ranks share rank 0's key (the masks are
+    # indexed by GLOBAL element, so all ranks must agree)
+    seed = int(torch.empty((), dtype=torch.int64).random_().item()) & 0x7FFFFFFFFFFFFFFF
+    if process_group is not None:
+      import torch.distributed as dist
+      if dist.get_world_size(process_group) > 1:
+        t = torch.tensor([seed], dtype=torch.int64, device=dev if dist.get_backend(process_group) == 'nccl' else 'cpu')
+        dist.broadcast(t, src=dist.get_global_rank(process_group, 0), group=process_group)
+        seed = int(t.item())
+    self.rng_seed = seed
     self.debug_noise_keep = None     # tests: explicit uint8 keep masks instead of Philox
     self.debug_dropout_keep = None
     self.buf = _Buffers(dev)
@@ -1177,6 +1196,10 @@ class TrainEngine:
     if self._slab_shared is None or self._slab_shared.nbytes < 4 * numel:
       # collective: every rank sees the same shapes, so every rank (re)allocates at the same step
       torch.cuda.synchronize()
+      if self._slab_shared is not None:
+        import torch.distributed as dist
+        dist.barrier(group=self.p2p.pg)      # no peer is still reading the outgrown slab
+        self._slab_shared.close()
       self._slab_shared = self.p2p.shared(4 * max(numel, capacity))
     return self._slab_shared.view(torch.float32, numel)
 
@@ -1344,6 +1367,10 @@ class TrainEngine:
     need = 4 * (nz + nz + 4 + 2 * r4) + 64
     if self._ip_shared is None or self._ip_shared.nbytes < need:
       torch.cuda.synchronize()          # collective: every rank sees the same shapes at the same step
+      if self._ip_shared is not None:
+        import torch.distributed as dist
+        dist.barrier(group=ctx.pg)
+        self._ip_shared.close()
       self._ip_shared = ctx.shared(need)
     sh = self._ip_shared
     o_z, o_dz = 0, 4 * nz

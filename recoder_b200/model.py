@@ -183,8 +183,9 @@ class Recoder(object):
       self.__optimizer_state_dict = self.__shard_optimizer_state(self.__optimizer_state_dict)
 
     if self.__optimizer_state_dict is not None:
+      # like torch's load_state_dict in the reference (model.py:158-160): the checkpoint's lr / initial_lr replace the
+      # lr argument — continuing or resuming a run trains on with the rates it was saved with
       self.optimizer.load_state_dict(self.__optimizer_state_dict, dense=True)
-      self.optimizer.lr = lr
       self.__optimizer_state_dict = None
     if self.__sparse_optimizer_state_dict is not None:
       self.optimizer.load_state_dict(self.__sparse_optimizer_state_dict, dense=False)
@@ -465,7 +466,8 @@ class Recoder(object):
     else:
       val_dataloader = None
 
-    self._base_lr = lr
+    self._base_lr = self.optimizer.base_lr if self.optimizer.resumed else lr
+    self.optimizer.base_lr = self._base_lr
     self._lr_milestones = sorted(lr_milestones) if lr_milestones is not None else None
     self._step_callback = step_callback
     self._sync_loss_every_step = bool(sync_loss_every_step)
@@ -488,7 +490,8 @@ class Recoder(object):
     """MultiStepLR(gamma=0.1) stepped at every epoch start (reference model.py:327-332, 364-366):
     during epoch e the dense optimizer runs at lr * 0.1 ** #{milestones <= e}."""
     if self._lr_milestones is None:
-      return self._base_lr
+      # no scheduler: the optimizer's own rate (the checkpoint's after a resume)
+      return self.optimizer.lr if self.optimizer is not None else self._base_lr
     k = sum(1 for m in self._lr_milestones if m <= epoch)
     return self._base_lr * (0.1 ** k)
 

@@ -85,6 +85,32 @@ class SharedBuffer:
     self.local = torch.as_tensor(self._mem, device=torch.device('cuda', torch.cuda.current_device()))
     assert self.local.data_ptr() == self.local_ptr
 
+  def close(self):
+    """Unmaps the peers' allocations and frees the local one (CUDA-IPC backend; the symmetric-memory backend is torn
+    down by torch when the tensor dies).  Call it on every rank after a group barrier: a peer may still be reading."""
+    if getattr(self, '_closed', False):
+      return
+    self._closed = True
+    if self.ctx.backend != 'ipc':
+      self._symm = None
+      return
+    lib = _native.load()
+    for p in getattr(self, '_opened', []):
+      lib.rcd_p2p_close(ctypes.c_void_p(p))
+    self._opened = []
+    self.local = None
+    self._mem = None
+    if getattr(self, 'local_ptr', 0):
+      lib.rcd_p2p_free(ctypes.c_void_p(self.local_ptr))
+      self.local_ptr = 0
+
+  def __del__(self):  # pragma: no cover  (best effort: interpreter shutdown may have unloaded the library)
+    try:
+      if self.ctx.backend == 'ipc':
+        self.close()
+    except Exception:
+      pass
+
   def view(self, dtype, numel, offset_bytes=0):
     """Typed view on the local allocation."""
     nbytes = numel * torch.empty((), dtype=dtype).element_size()
@@ -127,6 +153,20 @@ class P2PContext:
     mc_env = os.environ.get('RCD_P2P_MULTICAST', 'auto')
     self.multicast = (self.world >= 4) if mc_env == 'auto' else (mc_env != '0')
     self.backend = 'ipc'
+    if want in ('auto', 'symm'):
+      # agree on the backend BEFORE the first collective symmetric-memory call: if the module were missing on one rank
+      # only, that rank would skip the rendezvous the others are blocked in
+      try:
+        import torch.distributed._symmetric_memory as _sm  # noqa: F401
+        have = 1 if hasattr(_sm, 'empty') and hasattr(_sm, 'rendezvous') else 0
+      except Exception:  # noqa: BLE001
+        have = 0
+      probe_flag = torch.tensor([have], device=self.device)
+      dist.all_reduce(probe_flag, op=dist.ReduceOp.MIN, group=pg)
+      if not int(probe_flag.item()):
+        if want == 'symm':
+          raise RuntimeError('recoder_b200: torch symmetric memory is not available on every rank')
+        want = 'ipc'
     if want in ('auto', 'symm'):
       ok = 1
       try:

@@ -59,3 +59,25 @@ def test_reference_optimizer_state_round_trips():
   names = [n for n, _ in named]
   for n, g in zip(names, back['param_groups']):
     assert (g['weight_decay'] == 0) == ('bias' in n)
+
+
+def test_resume_keeps_the_checkpoint_learning_rates():
+  """torch's `optimizer.load_state_dict` restores every group's lr and MultiStepLR's `initial_lr` (reference
+  model.py:158-164, 327-332): a resumed or continued run trains on with the rates it was saved with, whatever lr is
+  passed to `train()`.  The fused Optimizer keeps both and writes `initial_lr` into its own state dicts."""
+  import torch
+  from recoder_b200.engine import Optimizer
+  p = torch.zeros(6, 4)
+  opt = Optimizer([('w', p)], 'adam', lr=1e-2, weight_decay=0.0)
+  opt.base_lr, opt.lr = 1e-2, 1e-3          # after one milestone
+  opt._ensure(opt.states['w'])
+  opt.states['w'].step = 7
+  sd = opt.state_dict(dense=True)
+  assert sd['param_groups'][0]['lr'] == 1e-3 and sd['param_groups'][0]['initial_lr'] == 1e-2
+  torch.optim.Adam([torch.nn.Parameter(p.clone())], lr=0.5).load_state_dict(
+    {'state': {0: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in sd['state'][0].items()}},
+     'param_groups': [dict(sd['param_groups'][0])]})   # torch accepts the layout
+  fresh = Optimizer([('w', p.clone())], 'adam', lr=0.5, weight_decay=0.0)
+  assert not fresh.resumed
+  fresh.load_state_dict(sd, dense=True)
+  assert fresh.resumed and fresh.lr == 1e-3 and fresh.base_lr == 1e-2 and fresh.states['w'].step == 7
