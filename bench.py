@@ -660,6 +660,7 @@ def b200_arm(args, w):
     'parity_check': parity,
     'items_per_batch': n_avg,
     'host_ms_per_step': s_dev.get('host'),   # timed region; wait = blocked on the GPU, launch / step = enqueue work
+    'e2e_host_ms_per_step': s_e2e.get('host'), 'e2e_per_rank_ms': s_e2e.get('per_rank'),
     'per_rank_ms': s_dev.get('per_rank'),    # N>1: [device ms/step, host step, host launch, host wait] per rank
     'per_rank_kernels': s_dev.get('per_rank_kernels'),
     'final_loss': s_dev['loss'],

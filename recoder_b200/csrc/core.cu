@@ -3,7 +3,11 @@
 
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
+
+#include <thread>
+#include <vector>
 
 static thread_local char g_err[512] = "";
 unsigned long long g_rcd_launches = 0;
@@ -54,6 +58,7 @@ RCD_EXPORT long long rcd_host_stage_rows(const int64_t* indptr_host, const int32
     rcd_set_error("rcd_host_stage_rows: invalid argument");
     return RCD_ERR_INVALID;
   }
+  // pass 1 (serial, P additions): validate and lay the rows out
   long long at = 0;
   row_ptr_out_host[0] = 0;
   for (int r = 0; r < pool_rows; ++r) {
@@ -62,16 +67,41 @@ RCD_EXPORT long long rcd_host_stage_rows(const int64_t* indptr_host, const int32
       rcd_set_error("rcd_host_stage_rows: user index %lld out of range", (long long)u);
       return RCD_ERR_INVALID;
     }
-    const int64_t s = indptr_host[u], e = indptr_host[u + 1];
-    const long long len = (long long)(e - s);
-    if (at + len > capacity) {
+    at += (long long)(indptr_host[u + 1] - indptr_host[u]);
+    if (at > capacity) {
       rcd_set_error("rcd_host_stage_rows: staging capacity %lld exceeded", capacity);
       return RCD_ERR_INVALID;
     }
-    memcpy(indices_out_host + at, indices_host + s, (size_t)len * sizeof(int32_t));
-    memcpy(data_out_host + at, data_host + s, (size_t)len * sizeof(float));
-    at += len;
     row_ptr_out_host[r + 1] = at;
+  }
+  // pass 2: the copies — one cache-missing row of the matrix per pool row (16 K rows per pool and rank in the 8-GPU
+  // item-parallel mode, where this loop was what the step waited for) — on a few threads (RCD_STAGE_THREADS, default 4)
+  auto copy_range = [&](int r0, int r1) {
+    for (int r = r0; r < r1; ++r) {
+      const int64_t s0 = indptr_host[users_host[r]];
+      const long long o = row_ptr_out_host[r], len = row_ptr_out_host[r + 1] - o;
+      memcpy(indices_out_host + o, indices_host + s0, (size_t)len * sizeof(int32_t));
+      memcpy(data_out_host + o, data_host + s0, (size_t)len * sizeof(float));
+    }
+  };
+  static int n_threads = 0;
+  if (n_threads == 0) {
+    const char* e = getenv("RCD_STAGE_THREADS");
+    const int v = e ? atoi(e) : 4;
+    n_threads = (v >= 1 && v <= 64) ? v : 4;
+  }
+  const int nt = (pool_rows >= 2048 && n_threads > 1) ? n_threads : 1;
+  if (nt == 1) {
+    copy_range(0, pool_rows);
+  } else {
+    std::vector<std::thread> th;
+    const int per = (pool_rows + nt - 1) / nt;
+    for (int t = 1; t < nt; ++t) {
+      const int r0 = t * per, r1 = (t + 1) * per < pool_rows ? (t + 1) * per : pool_rows;
+      if (r0 < r1) th.emplace_back(copy_range, r0, r1);
+    }
+    copy_range(0, per < pool_rows ? per : pool_rows);
+    for (auto& x : th) x.join();
   }
   return at;
 }
