@@ -254,6 +254,8 @@ class ClockSampler:
     self.proc = None
 
   def start(self):
+    if self.gpu is None:
+      return
     try:
       self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits',
                                     '-lms', '100', '-i', str(self.gpu)], stdout=subprocess.PIPE,
@@ -373,6 +375,17 @@ def b200_arm(args, w):
         (args.gpus, world, world))
   torch.cuda.set_device(local_rank)
   if world > 1:
+    # One process per GPU on a shared host: give every rank its own slice of the cores.  Unpinned, six of eight ranks
+    # spent 5 ms per step in the host staging of the e2e leg against 1.3 ms on the other two (profiles/README.md r02t):
+    # their main threads share cores with the other ranks' busy-polling NCCL proxy threads.
+    try:
+      cores = sorted(os.sched_getaffinity(0))
+      per = len(cores) // world
+      if per >= 2 and os.environ.get('RCD_PIN_RANKS', '1') != '0':
+        os.sched_setaffinity(0, cores[local_rank * per:(local_rank + 1) * per])
+        os.environ.setdefault('RCD_STAGE_THREADS', str(max(1, min(4, per - 1))))
+    except (AttributeError, OSError):
+      pass
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
   lib = _native.load()
@@ -420,7 +433,7 @@ def b200_arm(args, w):
     st = {'n': [], 'launch0': 0, 'launch1': 0, 'bytes0': None, 'bytes1': None, 'clocks': None, 'warm': {},
           'dominant': None}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank if rank == 0 else None)   # one nvidia-smi poller per job, not per rank
     if profile:
       _native.PROFILE = 'all'
       _native.TIMINGS.clear()
