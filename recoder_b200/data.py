@@ -59,7 +59,7 @@ class HostStagedCSR:
   staging buffers (K0, `rcd_host_stage_rows`) and sends them H2D; the result is a pool-local DeviceCSR whose
   row r is user `users[r]`."""
 
-  RING = 3   # pool i trains while pool i+1 is staged/collated; one spare so a slot is never rewritten in flight
+  RING = 4   # pool i trains while pools i+1, i+2 are staged / collated; one spare so a slot is never rewritten in flight
 
   def __init__(self, matrix: sparse.csr_matrix, device=None):
     _native.require_cuda()
@@ -352,11 +352,11 @@ class PoolBatch:
 
 
 class PoolRing:
-  """Grow-only device buffers for the collate outputs of successive pools (3 slots: the pool being trained on, the
-  one being collated, one spare).  The training loop collates thousands of pools of nearly equal size: without the
+  """Grow-only device buffers for the collate outputs of successive pools (4 slots: the pool being trained on, the
+  two collated / being collated ahead of it, one spare).  The training loop collates thousands of pools of nearly equal size: without the
   ring every pool costs a dozen allocator round trips on the host, which is what bounds small configurations."""
 
-  SLOTS = 3
+  SLOTS = 4
 
   def __init__(self):
     self._slots = [dict() for _ in range(self.SLOTS)]

@@ -530,23 +530,36 @@ class Recoder(object):
                                   stage_shard=shard) if tcsr is not None else None
       return pool, tpool
 
-    # One-pool-ahead software pipeline: the collate of pool i+1 is enqueued BEFORE the training steps of pool i, so
-    # its (n, nnz) read-back — the only host sync of the data path — is hidden behind those steps and the host can
-    # enqueue step i+1 while step i still runs.
+    # Software pipeline, RCD_POOL_PIPELINE pools deep (default 2): the collates of pools i+1 and i+2 are enqueued BEFORE
+    # the training steps of pool i.  The (n, nnz) read-back of a pool — the only host sync of the data path — then
+    # completes a whole pool before the host asks for it, so the host never waits for the GPU to reach a collate and
+    # can run a step ahead of the device even when enqueueing a pool takes most of a step (8 ranks staging 16 K rows
+    # each from host memory: 1.4 ms of host time per pool against a 2.6 ms step, profiles/README.md r02u).  With one
+    # pool in flight the read-back sat behind the previous step: host wait + enqueue time was the step time.
+    import collections
+    depth = max(1, int(os.environ.get('RCD_POOL_PIPELINE', '2')))
     pools = iter(dataloader.pools())
-    first = next(pools, None)
-    nxt = launch(first) if first is not None else None
+    queue = collections.deque()
+
+    def fill():
+      while len(queue) < depth:
+        index = next(pools, None)
+        if index is None:
+          return
+        queue.append(launch(index))
+
+    fill()
     import time as _time
     ht = self._host_timing = getattr(self, '_host_timing', {'wait': 0.0, 'launch': 0.0, 'step': 0.0, 'n': 0})
-    while nxt is not None:
-      pool, tpool = nxt
+    while queue:
+      pool, tpool = queue.popleft()
       t0 = _time.perf_counter()
       collate_pool_finish(pool)
       if tpool is not None:
         collate_pool_finish(tpool)
       t1 = _time.perf_counter()
-      index = next(pools, None)
-      nxt = launch(index) if index is not None else None
+      fill()
+      nxt = queue[0] if queue else None
       ht['wait'] += t1 - t0                      # blocked on the GPU (counts of the collated pool)
       ht['launch'] += _time.perf_counter() - t1  # host time to enqueue the next pool's collate
       if self._ip is not None:   # every rank takes all rows of the global slice; the item axis is what is split
