@@ -43,6 +43,18 @@ class _NoBar:
   def close(self): pass
 
 
+def steps_per_pass(num_users, global_step_rows, world, rows_sharded):
+  """Optimizer steps one pass over `num_users` users takes: the reference's `len(dataloader)` = ceil(U / batch)
+  (recoder/data.py:166-167; pools are whole multiples of the step, so only the very last slice is ragged).  A
+  row-parallel run gives every rank floor(rows / world) rows of a slice (`engine.shard_rows`): a last slice with fewer
+  users than ranks is no step at all."""
+  steps = -(-int(num_users) // int(global_step_rows))
+  tail = int(num_users) % int(global_step_rows)
+  if rows_sharded and 0 < tail < world:
+    steps -= 1
+  return steps
+
+
 class Recoder(object):
   """
   Module to train/evaluate a recommendation :class:`recoder_b200.nn.FactorizationModel`.
@@ -580,14 +592,17 @@ class Recoder(object):
              batch_size, model_checkpoint_prefix, checkpoint_freq,
              eval_freq, metrics, eval_num_recommendations, iters_per_epoch,
              eval_num_users, eval_batch_size):
-    num_batches = len(train_dataloader)
+    world, rank = self._world()
+    # optimizer steps of one pass over the data: len(dataloader), minus the step row-parallel runs skip when the last
+    # slice has fewer users than there are ranks (engine.shard_rows)
+    num_batches = steps_per_pass(len(train_dataloader.dataset), batch_size * world, world,
+                                 rows_sharded=world > 1 and self._ip is None)
 
     iters_processed = 0
     if iters_per_epoch is None:
       iters_per_epoch = num_batches
     refresh_every = 50
     iterator = None
-    world, rank = self._world()
 
     for epoch in range(current_epoch, num_epochs + 1):
       self.current_epoch = epoch

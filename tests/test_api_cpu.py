@@ -135,3 +135,74 @@ def test_loss_modules_keep_the_reference_constructor():
   assert torch.allclose(MSELoss(confidence=3, reduction='sum')(x, t), want)
   want = -(t * torch.log_softmax(x, dim=1)).sum()
   assert torch.allclose(MultinomialNLLLoss(reduction='sum')(x, t), want)
+
+
+class _StubEngine:
+  pg = None
+
+  def __init__(self):
+    self.steps_done = 0
+    self.seen = []
+
+  def train_step(self, pool, row0, rows, target_pool=None, global_rows=None):
+    self.steps_done += 1
+    self.seen.append(pool)
+
+  def losses(self, k):
+    return torch.arange(self.steps_done - k, self.steps_done, dtype=torch.float64)
+
+  def join(self):
+    pass
+
+
+class _StubOptimizer:
+  lr = 0.0
+  flushes = 0
+
+  def flush(self):
+    self.flushes += 1
+
+
+@pytest.mark.parametrize('iters_per_epoch,epochs,want', [
+  (None, 2, [7, 7]),            # whole passes
+  (3, 5, [3, 3, 1, 3, 3]),      # the pass continues across epochs; its ragged end is a short epoch, then a new pass
+  (10, 2, [7, 7]),              # more than one pass per epoch is capped at a pass
+  (7, 3, [7, 7, 7]),
+])
+def test_epoch_and_pass_bookkeeping_follows_the_reference(iters_per_epoch, epochs, want):
+  """reference model.py:354-383,417-418: `iters_per_epoch` steps per epoch taken from ONE running iterator over the
+  dataloader; a new pass starts only when the previous one was consumed.  Driven with a stub engine, so the host logic
+  of `Recoder._train` runs on the CPU; every pass must see its steps in order, and the deferred optimizer is flushed at
+  every epoch end."""
+  tr = Recoder(model=DynamicAutoencoder(hidden_layers=[4]), use_cuda=False)
+  ds = _dataset(users=7 * 4 - 1, items=30)            # 7 steps of 4 users, the last one ragged
+  loader = RecommendationDataLoader(ds, batch_size=4)
+  tr.engine, tr.optimizer, tr._ip = _StubEngine(), _StubOptimizer(), None
+  tr._base_lr, tr._lr_milestones, tr._step_callback, tr._sync_loss_every_step = 0.01, None, None, False
+  passes = []
+
+  def pool_steps(dataloader, batch_size):
+    passes.append(0)
+    tr._host_timing = {'wait': 0.0, 'launch': 0.0, 'step': 0.0, 'n': 0}
+    for i in range(len(dataloader)):
+      passes[-1] += 1
+      yield type('Pool', (), {'n': 5, 'tag': (len(passes), i)})(), None, 0, 4, 4
+  tr._pool_steps = pool_steps
+  per_epoch = []
+  tr._step_callback = lambda done: per_epoch[-1].append(done)
+  orig = tr._epoch_lr
+
+  def epoch_lr(epoch):
+    per_epoch.append([])
+    return orig(epoch)
+  tr._epoch_lr = epoch_lr
+  tr._train(loader, None, num_epochs=epochs, current_epoch=1, batch_size=4, model_checkpoint_prefix=None,
+            checkpoint_freq=0, eval_freq=0, metrics=None, eval_num_recommendations=None,
+            iters_per_epoch=iters_per_epoch, eval_num_users=None, eval_batch_size=4)
+  assert [len(e) for e in per_epoch] == want
+  assert tr.optimizer.flushes == epochs and tr.current_epoch == epochs
+  tags = [p.tag for p in tr.engine.seen]
+  for k in range(1, len(passes) + 1):                  # every started pass delivers its steps 0, 1, 2, ... in order
+    mine = [i for (pk, i) in tags if pk == k]
+    assert mine == list(range(len(mine))) and (k == len(passes) or len(mine) == 7)
+  assert len(tr.last_epoch_losses) == want[-1]

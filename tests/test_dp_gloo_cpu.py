@@ -126,3 +126,17 @@ def test_shard_matrix_by_items_partitions_the_matrix():
     np.testing.assert_allclose(row_sum, dense.sum(axis=1), rtol=1e-6)
     total += local.nnz
   assert total == m.nnz
+
+
+@pytest.mark.parametrize('U,batch,pool_batches,world', [(1000, 64, 1, 1), (1000, 64, 2, 2), (1027, 128, 2, 8),
+                                                        (1025, 128, 1, 2), (1024, 128, 4, 8), (5, 2, 1, 4), (130, 16, 3, 4)])
+def test_steps_per_pass_counts_what_the_trainer_yields(U, batch, pool_batches, world):
+  """`Recoder._train` bounds its epochs by the number of optimizer steps in one pass over the data: it has to equal what
+  `_pool_steps` yields — pools of num_sampling_users * world users cut by `shard_rows` — also when the last slice has
+  fewer users than there are ranks (the step every rank skips)."""
+  from recoder_b200.model import steps_per_pass
+  g, S = batch * world, batch * pool_batches * world
+  for rank in range(world):
+    yielded = sum(len(list(shard_rows(min(S, U - off), g, world, rank))) for off in range(0, U, S))
+    assert yielded == steps_per_pass(U, g, world, rows_sharded=world > 1)
+  assert steps_per_pass(U, g, world, rows_sharded=False) == int(np.ceil(U / g))     # the reference's len(dataloader)
