@@ -206,3 +206,53 @@ def test_epoch_and_pass_bookkeeping_follows_the_reference(iters_per_epoch, epoch
     mine = [i for (pk, i) in tags if pk == k]
     assert mine == list(range(len(mine))) and (k == len(passes) or len(mine) == 7)
   assert len(tr.last_epoch_losses) == want[-1]
+
+
+@pytest.mark.parametrize('depth', [1, 2, 3])
+def test_pool_pipeline_order_and_slices(monkeypatch, depth):
+  """`Recoder._pool_steps`: the collates of the next RCD_POOL_PIPELINE pools are enqueued before the steps of the
+  current one, a pool is waited for only when its steps are about to be yielded, and every pool is cut into
+  `batch_size` slices in order (reference data.py:138-144).  The collate itself is stubbed: host logic only."""
+  import recoder_b200.model as M
+  events = []
+
+  class FakePool:
+    def __init__(self, index):
+      self.index, self.num_rows, self.n = index, len(index), 3
+
+  def launch(csr, index, ns, **kw):
+    assert kw['stream'] is None and kw['table_rows'] == 30 and kw['stage_shard'] is None
+    events.append(('launch', int(index[0])))
+    return FakePool(index)
+
+  def finish(pool):
+    events.append(('finish', int(pool.index[0])))
+    return pool
+  monkeypatch.setattr(M, 'collate_pool_launch', launch)
+  monkeypatch.setattr(M, 'collate_pool_finish', finish)
+  monkeypatch.setenv('RCD_OVERLAP', '0')
+  monkeypatch.setenv('RCD_POOL_PIPELINE', str(depth))
+  ds = _dataset(users=43, items=30)
+  ds.device_csr = lambda: 'csr'
+  ds.device_target_csr = lambda: None
+  loader = RecommendationDataLoader(ds, batch_size=4, num_sampling_users=12, user_order=lambda e: np.arange(43))
+  tr = Recoder(model=DynamicAutoencoder(hidden_layers=[4]), use_cuda=False)
+  tr.engine, tr._ip, tr.num_items = None, None, 30
+  got = []
+  for pool, tpool, row0, rows, grows in tr._pool_steps(loader, 4):
+    events.append(('step', int(pool.index[0]), row0))
+    got.append((int(pool.index[0]), row0, rows, grows))
+    assert tpool is None
+  # 43 users in pools of 12: pools start at users 0, 12, 24, 36; the last has 7 rows -> slices of 4 and 3
+  assert got == [(p, r, 4, 4) for p in (0, 12, 24) for r in (0, 4, 8)] + [(36, 0, 4, 4), (36, 4, 3, 3)]
+  assert len(got) == len(loader)
+  starts = [0, 12, 24, 36]
+  for k, p in enumerate(starts):
+    first_step = events.index(('step', p, 0))
+    assert events.index(('finish', p)) < first_step
+    for ahead in starts[k + 1:k + 1 + depth]:              # the next `depth` pools are already in flight
+      assert events.index(('launch', ahead)) < first_step
+    for later in starts[k + 1 + depth:]:                   # and nothing beyond them
+      assert events.index(('launch', later)) > first_step
+    if k + 1 < len(starts):                                # a pool is not waited for before its turn
+      assert events.index(('finish', starts[k + 1])) > events.index(('step', p, 8 if k < 3 else 4))
